@@ -1,0 +1,147 @@
+/*
+ * r3dg_b200 — C ABI of the B200-native (sm_100a) relightable-Gaussian rasterizer hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types, an
+ * explicit CUDA stream, caller-allocated memory, no hidden allocation, errors returned as
+ * negative cudaError_t (never thrown).  Every entry point names the reference interface it
+ * replaces; the Python host side (relightable3dgaussian_b200/_C_raster.py) rebuilds the exact
+ * tuples of the reference's pybind module `r3dg_rasterization._C` on top of it.
+ *
+ * All pointers are DEVICE pointers unless stated otherwise; optional inputs are NULL when absent
+ * (the reference signals absence with an empty tensor whose data_ptr is null,
+ * r3dg-rasterization/cuda_rasterizer/forward.cu:206,242).
+ */
+#ifndef R3DG_B200_H_
+#define R3DG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* r3dg_stream_t; /* == cudaStream_t */
+
+#define R3DG_OK 0
+#define R3DG_ERR_BAD_ARG (-10001)
+#define R3DG_ERR_UNSUPPORTED (-10002)
+
+/* ------------------------------------------------------------------------------------------
+ * Work-buffer sizing.  Replaces CudaRasterizer::required<GeometryState/ImageState/BinningState>
+ * (r3dg-rasterization/cuda_rasterizer/rasterizer_impl.h:67-73, rasterizer_impl.cu:155-195).
+ * The three buffers are opaque blobs that round-trip from forward to backward exactly like the
+ * reference's geomBuffer / imgBuffer / binningBuffer (rasterize_points.cu:83-90,136-140).
+ * `capacity` is the number of (tile, Gaussian) instances the binning buffer can hold.
+ * ------------------------------------------------------------------------------------------ */
+size_t r3dg_raster_geom_bytes(int P, int S);
+size_t r3dg_raster_img_bytes(int W, int H);
+size_t r3dg_raster_binning_bytes(long long capacity);
+/* Byte offset of the int32 n_contrib[H,W] plane inside the image buffer: the reference returns
+ * n_contrib as a view of imgBuffer (rasterize_points.cu:136-139) and so does the host glue. */
+size_t r3dg_raster_img_n_contrib_offset(int W, int H);
+
+typedef struct r3dg_raster_fwd_args {
+    int P, S, D, M, W, H;          /* Gaussians, feature channels, SH degree, SH coeffs, image */
+    const float* background;       /* [3] */
+    const float* means3D;          /* [P,3] */
+    const float* shs;              /* [P,M,3] or NULL */
+    const float* colors_precomp;   /* [P,3]  or NULL (exactly one of shs / colors_precomp) */
+    const float* features;         /* [P,S]  or NULL when S == 0 */
+    const float* opacities;        /* [P] */
+    const float* scales;           /* [P,3]  or NULL */
+    const float* rotations;        /* [P,4]  or NULL */
+    const float* cov3D_precomp;    /* [P,6]  or NULL (exactly one of scales+rotations / cov3D) */
+    const float* viewmatrix;       /* [16] world->view, stored transposed (scene/cameras.py:62) */
+    const float* projmatrix;       /* [16] full projection, stored transposed */
+    const float* campos;           /* [3] */
+    float scale_modifier, tan_fovx, tan_fovy, cx, cy;
+    int prefiltered, computer_pseudo_normal, debug;
+    /* outputs (need not be initialised; every element is written) */
+    float* out_color;              /* [3,H,W] */
+    float* out_opacity;            /* [1,H,W] */
+    float* out_depth;              /* [1,H,W] */
+    float* out_feature;            /* [S,H,W] */
+    float* out_normal;             /* [3,H,W] */
+    float* out_surface_xyz;        /* [3,H,W] */
+    float* out_weights;            /* [P] */
+    int* radii;                    /* [P] */
+    int* n_contrib;                /* [H,W] */
+    /* opaque work buffers */
+    void* geom;   size_t geom_bytes;
+    void* img;    size_t img_bytes;
+    void* binning; size_t binning_bytes;
+    /* Pinned HOST int receiving num_rendered via an async copy on `stream` (may be NULL).
+     * num_rendered > capacity means the binning buffer was too small: outputs are invalid and
+     * the call must be repeated with a larger buffer (nothing out of bounds is ever written). */
+    int* num_rendered_host;
+} r3dg_raster_fwd_args;
+
+/* Replaces CudaRasterizer::Rasterizer::forward (rasterizer.h:34-65, rasterizer_impl.cu:199-380)
+ * == `_C.rasterize_gaussians` (rasterize_points.cu:36-141).  Enqueues the whole forward on
+ * `stream` without any host synchronisation. */
+int r3dg_raster_forward(const r3dg_raster_fwd_args* args, r3dg_stream_t stream);
+
+typedef struct r3dg_raster_bwd_args {
+    int P, S, D, M, W, H;
+    const float* background;
+    const float* means3D;
+    const float* shs;
+    const float* colors_precomp;
+    const float* features;
+    const float* scales;
+    const float* rotations;
+    const float* cov3D_precomp;
+    const float* viewmatrix;
+    const float* projmatrix;
+    const float* campos;
+    float scale_modifier, tan_fovx, tan_fovy;
+    int backward_geometry, debug;
+    /* cotangents, contiguous */
+    const float* dL_dout_color;    /* [3,H,W] */
+    const float* dL_dout_opacity;  /* [1,H,W] */
+    const float* dL_dout_depth;    /* [1,H,W] */
+    const float* dL_dout_feature;  /* [S,H,W] */
+    /* gradients out (need not be initialised; every element is written) */
+    float* dL_dmeans2D;            /* [P,3]  (depth gradient in .z) */
+    float* dL_dcolors;             /* [P,3] */
+    float* dL_dopacity;            /* [P] */
+    float* dL_dmeans3D;            /* [P,3] */
+    float* dL_dfeatures;           /* [P,S] */
+    float* dL_dcov3D;              /* [P,6] */
+    float* dL_dsh;                 /* [P,M,3] */
+    float* dL_dscales;             /* [P,3] */
+    float* dL_drotations;          /* [P,4] */
+    /* work buffers written by the matching forward */
+    void* geom;   size_t geom_bytes;
+    void* img;    size_t img_bytes;
+    void* binning; size_t binning_bytes;
+} r3dg_raster_bwd_args;
+
+/* Replaces CudaRasterizer::Rasterizer::backward (rasterizer.h:67-100, rasterizer_impl.cu:384-491)
+ * == `_C.rasterize_gaussians_backward` (rasterize_points.cu:143-235). */
+int r3dg_raster_backward(const r3dg_raster_bwd_args* args, r3dg_stream_t stream);
+
+/* Replaces Rasterizer::markVisible (rasterizer_impl.cu:141-153) == `_C.mark_visible`
+ * (rasterize_points.cu:237-256).  present: uint8/bool [P]. */
+int r3dg_mark_visible(int P, const float* means3D, const float* viewmatrix,
+                      const float* projmatrix, uint8_t* present, r3dg_stream_t stream);
+
+/* Debug / parity introspection of the opaque buffers after a forward (SURVEY.md §8c asks for the
+ * same visibility the reference's obtain() layout gives).  Copies one named intermediate into
+ * `dst` (device pointer) as a dense array in the REFERENCE's element layout.
+ * ids: 0 depths f32[P] | 1 clamped u8[3P] | 3 means2D f32[2P] | 5 conic_opacity f32[4P]
+ *      6 rgb f32[3P] | 7 tiles_touched u32[P] | 8 point_offsets u32[P] | 9 point_list u32[R]
+ *      10 point_list_keys u64[R] | 13 final_T f32[HW] | 15 ranges u32[2T]
+ * Returns bytes written or a negative error. */
+long long r3dg_raster_debug_copy(int id, int P, int S, int W, int H, const void* geom,
+                                 const void* img, const void* binning, size_t binning_bytes,
+                                 void* dst, long long max_bytes, r3dg_stream_t stream);
+
+/* Library identification: returns a static string such as "r3dg_b200 0.1 sm_100a". */
+const char* r3dg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* R3DG_B200_H_ */

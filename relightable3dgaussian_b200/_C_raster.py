@@ -1,0 +1,220 @@
+"""Drop-in replacement for the reference's pybind module `r3dg_rasterization._C`
+(r3dg-rasterization/ext.cpp:15-19): same three function names, positional arguments and return
+tuples as rasterize_points.cu:36-141 / :143-235 / :237-256, implemented on top of the C ABI of
+libr3dg_b200.so (include/r3dg_b200.h) with torch used only for device memory and streams.
+
+Differences that are not observable through the reference's Python wrapper
+(gaussian_renderer/r3dg_rasterization.py):
+  * the three returned byte buffers have our own opaque layout;
+  * outputs are allocated uninitialised (every element is written by the kernels) instead of with
+    torch::full / torch::zeros;
+  * work is enqueued on torch's current stream (the reference uses the legacy default stream);
+  * the binning buffer is sized speculatively from the previous call and the instance count is
+    read back once, after everything has been enqueued — the pipeline itself never synchronises.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_state = {}          # per-device speculative capacity + pinned readback slot
+
+
+def _dev_state(device):
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    st = _state.get(key)
+    if st is None:
+        st = {"capacity": 0, "pinned": torch.zeros(1, dtype=torch.int32).pin_memory()}
+        _state[key] = st
+    return st
+
+
+def _ptr(t):
+    """Device pointer of an optional tensor; empty tensors mean "absent" (NULL), like the
+    reference (forward.cu:206,242)."""
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def _prep(t, name):
+    if t is None or t.numel() == 0:
+        return t
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def rasterize_gaussians(background, means3D, features, colors, opacity, scales, rotations,
+                        scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
+                        cx, cy, image_height, image_width, sh, degree, campos, prefiltered,
+                        computer_pseudo_normal, debug):
+    """== RasterizeGaussiansCUDA (rasterize_points.cu:36-141).  Returns the 13-tuple
+    (rendered, n_contrib, out_color, out_opacity, out_depth, out_feature, out_normal,
+     out_surface_xyz, out_weights, radii, geomBuffer, binningBuffer, imgBuffer)."""
+    lib = _lib.load()
+    if means3D.ndimension() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")   # rasterize_points.cu:62-64
+    P = means3D.size(0)
+    S = features.size(1)
+    H, W = int(image_height), int(image_width)
+    dev = means3D.device
+    means3D = _prep(means3D, "means3D")
+    features = _prep(features, "features"); colors = _prep(colors, "colors")
+    opacity = _prep(opacity, "opacity"); scales = _prep(scales, "scales")
+    rotations = _prep(rotations, "rotations"); cov3D_precomp = _prep(cov3D_precomp, "cov3D_precomp")
+    sh = _prep(sh, "sh"); background = _prep(background, "background")
+    viewmatrix = _prep(viewmatrix, "viewmatrix"); projmatrix = _prep(projmatrix, "projmatrix")
+    campos = _prep(campos, "campos")
+    M = sh.size(1) if sh.numel() != 0 else 0
+
+    f32 = dict(dtype=torch.float32, device=dev)
+    out_color = torch.empty((3, H, W), **f32)
+    out_opacity = torch.empty((1, H, W), **f32)
+    out_depth = torch.empty((1, H, W), **f32)
+    out_feature = torch.empty((S, H, W), **f32)
+    out_normal = torch.empty((3, H, W), **f32)
+    out_surface_xyz = torch.empty((3, H, W), **f32)
+    out_weights = torch.empty((P, 1), **f32)
+    radii = torch.empty((P,), dtype=torch.int32, device=dev)
+    geomBuffer = torch.empty((lib.r3dg_raster_geom_bytes(P, S),), dtype=torch.uint8, device=dev)
+    imgBuffer = torch.empty((lib.r3dg_raster_img_bytes(W, H),), dtype=torch.uint8, device=dev)
+
+    st = _dev_state(dev)
+    capacity = max(st["capacity"], 4 * P + 4096)
+    stream = torch.cuda.current_stream(dev)
+    while True:
+        binningBuffer = torch.empty((lib.r3dg_raster_binning_bytes(capacity),), dtype=torch.uint8,
+                                    device=dev)
+        a = _lib.RasterFwdArgs()
+        a.P, a.S, a.D, a.M, a.W, a.H = P, S, int(degree), M, W, H
+        a.background = _ptr(background); a.means3D = _ptr(means3D); a.shs = _ptr(sh)
+        a.colors_precomp = _ptr(colors); a.features = _ptr(features); a.opacities = _ptr(opacity)
+        a.scales = _ptr(scales); a.rotations = _ptr(rotations); a.cov3D_precomp = _ptr(cov3D_precomp)
+        a.viewmatrix = _ptr(viewmatrix); a.projmatrix = _ptr(projmatrix); a.campos = _ptr(campos)
+        a.scale_modifier = float(scale_modifier); a.tan_fovx = float(tan_fovx)
+        a.tan_fovy = float(tan_fovy); a.cx = float(cx); a.cy = float(cy)
+        a.prefiltered = int(bool(prefiltered)); a.computer_pseudo_normal = int(bool(computer_pseudo_normal))
+        a.debug = int(bool(debug))
+        a.out_color = out_color.data_ptr(); a.out_opacity = out_opacity.data_ptr()
+        a.out_depth = out_depth.data_ptr(); a.out_feature = _ptr(out_feature)
+        a.out_normal = out_normal.data_ptr(); a.out_surface_xyz = out_surface_xyz.data_ptr()
+        a.out_weights = _ptr(out_weights); a.radii = _ptr(radii); a.n_contrib = None
+        a.geom = geomBuffer.data_ptr(); a.geom_bytes = geomBuffer.numel()
+        a.img = imgBuffer.data_ptr(); a.img_bytes = imgBuffer.numel()
+        a.binning = binningBuffer.data_ptr(); a.binning_bytes = binningBuffer.numel()
+        a.num_rendered_host = st["pinned"].data_ptr()
+        _lib.check(lib.r3dg_raster_forward(ctypes.byref(a), stream.cuda_stream), "rasterize_gaussians")
+        stream.synchronize()          # the one readback: num_rendered is part of the return tuple
+        rendered = int(st["pinned"].item())
+        if rendered <= capacity:
+            break
+        capacity = int(rendered * 1.25) + 4096      # speculation missed: rerun with room to spare
+    st["capacity"] = max(int(rendered * 1.25) + 4096, 4 * P + 4096)
+    off = lib.r3dg_raster_img_n_contrib_offset(W, H)
+    n_contrib = imgBuffer[off:off + 4 * H * W].view(torch.int32).view(H, W)   # view, like the reference
+    return (rendered, n_contrib, out_color, out_opacity, out_depth, out_feature, out_normal,
+            out_surface_xyz, out_weights, radii, geomBuffer, binningBuffer, imgBuffer)
+
+
+def rasterize_gaussians_backward(background, means3D, features, radii, colors, scales, rotations,
+                                 scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx,
+                                 tan_fovy, dL_dout_color, dL_dout_opacity, dL_dout_depth,
+                                 dL_dout_feature, sh, degree, campos, geomBuffer, R, binningBuffer,
+                                 imageBuffer, backward_geometry, debug):
+    """== RasterizeGaussiansBackwardCUDA (rasterize_points.cu:143-235).  Returns the 9-tuple
+    (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dfeatures, dL_dcov3D, dL_dsh,
+     dL_dscales, dL_drotations)."""
+    lib = _lib.load()
+    P = means3D.size(0)
+    S = features.size(1)
+    H, W = dL_dout_color.size(1), dL_dout_color.size(2)
+    dev = means3D.device
+    means3D = _prep(means3D, "means3D"); features = _prep(features, "features")
+    colors = _prep(colors, "colors"); scales = _prep(scales, "scales")
+    rotations = _prep(rotations, "rotations"); cov3D_precomp = _prep(cov3D_precomp, "cov3D_precomp")
+    sh = _prep(sh, "sh"); background = _prep(background, "background")
+    viewmatrix = _prep(viewmatrix, "viewmatrix"); projmatrix = _prep(projmatrix, "projmatrix")
+    campos = _prep(campos, "campos")
+    dL_dout_color = _prep(dL_dout_color, "dL_dout_color")
+    dL_dout_opacity = _prep(dL_dout_opacity, "dL_dout_opacity")
+    dL_dout_depth = _prep(dL_dout_depth, "dL_dout_depth")
+    dL_dout_feature = _prep(dL_dout_feature, "dL_dout_feature")
+    M = sh.size(1) if sh.numel() != 0 else 0
+
+    f32 = dict(dtype=torch.float32, device=dev)
+    dL_dmeans3D = torch.empty((P, 3), **f32)
+    dL_dmeans2D = torch.empty((P, 3), **f32)
+    dL_dfeatures = torch.empty((P, S), **f32)
+    dL_dcolors = torch.empty((P, 3), **f32)
+    dL_dopacity = torch.empty((P, 1), **f32)
+    dL_dcov3D = torch.empty((P, 6), **f32)
+    dL_dsh = torch.empty((P, M, 3), **f32)
+    dL_dscales = torch.empty((P, 3), **f32)
+    dL_drotations = torch.empty((P, 4), **f32)
+    if P != 0:
+        a = _lib.RasterBwdArgs()
+        a.P, a.S, a.D, a.M, a.W, a.H = P, S, int(degree), M, W, H
+        a.background = _ptr(background); a.means3D = _ptr(means3D); a.shs = _ptr(sh)
+        a.colors_precomp = _ptr(colors); a.features = _ptr(features); a.scales = _ptr(scales)
+        a.rotations = _ptr(rotations); a.cov3D_precomp = _ptr(cov3D_precomp)
+        a.viewmatrix = _ptr(viewmatrix); a.projmatrix = _ptr(projmatrix); a.campos = _ptr(campos)
+        a.scale_modifier = float(scale_modifier); a.tan_fovx = float(tan_fovx); a.tan_fovy = float(tan_fovy)
+        a.backward_geometry = int(bool(backward_geometry)); a.debug = int(bool(debug))
+        a.dL_dout_color = _ptr(dL_dout_color); a.dL_dout_opacity = _ptr(dL_dout_opacity)
+        a.dL_dout_depth = _ptr(dL_dout_depth); a.dL_dout_feature = _ptr(dL_dout_feature)
+        a.dL_dmeans2D = _ptr(dL_dmeans2D); a.dL_dcolors = _ptr(dL_dcolors)
+        a.dL_dopacity = _ptr(dL_dopacity); a.dL_dmeans3D = _ptr(dL_dmeans3D)
+        a.dL_dfeatures = _ptr(dL_dfeatures); a.dL_dcov3D = _ptr(dL_dcov3D); a.dL_dsh = _ptr(dL_dsh)
+        a.dL_dscales = _ptr(dL_dscales); a.dL_drotations = _ptr(dL_drotations)
+        a.geom = geomBuffer.data_ptr(); a.geom_bytes = geomBuffer.numel()
+        a.img = imageBuffer.data_ptr(); a.img_bytes = imageBuffer.numel()
+        a.binning = binningBuffer.data_ptr(); a.binning_bytes = binningBuffer.numel()
+        stream = torch.cuda.current_stream(dev)
+        _lib.check(lib.r3dg_raster_backward(ctypes.byref(a), stream.cuda_stream),
+                   "rasterize_gaussians_backward")
+    return (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dfeatures, dL_dcov3D, dL_dsh,
+            dL_dscales, dL_drotations)
+
+
+def mark_visible(means3D, viewmatrix, projmatrix):
+    """== markVisible (rasterize_points.cu:237-256): bool[P] = view-space z > 0.2."""
+    lib = _lib.load()
+    P = means3D.size(0)
+    present = torch.zeros((P,), dtype=torch.bool, device=means3D.device)
+    if P != 0:
+        means3D = _prep(means3D, "means3D"); viewmatrix = _prep(viewmatrix, "viewmatrix")
+        projmatrix = _prep(projmatrix, "projmatrix")
+        stream = torch.cuda.current_stream(means3D.device)
+        _lib.check(lib.r3dg_mark_visible(P, means3D.data_ptr(), viewmatrix.data_ptr(),
+                                         projmatrix.data_ptr(), present.data_ptr(),
+                                         stream.cuda_stream), "mark_visible")
+    return present
+
+
+def debug_intermediate(name, P, S, W, H, geomBuffer, imgBuffer, binningBuffer, num_rendered=0):
+    """Parity introspection (r3dg_raster_debug_copy): returns a dense tensor of one named
+    intermediate in the reference's element layout."""
+    lib = _lib.load()
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    spec = {"depths": (0, torch.float32, (P,)), "clamped": (1, torch.uint8, (P, 3)),
+            "means2D": (3, torch.float32, (P, 2)), "conic_opacity": (5, torch.float32, (P, 4)),
+            "rgb": (6, torch.float32, (P, 3)), "tiles_touched": (7, torch.int32, (P,)),
+            "point_offsets": (8, torch.int32, (P,)), "point_list": (9, torch.int32, (num_rendered,)),
+            "point_list_keys": (10, torch.int64, (num_rendered,)),
+            "final_T": (13, torch.float32, (H, W)), "n_contrib": (14, torch.int32, (H, W)),
+            "ranges": (15, torch.int32, (T, 2))}[name]
+    out = torch.empty(spec[2], dtype=spec[1], device=geomBuffer.device)
+    if out.numel() == 0:
+        return out
+    nbytes = out.numel() * out.element_size()
+    stream = torch.cuda.current_stream(geomBuffer.device)
+    rc = lib.r3dg_raster_debug_copy(spec[0], P, S, W, H, geomBuffer.data_ptr(), imgBuffer.data_ptr(),
+                                    binningBuffer.data_ptr(), binningBuffer.numel(), out.data_ptr(),
+                                    nbytes, stream.cuda_stream)
+    if rc < 0:
+        raise RuntimeError(f"debug_intermediate({name}) failed: {rc}")
+    return out

@@ -1,0 +1,175 @@
+// C ABI of libr3dg_b200.so (declared in include/r3dg_b200.h).  Orchestration only: all device
+// work is enqueued on the caller's stream; there is no host synchronisation, no allocation and
+// no global state besides the cached SM count.
+#include <cstdio>
+#include <cstring>
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace r3dg;
+
+namespace {
+int g_num_sms = 0;
+int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            g_num_sms = n;
+        else
+            g_num_sms = 148;   // B200
+    }
+    return g_num_sms;
+}
+int sort_passes(int W, int H) {
+    const int tiles = ((W + R3DG_TILE - 1) / R3DG_TILE) * ((H + R3DG_TILE - 1) / R3DG_TILE);
+    const int bits = 32 + (int)higher_msb((uint32_t)tiles);     // rasterizer_impl.cu:310,318
+    return (bits + 7) / 8;
+}
+}  // namespace
+
+extern "C" {
+
+const char* r3dg_version(void) { return "r3dg_b200 0.1 sm_100a"; }
+
+size_t r3dg_raster_geom_bytes(int P, int S) { return GeomLayout(P < 1 ? 1 : P, S).total; }
+size_t r3dg_raster_img_bytes(int W, int H) { return ImgLayout(W, H).total; }
+size_t r3dg_raster_binning_bytes(long long capacity) { return BinLayout(capacity < 1 ? 1 : capacity).total; }
+size_t r3dg_raster_img_n_contrib_offset(int W, int H) { return ImgLayout(W, H).n_contrib; }
+
+int r3dg_raster_forward(const r3dg_raster_fwd_args* a, r3dg_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!a || a->P < 0 || a->W <= 0 || a->H <= 0 || a->S < 0) return R3DG_ERR_BAD_ARG;
+    if (a->S > R3DG_MAX_S_FWD) return R3DG_ERR_UNSUPPORTED;
+    if (a->P > 0 && ((a->shs == nullptr) == (a->colors_precomp == nullptr))) return R3DG_ERR_BAD_ARG;
+    if (a->P > 0 && (a->cov3D_precomp == nullptr) && (a->scales == nullptr || a->rotations == nullptr)) return R3DG_ERR_BAD_ARG;
+    if (a->shs && a->M > 16) return R3DG_ERR_UNSUPPORTED;
+    const GeomLayout gl(a->P < 1 ? 1 : a->P, a->S);
+    const ImgLayout il(a->W, a->H);
+    if (a->geom_bytes < gl.total || a->img_bytes < il.total) return R3DG_ERR_BAD_ARG;
+    const long long capacity = bin_capacity_for_bytes(a->binning_bytes);
+    if (capacity < 1) return R3DG_ERR_BAD_ARG;
+    const BinLayout bl(capacity);
+    char* geom = (char*)a->geom;
+    char* img = (char*)a->img;
+    char* bin = (char*)a->binning;
+    const int tiles = ((a->W + R3DG_TILE - 1) / R3DG_TILE) * ((a->H + R3DG_TILE - 1) / R3DG_TILE);
+    R3DG_CUDA_TRY(cudaMemsetAsync(geom + gl.header, 0, sizeof(GeomHeader), stream));
+    int rc = 0;
+    const int passes = sort_passes(a->W, a->H);
+    if (a->P > 0) {
+        if ((rc = launch_projection(*a, gl, bl, stream)) != 0) return rc;
+        if ((rc = launch_sort(geom + gl.header, bin, bl, passes, num_sms(), stream)) != 0) return rc;
+    }
+    const bool in_b = (passes & 1) != 0;
+    const uint64_t* keys_sorted = (const uint64_t*)(bin + (in_b ? bl.keys_b : bl.keys_a));
+    const uint32_t* point_list = (const uint32_t*)(bin + (in_b ? bl.vals_b : bl.vals_a));
+    if ((rc = launch_tile_ranges(geom + gl.header, capacity, keys_sorted, img + il.ranges, tiles, num_sms(), stream)) != 0) return rc;
+    if ((rc = launch_composite_forward(*a, gl, il, point_list, stream)) != 0) return rc;
+    if (a->num_rendered_host)
+        R3DG_CUDA_TRY(cudaMemcpyAsync(a->num_rendered_host, geom + gl.header, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    if (a->debug) {   // reference CHECK_CUDA semantics (auxiliary.h:166-173): sync and report
+        cudaError_t e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) return -(int)e;
+    }
+    return 0;
+}
+
+int r3dg_raster_backward(const r3dg_raster_bwd_args* a, r3dg_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!a || a->P < 0 || a->W <= 0 || a->H <= 0 || a->S < 0) return R3DG_ERR_BAD_ARG;
+    if (a->S > R3DG_MAX_S_BWD) return R3DG_ERR_UNSUPPORTED;
+    if (a->P == 0) return 0;
+    const GeomLayout gl(a->P, a->S);
+    const ImgLayout il(a->W, a->H);
+    if (a->geom_bytes < gl.total || a->img_bytes < il.total) return R3DG_ERR_BAD_ARG;
+    const long long capacity = bin_capacity_for_bytes(a->binning_bytes);
+    if (capacity < 1) return R3DG_ERR_BAD_ARG;
+    const BinLayout bl(capacity);
+    char* bin = (char*)a->binning;
+    const bool in_b = (sort_passes(a->W, a->H) & 1) != 0;
+    const uint32_t* point_list = (const uint32_t*)(bin + (in_b ? bl.vals_b : bl.vals_a));
+    int rc = 0;
+    if ((rc = launch_composite_backward(*a, gl, il, point_list, stream)) != 0) return rc;
+    if ((rc = launch_projection_backward(*a, gl, stream)) != 0) return rc;
+    if (a->debug) {
+        cudaError_t e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) return -(int)e;
+    }
+    return 0;
+}
+
+int r3dg_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                      uint8_t* present, r3dg_stream_t stream) {
+    (void)projmatrix;   // the reference's in_frustum computes p_proj but never uses it (auxiliary.h:151-154)
+    return launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+}
+
+namespace {
+__global__ void unpack_rec_kernel(int P, int recf, int what, const float* __restrict__ rec,
+                                  const uint32_t* __restrict__ tiles, float* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const bool vis = tiles[i] > 0;
+    const float* r = rec + (size_t)i * recf;
+    switch (what) {
+        case 0: dst[i] = vis ? r[6] : 0.f; break;                                   // depths
+        case 3: dst[2 * i] = vis ? r[0] : 0.f; dst[2 * i + 1] = vis ? r[1] : 0.f; break;
+        case 5: dst[4 * i] = vis ? r[2] : 0.f; dst[4 * i + 1] = vis ? r[3] : 0.f;
+                dst[4 * i + 2] = vis ? r[4] : 0.f; dst[4 * i + 3] = vis ? r[5] : 0.f; break;
+        case 6: dst[3 * i] = vis ? r[8] : 0.f; dst[3 * i + 1] = vis ? r[9] : 0.f; dst[3 * i + 2] = vis ? r[10] : 0.f; break;
+    }
+}
+__global__ void unpack_clamped_kernel(int P, const uint8_t* __restrict__ cl, const uint32_t* __restrict__ tiles,
+                                      uint8_t* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const unsigned c = tiles[i] > 0 ? cl[i] : 0u;
+    dst[3 * i] = c & 1u; dst[3 * i + 1] = (c >> 1) & 1u; dst[3 * i + 2] = (c >> 2) & 1u;
+}
+}  // namespace
+
+long long r3dg_raster_debug_copy(int id, int P, int S, int W, int H, const void* geom_, const void* img_,
+                                 const void* bin_, size_t binning_bytes, void* dst, long long max_bytes,
+                                 r3dg_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const GeomLayout gl(P < 1 ? 1 : P, S);
+    const ImgLayout il(W, H);
+    const char* geom = (const char*)geom_;
+    const char* img = (const char*)img_;
+    const char* bin = (const char*)bin_;
+    const size_t HW = (size_t)W * H;
+    const int tiles = ((W + R3DG_TILE - 1) / R3DG_TILE) * ((H + R3DG_TILE - 1) / R3DG_TILE);
+    const float* rec = (const float*)(geom + gl.rec);
+    const uint32_t* tt = (const uint32_t*)(geom + gl.tiles_touched);
+    const int nb = (P + 255) / 256;
+    auto copy = [&](const void* src, size_t n) -> long long {
+        if ((long long)n > max_bytes) n = (size_t)max_bytes;
+        if (cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, stream) != cudaSuccess) return -2;
+        return (long long)n;
+    };
+    switch (id) {
+        case 0: if (max_bytes < 4LL * P) return -1; if (P) unpack_rec_kernel<<<nb, 256, 0, stream>>>(P, gl.recf, 0, rec, tt, (float*)dst); return 4LL * P;
+        case 1: if (max_bytes < 3LL * P) return -1; if (P) unpack_clamped_kernel<<<nb, 256, 0, stream>>>(P, (const uint8_t*)(geom + gl.clamped), tt, (uint8_t*)dst); return 3LL * P;
+        case 3: if (max_bytes < 8LL * P) return -1; if (P) unpack_rec_kernel<<<nb, 256, 0, stream>>>(P, gl.recf, 3, rec, tt, (float*)dst); return 8LL * P;
+        case 5: if (max_bytes < 16LL * P) return -1; if (P) unpack_rec_kernel<<<nb, 256, 0, stream>>>(P, gl.recf, 5, rec, tt, (float*)dst); return 16LL * P;
+        case 6: if (max_bytes < 12LL * P) return -1; if (P) unpack_rec_kernel<<<nb, 256, 0, stream>>>(P, gl.recf, 6, rec, tt, (float*)dst); return 12LL * P;
+        case 7: return copy(geom + gl.tiles_touched, 4 * (size_t)P);
+        case 8: return copy(geom + gl.point_offsets, 4 * (size_t)P);
+        case 13: return copy(img + il.final_T, 4 * HW);
+        case 14: return copy(img + il.n_contrib, 4 * HW);
+        case 15: return copy(img + il.ranges, 8 * (size_t)tiles);
+        case 9: case 10: {
+            const long long capacity = bin_capacity_for_bytes(binning_bytes);
+            if (capacity < 1) return -1;
+            const BinLayout bl(capacity);
+            const bool in_b = (sort_passes(W, H) & 1) != 0;
+            // caller limits the copy to R entries through max_bytes
+            if (id == 9) return copy(bin + (in_b ? bl.vals_b : bl.vals_a), (size_t)max_bytes);
+            return copy(bin + (in_b ? bl.keys_b : bl.keys_a), (size_t)max_bytes);
+        }
+    }
+    return -1;
+}
+
+}  // extern "C"

@@ -1,0 +1,150 @@
+// Shared device-side definitions: work-buffer layouts, the packed per-Gaussian record and
+// small helpers.  Nothing here is visible through the C ABI (include/r3dg_b200.h).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define R3DG_TILE 16                 // 16x16 pixel tiles (reference config.h:15-17, fixed by parity)
+#define R3DG_MAX_S_FWD 33            // forward.cu:312  F[33]
+#define R3DG_MAX_S_BWD 24            // backward.cu:449 collected_features[24 * BLOCK_SIZE]
+
+namespace r3dg {
+
+// ---------------------------------------------------------------------------------------------
+// Packed per-Gaussian record written by the projection kernel and gathered by the compositors.
+// One 16-byte-aligned AoS row of RECF = 8 + 4*NG floats per Gaussian:
+//   [0] mean2D.x [1] mean2D.y [2] conic.a [3] conic.b | [4] conic.c [5] opacity [6] depth(view z)
+//   [7] radius (int bits) | [8..] channels = {r,g,b,f0..f(S-1)} zero-padded to 4*NG
+// A compositor instance touches exactly this one row (2 sectors for S=5), instead of the
+// reference's 5 separate arrays (means2D, conic_opacity, depths, colors, features).
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline int num_groups(int S) { return (3 + S + 3) / 4; }
+__host__ __device__ inline int rec_floats(int S) { return 8 + 4 * num_groups(S); }
+
+// Per-Gaussian gradient row accumulated by the backward compositor, same width as the record:
+//   [0] dmean2D.x [1] dmean2D.y [2] dmean2D.z(depth) [3] dopacity | [4] dconic.a [5] dconic.b
+//   [6] dconic.c  [7] unused | [8..] d channels
+// A warp reduces the row across its 32 pixels and adds it with one vector of atomics.
+
+struct GeomHeader {               // first 256 bytes of the geometry buffer
+    uint32_t num_rendered;        // R = total (tile, Gaussian) instances (may exceed capacity)
+    uint32_t scan_ticket;         // dynamic block id for the chained scan
+    uint32_t sort_ticket[8];      // dynamic tile id per radix pass
+    uint32_t depth_or;            // OR / AND of visible depth bit patterns (pass skipping)
+    uint32_t depth_and;
+    uint32_t pad[52];
+};
+static_assert(sizeof(GeomHeader) == 256, "header size");
+
+inline __host__ __device__ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+#define R3DG_SCAN_ITEMS 2048       // items per chained-scan block
+
+struct GeomLayout {
+    size_t header, rec, tiles_touched, point_offsets, clamped, scan_state, grad, total;
+    int P, S, recf;
+    __host__ __device__ GeomLayout(int P_, int S_) : P(P_), S(S_) {
+        recf = rec_floats(S_);
+        size_t off = 0;
+        header = off;        off = align_up(off + sizeof(GeomHeader), 256);
+        rec = off;           off = align_up(off + (size_t)P_ * recf * 4, 256);
+        tiles_touched = off; off = align_up(off + (size_t)P_ * 4, 256);
+        point_offsets = off; off = align_up(off + (size_t)P_ * 4, 256);
+        clamped = off;       off = align_up(off + (size_t)P_, 256);
+        scan_state = off;    off = align_up(off + ((size_t)P_ / R3DG_SCAN_ITEMS + 2) * 4, 256);
+        grad = off;          off = align_up(off + (size_t)P_ * recf * 4, 256);   // backward scratch
+        total = off;
+    }
+};
+
+struct ImgLayout {
+    size_t final_T, n_contrib, ranges, total;
+    __host__ __device__ ImgLayout(int W, int H) {
+        size_t HW = (size_t)W * H;
+        size_t T = (size_t)((W + R3DG_TILE - 1) / R3DG_TILE) * ((H + R3DG_TILE - 1) / R3DG_TILE);
+        size_t off = 0;
+        final_T = off;   off = align_up(off + HW * 4, 256);
+        n_contrib = off; off = align_up(off + HW * 4, 256);
+        ranges = off;    off = align_up(off + T * 8, 256);
+        total = off;
+    }
+};
+
+#define R3DG_SORT_THREADS 256
+#define R3DG_SORT_ITEMS 12
+#define R3DG_SORT_TILE (R3DG_SORT_THREADS * R3DG_SORT_ITEMS)   // 3072 keys per onesweep tile
+#define R3DG_SORT_MAX_PASSES 8
+
+struct BinLayout {
+    size_t keys_a, keys_b, vals_a, vals_b, hist, lookback, total;
+    long long capacity, max_tiles;
+    __host__ __device__ BinLayout(long long cap) : capacity(cap) {
+        max_tiles = (cap + R3DG_SORT_TILE - 1) / R3DG_SORT_TILE + 1;
+        size_t off = 0;
+        keys_a = off; off = align_up(off + (size_t)cap * 8, 256);
+        keys_b = off; off = align_up(off + (size_t)cap * 8, 256);
+        vals_a = off; off = align_up(off + (size_t)cap * 4, 256);
+        vals_b = off; off = align_up(off + (size_t)cap * 4, 256);
+        hist = off;   off = align_up(off + (size_t)R3DG_SORT_MAX_PASSES * 256 * 4, 256);
+        lookback = off;
+        off = align_up(off + (size_t)R3DG_SORT_MAX_PASSES * max_tiles * 256 * 4, 256);
+        total = off;
+    }
+};
+
+// capacity such that BinLayout(capacity).total <= bytes (monotone; solved by a short search)
+inline __host__ long long bin_capacity_for_bytes(size_t bytes) {
+    long long lo = 0, hi = (long long)(bytes / 24) + 1;
+    while (lo < hi) {
+        long long mid = (lo + hi + 1) / 2;
+        if (BinLayout(mid).total <= bytes) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// getHigherMsb (reference rasterizer_impl.cu:35-50): bits needed for tile ids.
+inline __host__ uint32_t higher_msb(uint32_t n) {
+    uint32_t msb = sizeof(n) * 4, step = msb;
+    while (step > 1) {
+        step /= 2;
+        if (n >> msb) msb += step; else msb -= step;
+    }
+    if (n >> msb) msb++;
+    return msb;
+}
+
+// --- exact-association arithmetic (see tools/sass_trace.py / DESIGN.md "bit-exact binning") ----
+// Explicit intrinsics are never re-contracted by nvcc, so the association below is what runs.
+__device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ float mul_(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float div_(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float rcp_(float a) { return __frcp_rn(a); }
+__device__ __forceinline__ float sqrt_(float a) { return __fsqrt_rn(a); }
+// a0*b0 + a1*b1 + a2*b2 with the middle product as the plain multiply (reference SASS pattern)
+__device__ __forceinline__ float dot3_(float a0, float b0, float a1, float b1, float a2, float b2) {
+    return fma_(a2, b2, fma_(a0, b0, mul_(a1, b1)));
+}
+__device__ __forceinline__ float xform_row_(const float* __restrict__ m, int r, float x, float y, float z) {
+    return add_(dot3_(x, m[r], y, m[4 + r], z, m[8 + r]), m[12 + r]);
+}
+
+// getRect (reference auxiliary.h:46-56), /16 compiled to an exact *0.0625f
+__device__ __forceinline__ void get_rect(float px, float py, int radius, int gx, int gy, int& x0,
+                                         int& y0, int& x1, int& y1) {
+    const float r = (float)radius;
+    x0 = min(gx, max(0, (int)mul_(sub_(px, r), 0.0625f)));
+    y0 = min(gy, max(0, (int)mul_(sub_(py, r), 0.0625f)));
+    x1 = min(gx, max(0, (int)mul_(add_(add_(add_(px, r), 16.0f), -1.0f), 0.0625f)));
+    y1 = min(gy, max(0, (int)mul_(add_(add_(add_(py, r), 16.0f), -1.0f), 0.0625f)));
+}
+
+}  // namespace r3dg
+
+#define R3DG_CUDA_TRY(expr)                                  \
+    do {                                                     \
+        cudaError_t _e = (expr);                             \
+        if (_e != cudaSuccess) return -(int)_e;              \
+    } while (0)

@@ -1,0 +1,235 @@
+// Stage 2 backward: per-tile back-to-front re-traversal (reference K10, backward.cu:401-614).
+//
+// B200 design notes
+//  * the reference issues 10+S global atomicAdds per contributing (pixel, Gaussian) pair.  Here a
+//    warp (8x4 pixels) first reduces its 32 per-pixel gradient rows with a transposed butterfly
+//    ("reduce-scatter": ~V shuffles for V values instead of 5V), after which 16/32 lanes each
+//    hold one finished component and add the whole per-Gaussian gradient row with ONE vectorised
+//    atomic instruction into a packed [P][RECF] row (2-4 sectors);
+//  * the traversal starts at the tile's largest n_contrib instead of the end of the tile list —
+//    entries behind every pixel's last contributor are never loaded;
+//  * per-pixel state is register resident (template on channel groups); the reference keeps three
+//    float[24] arrays in local memory and 36 KB of shared memory per CTA;
+//  * gradients differ from the reference only by fp32 summation order (the reference's own
+//    atomics make it run-to-run nondeterministic), tolerance 1e-3 relative.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace r3dg {
+
+struct CompositeBwdParams {
+    int W, H, gx, S, recf, backward_geometry;
+    const uint2* ranges;
+    const uint32_t* point_list;
+    const float* rec;
+    const float* bg;
+    const float* final_T;
+    const int* n_contrib;
+    const float *dL_dpix, *dL_dpix_o, *dL_dpix_d, *dL_dpix_f;
+    float* grad;     // [P][recf], zero-initialised
+};
+
+// Sum v[i] over the 32 lanes for every i in [0,N) (N power of two, 4 <= N <= 32) with a
+// transposed butterfly; on return lane l holds the total of component (l >> (5 - log2 N)).
+template <int N>
+__device__ __forceinline__ float reduce_scatter(float (&v)[N], int lane) {
+    int m = 16;
+#pragma unroll
+    for (int n = N; n > 1; n >>= 1) {
+        const bool upper = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float send = upper ? v[i] : v[i + n / 2];
+            const float keep = upper ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+        }
+        m >>= 1;
+    }
+    float r = v[0];
+#pragma unroll
+    for (int mm = 16 / N; mm > 0; mm >>= 1) r += __shfl_xor_sync(0xffffffffu, r, mm);
+    return r;
+}
+
+template <int NG>
+__global__ void __launch_bounds__(256) composite_bwd_kernel(const CompositeBwdParams p) {
+    constexpr int NC = 4 * NG;              // padded channel count {r,g,b,f...}
+    constexpr int V = 8 + NC;               // gradient row width
+    constexpr int V0 = V <= 16 ? 16 : 32;   // first butterfly chunk
+    constexpr int V1 = V > 32 ? 4 : 0;      // tail chunk (only V == 36)
+    __shared__ float4 sA[256], sB[256];
+    __shared__ float4 sC[NG][256];
+    __shared__ int sId[256];
+    __shared__ int sMax[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int tx = tile % p.gx, ty = tile / p.gx;
+    const int px = tx * R3DG_TILE + (warp & 1) * 8 + (lane & 7);
+    const int py = ty * R3DG_TILE + (warp >> 1) * 4 + (lane >> 3);
+    const bool inside = px < p.W && py < p.H;
+    const float pxf = (float)px, pyf = (float)py;
+    const uint2 range = p.ranges[tile];
+    const size_t HW = (size_t)p.H * p.W, pix = (size_t)p.W * py + px;
+    const float4* __restrict__ rec4 = reinterpret_cast<const float4*>(p.rec);
+    const int rec4n = p.recf >> 2;
+
+    const float T_final = inside ? p.final_T[pix] : 0.0f;
+    float T = T_final;
+    const int last_contributor = inside ? p.n_contrib[pix] : 0;
+    // tile-wide maximum of n_contrib: nothing behind it contributes to any pixel
+    int wmax = last_contributor;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if (lane == 0) sMax[warp] = wmax;
+    __syncthreads();
+    int total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) total = max(total, sMax[w]);
+    total = min(total, (int)(range.y - range.x));
+
+    float dpix[NC], accum[NC], lastc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        accum[c] = 0.0f; lastc[c] = 0.0f;
+        float g = 0.0f;
+        if (inside) {
+            if (c < 3) g = p.dL_dpix[c * HW + pix];
+            else if (c - 3 < p.S) g = p.dL_dpix_f[(size_t)(c - 3) * HW + pix];
+        }
+        dpix[c] = g;
+    }
+    const float dpix_d = inside ? p.dL_dpix_d[pix] : 0.0f;
+    const float dpix_o = inside ? p.dL_dpix_o[pix] : 0.0f;
+    float accum_d = 0.0f, accum_o = 0.0f, last_alpha = 0.0f, last_depth = 0.0f;
+    const float bg_dot = p.bg[0] * dpix[0] + p.bg[1] * dpix[1] + p.bg[2] * dpix[2];
+    const float ddelx_dx = 0.5f * p.W, ddely_dy = 0.5f * p.H;
+    const bool geo = p.backward_geometry != 0;
+
+    for (int base = 0; base < total; base += 256) {
+        __syncthreads();
+        const int n = min(256, total - base);
+        if (tid < n) {
+            const uint32_t id = p.point_list[range.x + (total - 1 - (base + tid))];
+            const float4* r = rec4 + (size_t)id * rec4n;
+            sId[tid] = (int)id;
+            sA[tid] = r[0];
+            sB[tid] = r[1];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) sC[g][tid] = r[2 + g];
+        }
+        __syncthreads();
+        // this warp can skip the batch if none of its pixels reaches that deep
+        if (total - 1 - base - (n - 1) >= wmax) continue;
+        for (int j = 0; j < n; ++j) {
+            const int k = total - 1 - (base + j);            // 0-based list position == contributor
+            if (k >= wmax) continue;                         // warp-uniform
+            const float4 a = sA[j];
+            const float4 b = sB[j];
+            const float dx = sub_(a.x, pxf), dy = sub_(a.y, pyf);
+            const float q = fma_(dx, mul_(dx, a.z), mul_(dy, mul_(dy, b.x)));
+            const float power = fma_(q, -0.5f, -mul_(dy, mul_(dx, a.w)));
+            const float G = expf(power);
+            const float alpha = fminf(0.99f, mul_(b.y, G));
+            const bool valid = k < last_contributor && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+            if (!__any_sync(0xffffffffu, valid)) continue;
+            float v0[V0];
+            float v1[V1 > 0 ? V1 : 4];
+#pragma unroll
+            for (int i = 0; i < V0; ++i) v0[i] = 0.0f;
+#pragma unroll
+            for (int i = 0; i < (V1 > 0 ? V1 : 4); ++i) v1[i] = 0.0f;
+            if (valid) {
+                T = T / (1.0f - alpha);
+                const float dchannel_dcolor = alpha * T;
+                float dL_dalpha = 0.0f;
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    const float4 c4 = sC[g][j];
+                    const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int c = 4 * g + e;
+                        accum[c] = last_alpha * lastc[c] + (1.0f - last_alpha) * accum[c];
+                        lastc[c] = cc[e];
+                        if (c < 3 || geo) dL_dalpha += (cc[e] - accum[c]) * dpix[c];
+                        const float gv = dchannel_dcolor * dpix[c];
+                        if (8 + c < V0) v0[(8 + c) < V0 ? (8 + c) : 0] = gv;
+                        else v1[(8 + c - V0) >= 0 && (8 + c - V0) < 4 ? (8 + c - V0) : 0] = gv;
+                    }
+                }
+                const float depth = b.z;
+                accum_d = last_alpha * last_depth + (1.0f - last_alpha) * accum_d;
+                last_depth = depth;
+                dL_dalpha += (depth - accum_d) * dpix_d;
+                accum_o = last_alpha + (1.0f - last_alpha) * accum_o;
+                dL_dalpha += (1.0f - accum_o) * dpix_o;
+                dL_dalpha *= T;
+                last_alpha = alpha;
+                dL_dalpha += (-T_final / (1.0f - alpha)) * bg_dot;
+                const float dL_dG = b.y * dL_dalpha;
+                const float gdx = G * dx, gdy = G * dy;
+                const float dG_ddelx = -gdx * a.z - gdy * a.w;
+                const float dG_ddely = -gdy * b.x - gdx * a.w;
+                v0[0] = dL_dG * dG_ddelx * ddelx_dx;
+                v0[1] = dL_dG * dG_ddely * ddely_dy;
+                v0[2] = dpix_d * dchannel_dcolor;
+                v0[3] = G * dL_dalpha;
+                v0[4] = -0.5f * gdx * dx * dL_dG;
+                v0[5] = -0.5f * gdx * dy * dL_dG;
+                v0[6] = -0.5f * gdy * dy * dL_dG;
+            }
+            float* grow = p.grad + (size_t)sId[j] * p.recf;
+            const float r0 = reduce_scatter<V0>(v0, lane);
+            {
+                constexpr int SH = V0 == 32 ? 0 : 1;            // lanes per component - 1 (log2)
+                const int comp = lane >> SH;
+                if ((lane & ((1 << SH) - 1)) == 0 && comp < V && comp != 7) atomicAdd(grow + comp, r0);
+            }
+            if constexpr (V1 > 0) {
+                const float r1 = reduce_scatter<4>(v1, lane);
+                const int comp = lane >> 3;
+                if ((lane & 7) == 0 && V0 + comp < V) atomicAdd(grow + V0 + comp, r1);
+            }
+        }
+    }
+}
+
+template <int NG>
+static void launch_bwd_ng(const CompositeBwdParams& p, int tiles, cudaStream_t stream) {
+    composite_bwd_kernel<NG><<<tiles, 256, 0, stream>>>(p);
+}
+
+int launch_composite_backward(const r3dg_raster_bwd_args& a, const GeomLayout& gl, const ImgLayout& il,
+                              const uint32_t* point_list, cudaStream_t stream) {
+    char* geom = (char*)a.geom;
+    char* img = (char*)a.img;
+    CompositeBwdParams p;
+    p.W = a.W; p.H = a.H; p.gx = (a.W + R3DG_TILE - 1) / R3DG_TILE; p.S = a.S; p.recf = gl.recf;
+    p.backward_geometry = a.backward_geometry;
+    const int gy = (a.H + R3DG_TILE - 1) / R3DG_TILE;
+    p.ranges = (const uint2*)(img + il.ranges);
+    p.point_list = point_list;
+    p.rec = (const float*)(geom + gl.rec);
+    p.bg = a.background;
+    p.final_T = (const float*)(img + il.final_T);
+    p.dL_dpix = a.dL_dout_color; p.dL_dpix_o = a.dL_dout_opacity; p.dL_dpix_d = a.dL_dout_depth;
+    p.dL_dpix_f = a.dL_dout_feature;
+    p.grad = (float*)(geom + gl.grad);
+    p.n_contrib = (const int*)(img + il.n_contrib);
+    R3DG_CUDA_TRY(cudaMemsetAsync(p.grad, 0, (size_t)a.P * gl.recf * 4, stream));
+    const int tiles = p.gx * gy;
+    switch (num_groups(a.S)) {
+        case 1: launch_bwd_ng<1>(p, tiles, stream); break;
+        case 2: launch_bwd_ng<2>(p, tiles, stream); break;
+        case 3: launch_bwd_ng<3>(p, tiles, stream); break;
+        case 4: launch_bwd_ng<4>(p, tiles, stream); break;
+        case 5: launch_bwd_ng<5>(p, tiles, stream); break;
+        case 6: launch_bwd_ng<6>(p, tiles, stream); break;
+        case 7: launch_bwd_ng<7>(p, tiles, stream); break;
+        default: return R3DG_ERR_UNSUPPORTED;   // S > 24: reference backward limit (backward.cu:449)
+    }
+    R3DG_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace r3dg

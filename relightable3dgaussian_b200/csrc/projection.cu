@@ -1,0 +1,375 @@
+// Stage 1 of the hot path: per-Gaussian projection / cull / covariance (reference K1,
+// forward.cu:156-258), tile-count prefix sum (K2, rasterizer_impl.cu:287), key duplication
+// (K4, rasterizer_impl.cu:70-111), tile ranges (K6, rasterizer_impl.cu:116-138) and
+// markVisible (K13).  The radix sort (K5) lives in radix_sort.cu.
+//
+// B200 design notes
+//  * one packed 16B-aligned record per Gaussian (common.cuh) is produced here so the compositors
+//    gather one row instead of five arrays;
+//  * the floating-point association of everything that feeds radii / tile rectangles / depth keys
+//    is pinned with explicit round-to-nearest intrinsics to the association of the reference's
+//    sm_100 binary, which makes point_list / ranges / n_contrib bit-identical;
+//  * the instance count R never travels to the host inside the pipeline: kernels read it from
+//    the geometry header, grids are sized from the SM count, and the binning buffer is
+//    capacity-checked on the device.
+#include <cstdio>
+#include "common.cuh"
+#include "kernels.h"
+
+namespace r3dg {
+
+__constant__ float SH_C2c[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                -1.0925484305920792f, 0.5462742152960396f};
+__constant__ float SH_C3c[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
+                                -0.5900435899266435f};
+
+// computeCov3D, association pinned (see oracle/oracle_raster.c:cov3d_from_scale_rot)
+__device__ __forceinline__ void cov3d_from_scale_rot(const float* __restrict__ s3, float mod,
+                                                     const float4 q, float* c6) {
+    const float r = q.x, x = q.y, y = q.z, z = q.w;
+    const float sx = mul_(s3[0], mod), sy = mul_(s3[1], mod), sz = mul_(s3[2], mod);
+    const float yy = mul_(y, y), zz = mul_(z, z), xz = mul_(x, z), rx = mul_(r, x), rz = mul_(r, z);
+    float t;
+    t = add_(yy, zz);            const float R00 = sub_(1.0f, add_(t, t));
+    t = fma_(x, y, -rz);         const float R01 = add_(t, t);
+    t = fma_(r, y, xz);          const float R02 = add_(t, t);
+    t = fma_(x, y, rz);          const float R10 = add_(t, t);
+    t = fma_(x, x, zz);          const float R11 = sub_(1.0f, add_(t, t));
+    t = fma_(y, z, -rx);         const float R12 = add_(t, t);
+    t = fma_(-r, y, xz);         const float R20 = add_(t, t);
+    t = fma_(y, z, rx);          const float R21 = add_(t, t);
+    t = fma_(x, x, yy);          const float R22 = sub_(1.0f, add_(t, t));
+    const float z00 = mul_(0.0f, R00), z11 = mul_(0.0f, R11), z21 = mul_(0.0f, R21);
+    const float m00 = fma_(0.0f, R02, fma_(0.0f, R01, mul_(sx, R00)));
+    const float m01 = fma_(0.0f, R02, fma_(sy, R01, z00));
+    const float m02 = fma_(sz, R02, fma_(0.0f, R01, z00));
+    const float m10 = fma_(0.0f, R12, fma_(sx, R10, z11));
+    const float m11 = fma_(0.0f, R12, fma_(0.0f, R10, mul_(sy, R11)));
+    const float m12 = fma_(sz, R12, fma_(0.0f, R10, z11));
+    const float m20 = fma_(0.0f, R22, fma_(sx, R20, z21));
+    const float m21 = fma_(0.0f, R22, fma_(0.0f, R20, mul_(sy, R21)));
+    const float m22 = fma_(sz, R22, fma_(0.0f, R20, z21));
+    c6[0] = dot3_(m00, m00, m01, m01, m02, m02);
+    c6[1] = dot3_(m00, m10, m01, m11, m02, m12);
+    c6[2] = dot3_(m00, m20, m01, m21, m02, m22);
+    c6[3] = dot3_(m10, m10, m11, m11, m12, m12);
+    c6[4] = dot3_(m10, m20, m11, m21, m12, m22);
+    c6[5] = dot3_(m20, m20, m21, m21, m22, m22);
+}
+
+// SH -> RGB (forward.cu:20-71).  sh rows are [M][3] floats.
+__device__ __forceinline__ void sh_to_rgb(int deg, float px, float py, float pz,
+                                          const float* __restrict__ campos,
+                                          const float* __restrict__ sh, float* rgb,
+                                          unsigned& clamped_bits) {
+    const float dx = px - campos[0], dy = py - campos[1], dz = pz - campos[2];
+    const float len = sqrt_(dot3_(dx, dx, dy, dy, dz, dz));
+    const float x = div_(dx, len), y = div_(dy, len), z = div_(dz, len);
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    float w[16];
+    w[0] = 0.28209479177387814f;
+    if (deg > 0) {
+        w[1] = -(0.4886025119029199f * y); w[2] = 0.4886025119029199f * z; w[3] = -(0.4886025119029199f * x);
+        if (deg > 1) {
+            w[4] = SH_C2c[0] * xy; w[5] = SH_C2c[1] * yz; w[6] = SH_C2c[2] * ((zz + zz) - xx - yy);
+            w[7] = SH_C2c[3] * xz; w[8] = SH_C2c[4] * (xx - yy);
+            if (deg > 2) {
+                w[9] = SH_C3c[0] * y * fmaf(xx, 3.0f, -yy);
+                w[10] = SH_C3c[1] * xy * z;
+                w[11] = SH_C3c[2] * y * (fmaf(zz, 4.0f, -xx) - yy);
+                w[12] = SH_C3c[3] * z * fmaf(yy, -3.0f, fmaf(xx, -3.0f, zz + zz));
+                w[13] = SH_C3c[4] * x * (fmaf(zz, 4.0f, -xx) - yy);
+                w[14] = SH_C3c[5] * z * (xx - yy);
+                w[15] = SH_C3c[6] * x * fmaf(yy, -3.0f, xx);
+            }
+        }
+    }
+    const int n = (deg + 1) * (deg + 1);
+    float res[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) res[c] = w[0] * sh[c];
+#pragma unroll
+    for (int k = 1; k < 16; ++k) {
+        if (k < n) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) res[c] = fmaf(w[k], sh[3 * k + c], res[c]);
+        }
+    }
+    clamped_bits = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        res[c] += 0.5f;
+        if (res[c] < 0.0f) clamped_bits |= 1u << c;
+        rgb[c] = fmaxf(res[c], 0.0f);
+    }
+}
+
+struct ProjParams {
+    int P, S, D, M, W, H, gx, gy, recf, ng;
+    const float *means3D, *shs, *colors_precomp, *features, *opacities, *scales, *rotations,
+        *cov3D_precomp, *viewmatrix, *projmatrix, *campos;
+    float scale_modifier, tan_fovx, tan_fovy, focal_x, focal_y;
+    int prefiltered;
+    float* rec;
+    uint32_t* tiles_touched;
+    uint8_t* clamped;
+    int* radii;
+    float* out_weights;
+    GeomHeader* header;
+};
+
+__global__ void __launch_bounds__(256) project_kernel(const ProjParams p) {
+    __shared__ float sV[16], sPr[16], sCam[3];
+    if (threadIdx.x < 16) { sV[threadIdx.x] = p.viewmatrix[threadIdx.x]; sPr[threadIdx.x] = p.projmatrix[threadIdx.x]; }
+    if (threadIdx.x < 3) sCam[threadIdx.x] = p.campos[threadIdx.x];
+    __syncthreads();
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.P) return;
+    p.radii[idx] = 0;
+    p.tiles_touched[idx] = 0;
+    p.out_weights[idx] = 0.0f;
+    const float px = p.means3D[3 * idx], py = p.means3D[3 * idx + 1], pz = p.means3D[3 * idx + 2];
+    const float tz = xform_row_(sV, 2, px, py, pz);
+    if (tz <= 0.2f) {                                  // auxiliary.h:154 (x/y frustum test is disabled there)
+        if (p.prefiltered) { printf("Point is filtered although prefiltered is set. This shouldn't happen!"); __trap(); }
+        return;
+    }
+    const float hx = xform_row_(sPr, 0, px, py, pz);
+    const float hy = xform_row_(sPr, 1, px, py, pz);
+    const float hw = xform_row_(sPr, 3, px, py, pz);
+    const float p_w = rcp_(add_(hw, 0.0000001f));
+    const float projx = mul_(hx, p_w), projy = mul_(hy, p_w);
+
+    float c6[6];
+    if (p.cov3D_precomp) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) c6[i] = p.cov3D_precomp[6 * (size_t)idx + i];
+    } else {
+        const float4 q = *reinterpret_cast<const float4*>(p.rotations + 4 * (size_t)idx);
+        const float s3[3] = {p.scales[3 * (size_t)idx], p.scales[3 * (size_t)idx + 1], p.scales[3 * (size_t)idx + 2]};
+        cov3d_from_scale_rot(s3, p.scale_modifier, q, c6);
+    }
+    // computeCov2D (forward.cu:74-113), association as compiled
+    const float tx = xform_row_(sV, 0, px, py, pz), ty = xform_row_(sV, 1, px, py, pz);
+    const float limx = mul_(p.tan_fovx, 1.3f), limy = mul_(p.tan_fovy, 1.3f);
+    const float cxz = fminf(fmaxf(div_(tx, tz), -limx), limx);
+    const float cyz = fminf(fmaxf(div_(ty, tz), -limy), limy);
+    const float tz2 = mul_(tz, tz);
+    const float j00 = div_(p.focal_x, tz), j11 = div_(p.focal_y, tz);
+    const float j02 = div_(mul_(mul_(tz, -cxz), p.focal_x), tz2);
+    const float j12 = div_(mul_(mul_(tz, -cyz), p.focal_y), tz2);
+    float T0[3], T1[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float w0 = sV[4 * k + 0], w1 = sV[4 * k + 1], w2 = sV[4 * k + 2];
+        T0[k] = fma_(w2, j02, fma_(w0, j00, mul_(0.0f, w1)));
+        T1[k] = fma_(w2, j12, fma_(0.0f, w0, mul_(w1, j11)));
+    }
+    const float a0 = dot3_(T0[0], c6[0], T0[1], c6[1], T0[2], c6[2]);
+    const float a1 = dot3_(T0[0], c6[1], T0[1], c6[3], T0[2], c6[4]);
+    const float a2 = dot3_(T0[0], c6[2], T0[1], c6[4], T0[2], c6[5]);
+    const float b0 = dot3_(T1[0], c6[0], T1[1], c6[1], T1[2], c6[2]);
+    const float b1 = dot3_(T1[0], c6[1], T1[1], c6[3], T1[2], c6[4]);
+    const float b2 = dot3_(T1[0], c6[2], T1[1], c6[4], T1[2], c6[5]);
+    const float cov_a = add_(dot3_(T0[0], a0, T0[1], a1, T0[2], a2), 0.3f);
+    const float cov_c = add_(dot3_(T1[0], b0, T1[1], b1, T1[2], b2), 0.3f);
+    const float cov_b = dot3_(T0[0], b0, T0[1], b1, T0[2], b2);
+    const float det = fma_(cov_a, cov_c, -mul_(cov_b, cov_b));
+    if (det == 0.0f) return;
+    const float det_inv = rcp_(det);
+    const float con_a = mul_(cov_c, det_inv), con_b = mul_(cov_b, -det_inv), con_c = mul_(cov_a, det_inv);
+    const float mid = mul_(add_(cov_a, cov_c), 0.5f);
+    const float disc = sqrt_(fmaxf(fma_(mid, mid, -det), 0.1f));
+    const float lam = fmaxf(add_(mid, disc), sub_(mid, disc));
+    const int my_radius = (int)ceilf(mul_(sqrt_(lam), 3.0f));
+    const float pix_x = (float)(fma((double)projx + 1.0, (double)p.W, -1.0) * 0.5);   // ndc2Pix, auxiliary.h:41-44
+    const float pix_y = (float)(fma((double)projy + 1.0, (double)p.H, -1.0) * 0.5);
+    int x0, y0, x1, y1;
+    get_rect(pix_x, pix_y, my_radius, p.gx, p.gy, x0, y0, x1, y1);
+    if ((x1 - x0) * (y1 - y0) == 0) return;
+
+    float rgb[3];
+    unsigned cl = 0;
+    if (p.colors_precomp == nullptr) {
+        sh_to_rgb(p.D, px, py, pz, sCam, p.shs + (size_t)idx * p.M * 3, rgb, cl);
+        p.clamped[idx] = (uint8_t)cl;
+    } else {
+        rgb[0] = p.colors_precomp[3 * (size_t)idx]; rgb[1] = p.colors_precomp[3 * (size_t)idx + 1]; rgb[2] = p.colors_precomp[3 * (size_t)idx + 2];
+    }
+    float4* rec = reinterpret_cast<float4*>(p.rec + (size_t)idx * p.recf);
+    rec[0] = make_float4(pix_x, pix_y, con_a, con_b);
+    rec[1] = make_float4(con_c, p.opacities[idx], tz, __int_as_float(my_radius));
+    // channels {r,g,b,f0..}, zero padded
+    const float* f = p.features + (size_t)idx * p.S;
+    for (int g = 0; g < p.ng; ++g) {
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = 4 * g + k;
+            v[k] = c < 3 ? rgb[c] : (c - 3 < p.S ? f[c - 3] : 0.0f);
+        }
+        rec[2 + g] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    p.radii[idx] = my_radius;
+    p.tiles_touched[idx] = (uint32_t)((y1 - y0) * (x1 - x0));
+}
+
+// ---- chained (decoupled look-back) inclusive scan of tiles_touched -> point_offsets ----------
+// One pass over the data, block order fixed by an atomic ticket.  state[b]: bits 31..30 flag
+// (1 = aggregate, 2 = inclusive prefix), bits 29..0 value.
+#define SCAN_THREADS 256
+#define SCAN_PER_THREAD (R3DG_SCAN_ITEMS / SCAN_THREADS)
+__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(int P, const uint32_t* __restrict__ in,
+                                                            uint32_t* __restrict__ out,
+                                                            volatile uint32_t* state, GeomHeader* header) {
+    __shared__ uint32_t s_block, s_warp[SCAN_THREADS / 32], s_prefix;
+    if (threadIdx.x == 0) s_block = atomicAdd(&header->scan_ticket, 1u);
+    __syncthreads();
+    const uint32_t b = s_block;
+    const int base = b * R3DG_SCAN_ITEMS + threadIdx.x * SCAN_PER_THREAD;
+    uint32_t v[SCAN_PER_THREAD], sum = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_PER_THREAD; ++i) { v[i] = base + i < P ? in[base + i] : 0u; sum += v[i]; }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < SCAN_THREADS / 32 ? s_warp[lane] : 0u, wi = w;
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += t; }
+        if (lane < SCAN_THREADS / 32) s_warp[lane] = wi - w;            // exclusive warp offsets
+        const uint32_t total = __shfl_sync(0xffffffffu, wi, SCAN_THREADS / 32 - 1);
+        if (lane == 0) {
+            uint32_t prefix = 0;
+            if (b == 0) {
+                state[0] = total | 0x80000000u;
+            } else {
+                state[b] = total | 0x40000000u;
+                __threadfence();
+                int t = (int)b - 1;
+                while (true) {
+                    uint32_t s;
+                    do { s = state[t]; } while ((s >> 30) == 0u);
+                    prefix += s & 0x3fffffffu;
+                    if ((s >> 30) == 2u) break;
+                    --t;
+                }
+                state[b] = (prefix + total) | 0x80000000u;
+            }
+            s_prefix = prefix;
+            if ((int)b == (P + R3DG_SCAN_ITEMS - 1) / R3DG_SCAN_ITEMS - 1) header->num_rendered = prefix + total;
+        }
+    }
+    __syncthreads();
+    uint32_t run = s_prefix + s_warp[warp] + (inc - sum);
+#pragma unroll
+    for (int i = 0; i < SCAN_PER_THREAD; ++i) { run += v[i]; if (base + i < P) out[base + i] = run; }
+}
+
+// ---- duplicateWithKeys (rasterizer_impl.cu:70-111): emission order = Gaussian index, then tile
+// row, then tile column — the stable sort preserves it for equal (tile, depth) keys. -------------
+__global__ void __launch_bounds__(256) emit_keys_kernel(int P, int recf, int gx, int gy,
+                                                        const float* __restrict__ rec,
+                                                        const int* __restrict__ radii,
+                                                        const uint32_t* __restrict__ offsets,
+                                                        uint64_t* __restrict__ keys,
+                                                        uint32_t* __restrict__ vals, long long capacity) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const int radius = radii[idx];
+    if (radius <= 0) return;
+    uint32_t off = idx == 0 ? 0u : offsets[idx - 1];
+    const float4 a = *reinterpret_cast<const float4*>(rec + (size_t)idx * recf);
+    const float4 b = *reinterpret_cast<const float4*>(rec + (size_t)idx * recf + 4);
+    int x0, y0, x1, y1;
+    get_rect(a.x, a.y, radius, gx, gy, x0, y0, x1, y1);
+    const uint64_t dbits = (uint64_t)__float_as_uint(b.z);
+    for (int y = y0; y < y1; ++y)
+        for (int x = x0; x < x1; ++x) {
+            if ((long long)off < capacity) {
+                keys[off] = ((uint64_t)(uint32_t)(y * gx + x) << 32) | dbits;
+                vals[off] = (uint32_t)idx;
+            }
+            ++off;
+        }
+}
+
+// ---- identifyTileRanges (rasterizer_impl.cu:116-138) ----------------------------------------
+__global__ void __launch_bounds__(256) tile_ranges_kernel(const GeomHeader* __restrict__ header,
+                                                          long long capacity,
+                                                          const uint64_t* __restrict__ keys,
+                                                          uint2* __restrict__ ranges) {
+    const long long R = min((long long)header->num_rendered, capacity);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < R;
+         i += (long long)gridDim.x * blockDim.x) {
+        const uint32_t cur = (uint32_t)(keys[i] >> 32);
+        if (i == 0) ranges[cur].x = 0;
+        else {
+            const uint32_t prev = (uint32_t)(keys[i - 1] >> 32);
+            if (cur != prev) { ranges[prev].y = (uint32_t)i; ranges[cur].x = (uint32_t)i; }
+        }
+        if (i == R - 1) ranges[cur].y = (uint32_t)R;
+    }
+}
+
+__global__ void mark_visible_kernel(int P, const float* __restrict__ means3D,
+                                    const float* __restrict__ viewmatrix, uint8_t* __restrict__ present) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const float tz = xform_row_(viewmatrix, 2, means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
+    present[idx] = tz > 0.2f ? 1 : 0;
+}
+
+// ---- host launchers -----------------------------------------------------------------------
+int launch_projection(const r3dg_raster_fwd_args& a, const GeomLayout& gl, const BinLayout& bl,
+                      cudaStream_t stream) {
+    char* geom = (char*)a.geom;
+    char* bin = (char*)a.binning;
+    ProjParams p;
+    p.P = a.P; p.S = a.S; p.D = a.D; p.M = a.M; p.W = a.W; p.H = a.H;
+    p.gx = (a.W + R3DG_TILE - 1) / R3DG_TILE; p.gy = (a.H + R3DG_TILE - 1) / R3DG_TILE;
+    p.recf = gl.recf; p.ng = num_groups(a.S);
+    p.means3D = a.means3D; p.shs = a.shs; p.colors_precomp = a.colors_precomp; p.features = a.features;
+    p.opacities = a.opacities; p.scales = a.scales; p.rotations = a.rotations; p.cov3D_precomp = a.cov3D_precomp;
+    p.viewmatrix = a.viewmatrix; p.projmatrix = a.projmatrix; p.campos = a.campos;
+    p.scale_modifier = a.scale_modifier; p.tan_fovx = a.tan_fovx; p.tan_fovy = a.tan_fovy;
+    p.focal_y = a.H / (2.0f * a.tan_fovy);            // rasterizer_impl.cu:232-233
+    p.focal_x = a.W / (2.0f * a.tan_fovx);
+    p.prefiltered = a.prefiltered;
+    p.rec = (float*)(geom + gl.rec); p.tiles_touched = (uint32_t*)(geom + gl.tiles_touched);
+    p.clamped = (uint8_t*)(geom + gl.clamped); p.radii = a.radii; p.out_weights = a.out_weights;
+    p.header = (GeomHeader*)(geom + gl.header);
+    const int nb = (a.P + 255) / 256;
+    project_kernel<<<nb, 256, 0, stream>>>(p);
+    const int nscan = (a.P + R3DG_SCAN_ITEMS - 1) / R3DG_SCAN_ITEMS;
+    R3DG_CUDA_TRY(cudaMemsetAsync(geom + gl.scan_state, 0, (size_t)(nscan + 1) * 4, stream));
+    scan_kernel<<<nscan, SCAN_THREADS, 0, stream>>>(a.P, p.tiles_touched, (uint32_t*)(geom + gl.point_offsets),
+                                                    (volatile uint32_t*)(geom + gl.scan_state), p.header);
+    emit_keys_kernel<<<nb, 256, 0, stream>>>(a.P, gl.recf, p.gx, p.gy, p.rec, a.radii,
+                                             (const uint32_t*)(geom + gl.point_offsets),
+                                             (uint64_t*)(bin + bl.keys_a), (uint32_t*)(bin + bl.vals_a), bl.capacity);
+    R3DG_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int launch_tile_ranges(const void* geom_header, long long capacity, const uint64_t* keys, void* ranges,
+                       int num_tiles, int num_sms, cudaStream_t stream) {
+    R3DG_CUDA_TRY(cudaMemsetAsync(ranges, 0, (size_t)num_tiles * 8, stream));
+    tile_ranges_kernel<<<num_sms * 8, 256, 0, stream>>>((const GeomHeader*)geom_header, capacity, keys, (uint2*)ranges);
+    R3DG_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,
+                        cudaStream_t stream) {
+    if (P <= 0) return 0;
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, viewmatrix, present);
+    R3DG_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace r3dg
