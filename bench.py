@@ -1,0 +1,393 @@
+#!/usr/bin/env python3
+"""bench.py — fwd+bwd views/sec of the rasterizer hot path (BASELINE.json metric) on N B200s.
+
+  python bench.py --gpus 1 --steps 50 --warmup 10                      # our kernels
+  python bench.py --impl reference --gpus 1 --steps 20 --warmup 3      # reference CUDA kernels
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+         --master-port P bench.py --gpus N --steps K --warmup W        # one rank per GPU
+
+A "step" is one full forward + backward of the differentiable rasterizer for one view per GPU
+(1M Gaussians, 800x800, S=5 feature channels, SH degree 3, seeded synthetic `shell-v1` scene,
+8-camera ring, fixed random cotangents); with N GPUs the views of a step are sharded one per GPU
+and a single NCCL all-reduce of the per-Gaussian parameter gradients follows backward (weak
+scaling).  Prints ONE JSON line on rank 0.
+
+Keys: `value` = whole-job views/s with inputs resident in HBM (C-ABI level operator calls);
+`e2e` = the same step through the reference-facing public API (GaussianRasterizer module +
+autograd) including, every step, the host->device copy of that step's inputs from pinned memory
+(camera + ground-truth image) and the device->host read of the loss; `roofline` = dominant kernel
+vs the measured HBM peak (MEASURED_PEAKS.json); `cpu_baseline` = the CPU oracle port timed on a
+bounded sample (rank 0, N=1 only).  `--impl reference` times the UNMODIFIED reference CUDA kernels
+(oracle/_ref, built from /root/reference by oracle/build_ref.sh) on the same GPU; when that build
+is absent it falls back to the CPU oracle port.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HEADLINE = dict(P=1_000_000, W=800, H=800, S=5, views=8, recipe="shell-v1", seed=0)
+STAGES = ["project", "scan", "emit_keys", "radix_sort", "tile_ranges", "composite_fwd",
+          "surface_normal", "composite_bwd", "project_bwd"]
+
+
+class ClockSampler:
+    """nvidia-smi sampler running DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def alg_bytes(P, Pv, R, HW, T, S):
+    """Algorithmic bytes per stage and view (R, Pv measured in this run)."""
+    return {
+        "project": 236 * P + 48 * Pv,
+        "scan": 8 * P, "emit_keys": 12 * R,
+        "radix_sort": 24 * R, "tile_ranges": 8 * R + 8 * T,
+        "composite_fwd": R * (4 + 40 + 4 * S) + HW * 4 * (3 + 1 + 1 + S) + 8 * HW + 4 * P,
+        "surface_normal": 44 * HW,
+        "composite_bwd": R * (44 + 4 * S) + HW * 4 * (5 + S) + 8 * HW + Pv * 4 * (11 + S),
+        "project_bwd": Pv * (236 + 24 + 3 + 4 + 40) + P * 4 * (3 + 6 + 48 + 3 + 4),
+    }
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_inputs(cfg, device):
+    from relightable3dgaussian_b200 import synth
+    sc = synth.make_scene(cfg["P"], cfg["recipe"], cfg["seed"], cfg["S"])
+    cams = [synth.make_camera(k, cfg["W"], cfg["H"]) for k in range(cfg["views"])]
+    g = torch.Generator().manual_seed(1234)
+    H, W, S = cfg["H"], cfg["W"], cfg["S"]
+    cot = dict(color=torch.randn(3, H, W, generator=g), opacity=torch.randn(1, H, W, generator=g),
+               depth=torch.randn(1, H, W, generator=g), feature=torch.randn(S, H, W, generator=g))
+    gts = [torch.rand(3, H, W, generator=g) for _ in range(cfg["views"])]
+    return sc, cams, cot, gts
+
+
+def bench_ours(args, cfg, rank, local, world):
+    from relightable3dgaussian_b200 import _C_raster as C, _lib, dist as rdist
+    from relightable3dgaussian_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+    import torch.distributed as tdist
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    sc, cams, cot, gts = make_inputs(cfg, dev)
+    P, S, W, H = cfg["P"], cfg["S"], cfg["W"], cfg["H"]
+    M = 16
+    d = lambda t: t.to(dev)
+    means3D, scales, rots, opac, shs, feats = map(d, (sc.means3D, sc.scales, sc.rotations, sc.opacities, sc.shs, sc.features))
+    bg = torch.tensor([0.0, 0.0, 0.0], device=dev)
+    camd = [dict(view=d(c.viewmatrix), proj=d(c.projmatrix), pos=d(c.campos), c=c) for c in cams]
+    dcot = {k: d(v) for k, v in cot.items()}
+    E = torch.Tensor([])
+    bucket = rdist.GradBucket(P, S, M, dev)
+    stats = {}
+
+    def step_resident(i):
+        cam = camd[rdist.view_for_rank(i, rank, world, cfg["views"])]
+        c = cam["c"]
+        out = C.rasterize_gaussians(bg, means3D, feats, E, opac, scales, rots, 1.0, E, cam["view"], cam["proj"],
+                                    c.tanfovx, c.tanfovy, c.cx, c.cy, H, W, shs, 3, cam["pos"], False, True, False)
+        stats["R"] = out[0]; stats["radii"] = out[9]
+        C.rasterize_gaussians_backward(bg, means3D, feats, out[9], E, scales, rots, 1.0, E, cam["view"], cam["proj"],
+                                       c.tanfovx, c.tanfovy, dcot["color"], dcot["opacity"], dcot["depth"],
+                                       dcot["feature"], shs, 3, cam["pos"], out[10], out[0], out[11], out[12],
+                                       True, False, _out=bucket.views)
+        bucket.allreduce_mean()
+
+    def timed(fn, steps, warmup, profile=False):
+        for i in range(warmup):
+            fn(i)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize(dev)
+        if profile:
+            lib.r3dg_prof_begin(steps)
+        l0 = lib.r3dg_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        stage = None
+        if profile:
+            arr = (ctypes.c_float * 9)(); nf = ctypes.c_int(); nb = ctypes.c_int()
+            lib.r3dg_prof_end(arr, ctypes.byref(nf), ctypes.byref(nb))
+            stage = {n: arr[i] / max(nf.value if i < 7 else nb.value, 1) for i, n in enumerate(STAGES)}
+        launches = lib.r3dg_launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, stage, launches
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, stage, launches = timed(step_resident, args.steps, args.warmup, profile=True)
+    clocks = sampler.stop() if sampler else None
+    value = world * args.steps / (ms / 1e3)
+
+    # ---- e2e: public API (module + autograd), per-step host inputs from pinned memory -------
+    params = [t.clone().requires_grad_(True) for t in (means3D, opac, shs, scales, rots, feats)]
+    pinned_gt = [g.pin_memory() for g in gts]
+    pinned_cam = [torch.cat([c.viewmatrix.reshape(-1), c.projmatrix.reshape(-1), c.campos]).pin_memory() for c in cams]
+    gt_dev = torch.empty(3, H, W, device=dev)
+    cam_dev = torch.empty(35, device=dev)
+    loss_host = torch.zeros(1).pin_memory()
+    h2d = gt_dev.numel() * 4 + cam_dev.numel() * 4
+    d2h = 4
+
+    def step_e2e(i):
+        v = rdist.view_for_rank(i, rank, world, cfg["views"])
+        c = cams[v]
+        gt_dev.copy_(pinned_gt[v], non_blocking=True)
+        cam_dev.copy_(pinned_cam[v], non_blocking=True)
+        rs = GaussianRasterizationSettings(H, W, c.tanfovx, c.tanfovy, c.cx, c.cy, bg, 1.0,
+                                           cam_dev[:16].view(4, 4), cam_dev[16:32].view(4, 4), 3, cam_dev[32:35],
+                                           False, True, True, False)
+        p_means, p_opac, p_shs, p_scales, p_rots, p_feats = params
+        means2D = torch.zeros_like(p_means, requires_grad=True)
+        out = GaussianRasterizer(rs)(means3D=p_means, means2D=means2D, opacities=p_opac, shs=p_shs,
+                                     scales=p_scales, rotations=p_rots, features=p_feats)
+        color, opacity, depth, feature = out[2], out[3], out[4], out[5]
+        loss = (color - gt_dev).abs().mean() + 0.01 * opacity.mean() + 0.01 * depth.mean() + 0.01 * feature.square().mean()
+        for p_ in params:
+            p_.grad = None
+        loss.backward()
+        if world > 1:
+            flat = torch.cat([p_.grad.reshape(-1) for p_ in params])
+            flat.mul_(1.0 / world)
+            tdist.all_reduce(flat)
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+
+    e_steps = max(3, args.steps // 2)
+    ms_e, _, _ = timed(step_e2e, e_steps, min(args.warmup, 3))
+    e2e_value = world * e_steps / (ms_e / 1e3)
+
+    res = None
+    if rank == 0:
+        Pv = int((stats["radii"] > 0).sum().item())
+        R = int(stats["R"])
+        T = ((W + 15) // 16) * ((H + 15) // 16)
+        ab = alg_bytes(P, Pv, R, H * W, T, S)
+        dom = max(stage, key=lambda k: stage[k])
+        peak, peak_src = measured_peak()
+        achieved = ab[dom] / (stage[dom] * 1e-3) / 1e9
+        step_alg = sum(ab.values())
+        res = {
+            "metric": "fwd+bwd views/sec at 1M Gaussians 800x800, 1/2/4/8 B200; HBM GB/s vs peak" if cfg == HEADLINE else "fwd+bwd views/sec (non-headline config)",
+            "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"rasterizer fwd+bwd, {cfg['recipe']} seed {cfg['seed']}, P={P}, {W}x{H}, S={S}, SH deg 3, "
+                                   f"{cfg['views']}-camera ring, one view per GPU per step",
+                       "P": P, "W": W, "H": H, "S": S, "num_rendered": R, "P_visible": Pv,
+                       "parallelism": f"view-parallel x{world}, 1 NCCL all-reduce of {bucket.bytes() / 1e6:.0f} MB grads/step" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (236 MB Gaussian parameters + ~190 MB binning per step vs 126 MB L2)"},
+            "e2e": {"value": e2e_value, "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e_steps, "ms_per_step": ms_e / e_steps,
+                    "what": "GaussianRasterizer module + autograd + L1 loss; per step H2D of ground-truth image + camera from pinned memory, D2H of the loss"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "stage_ms": stage,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "alg_bytes_per_launch": ab[dom],
+                         "step_alg_bytes": step_alg, "step_frac_of_peak": step_alg / (ms / args.steps * 1e-3) / 1e9 / peak},
+        }
+    return res
+
+
+def cpu_baseline_sample(cfg, seconds_budget=25.0):
+    """The CPU oracle (port of the reference algorithm) on a bounded sample of the same workload:
+    one view, the first P_s Gaussians of the scene at the full resolution."""
+    import numpy as np
+    from oracle import oracle
+    from relightable3dgaussian_b200 import synth
+    P_s = min(cfg["P"], 100_000)
+    sc = synth.make_scene(cfg["P"], cfg["recipe"], cfg["seed"], cfg["S"])
+    cam = synth.make_camera(0, cfg["W"], cfg["H"])
+    n = lambda t: t[:P_s].numpy() if t.shape[0] == cfg["P"] else t.numpy()
+    W, H, S = cfg["W"], cfg["H"], cfg["S"]
+    rng = np.random.default_rng(0)
+    cots = [rng.standard_normal((c, H, W)).astype(np.float32) for c in (3, 1, 1, S)]
+    bg = np.zeros(3, np.float32)
+    t0 = time.time()
+    f = oracle.rasterize_forward(n(sc.means3D), n(sc.opacities), cam.viewmatrix.numpy(), cam.projmatrix.numpy(),
+                                 cam.campos.numpy(), bg, W, H, cam.tanfovx, cam.tanfovy, cam.cx, cam.cy,
+                                 shs=n(sc.shs), scales=n(sc.scales), rotations=n(sc.rotations), features=n(sc.features))
+    oracle.rasterize_backward(f, n(sc.means3D), cam.viewmatrix.numpy(), cam.projmatrix.numpy(), cam.campos.numpy(), bg,
+                              W, H, cam.tanfovx, cam.tanfovy, *cots, shs=n(sc.shs), scales=n(sc.scales),
+                              rotations=n(sc.rotations), features=n(sc.features))
+    dt = time.time() - t0
+    frac = P_s / cfg["P"]
+    return {"value": frac / dt, "unit": "views/s", "cores": oracle.num_threads(), "kind": "port",
+            "sample": f"1 view fwd+bwd of the first {P_s} of {cfg['P']} Gaussians at {W}x{H} (R={f['binned']['num_rendered']}) "
+                      f"took {dt:.2f}s on {oracle.num_threads()} threads; value = that scaled by the sample fraction {frac:.2f} (work ~ R)",
+            "sample_seconds": dt}
+
+
+def bench_reference(args, cfg, rank, local, world):
+    """--impl reference: the unmodified reference CUDA kernels on this GPU (rank 0 only)."""
+    if rank != 0:
+        return None
+    from oracle import ref_gpu
+    base = {"impl": "reference", "metric": "fwd+bwd views/sec at 1M Gaussians 800x800, 1/2/4/8 B200; HBM GB/s vs peak" if cfg == HEADLINE else "fwd+bwd views/sec (non-headline config)",
+            "unit": "views/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+    P, S, W, H = cfg["P"], cfg["S"], cfg["W"], cfg["H"]
+    if ref_gpu.available():
+        dev = torch.device("cuda", local)
+        torch.cuda.set_device(dev)
+        sc, cams, cot, gts = make_inputs(cfg, dev)
+        d = lambda t: t.to(dev)
+        kw = dict(means3D=d(sc.means3D), opacities=d(sc.opacities), shs=d(sc.shs), scales=d(sc.scales),
+                  rotations=d(sc.rotations), features=d(sc.features))
+        bg = torch.zeros(3, device=dev)
+        dc = {k: d(v) for k, v in cot.items()}
+        camd = [dict(viewmatrix=d(c.viewmatrix), projmatrix=d(c.projmatrix), campos=d(c.campos)) for c in cams]
+        ref = ref_gpu.RefRasterizer()
+
+        def step(i):
+            c, cd = cams[i % len(cams)], camd[i % len(cams)]
+            o = ref.forward(bg=bg, W=W, H=H, tan_fovx=c.tanfovx, tan_fovy=c.tanfovy, cx=c.cx, cy=c.cy, **cd, **kw)
+            ref.backward(o, bg=bg, tan_fovx=c.tanfovx, tan_fovy=c.tanfovy, dL_dcolor=dc["color"], dL_dopacity=dc["opacity"],
+                         dL_ddepth=dc["depth"], dL_dfeature=dc["feature"], **cd,
+                         **{k: v for k, v in kw.items() if k != "opacities"})
+            return o
+        for i in range(args.warmup):
+            step(i)
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local); sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            o = step(args.warmup + i)
+        e1.record()
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+        ms = e0.elapsed_time(e1)
+        v = args.steps / (ms / 1e3)
+        base.update({"value": v, "ms_per_step": ms / args.steps, "clocks": clocks,
+                     "config": {"workload": f"reference CUDA kernels (sm_100 build of /root/reference), same scene/cameras/cotangents, P={P}, {W}x{H}, S={S}",
+                                "num_rendered": int(o["num_rendered"])},
+                     "cpu_baseline": {"value": v, "unit": "views/s", "cores": os.cpu_count(), "kind": "reference",
+                                      "sample": "not a CPU run: the reference has no CPU rasterizer; this is its own CUDA build timed on the same B200 (north_star), full workload, 8-camera ring"},
+                     "e2e": {"value": v, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        return base
+    # fallback: CPU oracle port on a bounded sample
+    cb = cpu_baseline_sample(cfg)
+    base.update({"value": cb["value"], "ms_per_step": 1e3 / cb["value"],
+                 "config": {"workload": "CPU oracle port of the reference algorithm (oracle/_ref CUDA build absent)"},
+                 "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    return base
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--P", type=int, default=None)
+    ap.add_argument("--W", type=int, default=None)
+    ap.add_argument("--H", type=int, default=None)
+    ap.add_argument("--S", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    cfg = dict(HEADLINE)
+    for k in ("P", "W", "H", "S"):
+        if getattr(args, k) is not None:
+            cfg[k] = getattr(args, k)
+    from relightable3dgaussian_b200 import dist as rdist
+    rank, local, world = rdist.init_from_env()
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps(bench_reference(args, cfg, rank, local, world)), flush=True)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA GPU: the rasterizer hot path has no CPU fallback")
+    res = bench_ours(args, cfg, rank, local, world)
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                res["cpu_baseline"] = cpu_baseline_sample(cfg)
+            except Exception as e:   # the oracle is only a reported baseline
+                res["cpu_baseline"] = {"value": None, "unit": "views/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(res), flush=True)
+    if world > 1:
+        import torch.distributed as tdist
+        tdist.barrier()
+        tdist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

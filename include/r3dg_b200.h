@@ -138,6 +138,16 @@ long long r3dg_raster_debug_copy(int id, int P, int S, int W, int H, const void*
                                  const void* img, const void* binning, size_t binning_bytes,
                                  void* dst, long long max_bytes, r3dg_stream_t stream);
 
+/* Measurement hooks used by bench.py (never needed by the reference's callers).
+ * r3dg_launch_count: number of this library's kernels launched so far in the process.
+ * r3dg_prof_begin/end: while active, every forward/backward records CUDA events on the launching
+ * stream between its stages (0 project, 1 scan, 2 emit keys, 3 radix sort, 4 tile ranges,
+ * 5 composite fwd, 6 surface/normal, 7 composite bwd, 8 projection bwd); r3dg_prof_end sums the
+ * per-stage milliseconds over the recorded calls (caller synchronises first). */
+unsigned long long r3dg_launch_count(void);
+int r3dg_prof_begin(int max_calls);
+int r3dg_prof_end(float* stage_ms /* [9] */, int* fwd_calls, int* bwd_calls);
+
 /* Library identification: returns a static string such as "r3dg_b200 0.1 sm_100a". */
 const char* r3dg_version(void);
 

@@ -124,7 +124,7 @@ def rasterize_gaussians_backward(background, means3D, features, radii, colors, s
                                  scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx,
                                  tan_fovy, dL_dout_color, dL_dout_opacity, dL_dout_depth,
                                  dL_dout_feature, sh, degree, campos, geomBuffer, R, binningBuffer,
-                                 imageBuffer, backward_geometry, debug):
+                                 imageBuffer, backward_geometry, debug, _out=None):
     """== RasterizeGaussiansBackwardCUDA (rasterize_points.cu:143-235).  Returns the 9-tuple
     (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dfeatures, dL_dcov3D, dL_dsh,
      dL_dscales, dL_drotations)."""
@@ -146,15 +146,25 @@ def rasterize_gaussians_backward(background, means3D, features, radii, colors, s
     M = sh.size(1) if sh.numel() != 0 else 0
 
     f32 = dict(dtype=torch.float32, device=dev)
-    dL_dmeans3D = torch.empty((P, 3), **f32)
-    dL_dmeans2D = torch.empty((P, 3), **f32)
-    dL_dfeatures = torch.empty((P, S), **f32)
-    dL_dcolors = torch.empty((P, 3), **f32)
-    dL_dopacity = torch.empty((P, 1), **f32)
-    dL_dcov3D = torch.empty((P, 6), **f32)
-    dL_dsh = torch.empty((P, M, 3), **f32)
-    dL_dscales = torch.empty((P, 3), **f32)
-    dL_drotations = torch.empty((P, 4), **f32)
+
+    def _alloc(name, shape):
+        # `_out` (dist.GradBucket views) lets the multi-GPU path have the kernels write straight
+        # into the flat all-reduce buffer; every element is written, so empty() is enough.
+        if _out is not None and name in _out:
+            t = _out[name]
+            assert t.is_contiguous() and tuple(t.shape) == tuple(shape) and t.dtype == torch.float32
+            return t
+        return torch.empty(shape, **f32)
+
+    dL_dmeans3D = _alloc("means3D", (P, 3))
+    dL_dmeans2D = _alloc("means2D", (P, 3))
+    dL_dfeatures = _alloc("features", (P, S))
+    dL_dcolors = _alloc("colors", (P, 3))
+    dL_dopacity = _alloc("opacity", (P, 1))
+    dL_dcov3D = _alloc("cov3D", (P, 6))
+    dL_dsh = _alloc("sh", (P, M, 3))
+    dL_dscales = _alloc("scales", (P, 3))
+    dL_drotations = _alloc("rotations", (P, 4))
     if P != 0:
         a = _lib.RasterBwdArgs()
         a.P, a.S, a.D, a.M, a.W, a.H = P, S, int(degree), M, W, H

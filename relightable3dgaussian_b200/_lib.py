@@ -55,6 +55,9 @@ SYMBOLS = [
     ("r3dg_raster_forward", c_int, [ctypes.POINTER(RasterFwdArgs), c_void_p]),
     ("r3dg_raster_backward", c_int, [ctypes.POINTER(RasterBwdArgs), c_void_p]),
     ("r3dg_mark_visible", c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    ("r3dg_launch_count", ctypes.c_ulonglong, []),
+    ("r3dg_prof_begin", c_int, [c_int]),
+    ("r3dg_prof_end", c_int, [ctypes.POINTER(c_float), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     ("r3dg_raster_debug_copy", c_ll, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                       c_void_p, c_size_t, c_void_p, c_ll, c_void_p]),
 ]

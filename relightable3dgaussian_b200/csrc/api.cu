@@ -3,6 +3,7 @@
 // no global state besides the cached SM count.
 #include <cstdio>
 #include <cstring>
+#include <vector>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -20,6 +21,22 @@ int num_sms() {
             g_num_sms = 148;   // B200
     }
     return g_num_sms;
+}
+// ---- optional stage profiler: CUDA events recorded on the launching stream between stages ----
+enum { ST_PROJECT = 0, ST_SCAN, ST_EMIT, ST_SORT, ST_RANGES, ST_COMPOSITE, ST_NORMAL, ST_COMPOSITE_BWD,
+       ST_PROJECT_BWD, ST_COUNT };
+struct Prof {
+    bool on = false;
+    int max_calls = 0, fwd_calls = 0, bwd_calls = 0;
+    std::vector<cudaEvent_t> ev;      // [max_calls][ST_COUNT + 2]  (fwd: 0..7 boundaries, bwd: 8..10)
+    cudaEvent_t& at(int call, int i) { return ev[(size_t)call * (ST_COUNT + 2) + i]; }
+} g_prof;
+unsigned long long g_launches = 0;
+inline void prof_mark(bool fwd, int i, cudaStream_t s) {
+    if (!g_prof.on) return;
+    const int call = fwd ? g_prof.fwd_calls : g_prof.bwd_calls;
+    if (call >= g_prof.max_calls) return;
+    cudaEventRecord(g_prof.at(call, i), s);
 }
 int sort_passes(int W, int H) {
     const int tiles = ((W + R3DG_TILE - 1) / R3DG_TILE) * ((H + R3DG_TILE - 1) / R3DG_TILE);
@@ -57,15 +74,23 @@ int r3dg_raster_forward(const r3dg_raster_fwd_args* a, r3dg_stream_t stream_) {
     R3DG_CUDA_TRY(cudaMemsetAsync(geom + gl.header, 0, sizeof(GeomHeader), stream));
     int rc = 0;
     const int passes = sort_passes(a->W, a->H);
+    prof_mark(true, 0, stream);
     if (a->P > 0) {
-        if ((rc = launch_projection(*a, gl, bl, stream)) != 0) return rc;
+        if ((rc = launch_projection(*a, gl, bl, stream, [](int i, cudaStream_t s) { prof_mark(true, i, s); })) != 0) return rc;
+        prof_mark(true, 3, stream);
         if ((rc = launch_sort(geom + gl.header, bin, bl, passes, num_sms(), stream)) != 0) return rc;
+        g_launches += 3 + 2 + passes;
     }
+    prof_mark(true, 4, stream);
     const bool in_b = (passes & 1) != 0;
     const uint64_t* keys_sorted = (const uint64_t*)(bin + (in_b ? bl.keys_b : bl.keys_a));
     const uint32_t* point_list = (const uint32_t*)(bin + (in_b ? bl.vals_b : bl.vals_a));
     if ((rc = launch_tile_ranges(geom + gl.header, capacity, keys_sorted, img + il.ranges, tiles, num_sms(), stream)) != 0) return rc;
-    if ((rc = launch_composite_forward(*a, gl, il, point_list, stream)) != 0) return rc;
+    prof_mark(true, 5, stream);
+    if ((rc = launch_composite_forward(*a, gl, il, point_list, stream, [](int i, cudaStream_t s) { prof_mark(true, i, s); })) != 0) return rc;
+    prof_mark(true, 7, stream);
+    g_launches += 2 + (a->computer_pseudo_normal ? 1 : 0);
+    if (g_prof.on) g_prof.fwd_calls++;
     if (a->num_rendered_host)
         R3DG_CUDA_TRY(cudaMemcpyAsync(a->num_rendered_host, geom + gl.header, sizeof(int), cudaMemcpyDeviceToHost, stream));
     if (a->debug) {   // reference CHECK_CUDA semantics (auxiliary.h:166-173): sync and report
@@ -90,8 +115,13 @@ int r3dg_raster_backward(const r3dg_raster_bwd_args* a, r3dg_stream_t stream_) {
     const bool in_b = (sort_passes(a->W, a->H) & 1) != 0;
     const uint32_t* point_list = (const uint32_t*)(bin + (in_b ? bl.vals_b : bl.vals_a));
     int rc = 0;
+    prof_mark(false, 8, stream);
     if ((rc = launch_composite_backward(*a, gl, il, point_list, stream)) != 0) return rc;
+    prof_mark(false, 9, stream);
     if ((rc = launch_projection_backward(*a, gl, stream)) != 0) return rc;
+    prof_mark(false, 10, stream);
+    g_launches += 2;
+    if (g_prof.on) g_prof.bwd_calls++;
     if (a->debug) {
         cudaError_t e = cudaStreamSynchronize(stream);
         if (e != cudaSuccess) return -(int)e;
@@ -99,9 +129,43 @@ int r3dg_raster_backward(const r3dg_raster_bwd_args* a, r3dg_stream_t stream_) {
     return 0;
 }
 
+unsigned long long r3dg_launch_count(void) { return g_launches; }
+
+int r3dg_prof_begin(int max_calls) {
+    for (auto& e : g_prof.ev) cudaEventDestroy(e);
+    g_prof.ev.assign((size_t)max_calls * (ST_COUNT + 2), nullptr);
+    for (auto& e : g_prof.ev) R3DG_CUDA_TRY(cudaEventCreate(&e));
+    g_prof.max_calls = max_calls; g_prof.fwd_calls = g_prof.bwd_calls = 0; g_prof.on = true;
+    return 0;
+}
+
+// Sums the per-stage durations (ms) over the recorded calls; the caller must have synchronised.
+int r3dg_prof_end(float* stage_ms /*[9]*/, int* fwd_calls, int* bwd_calls) {
+    g_prof.on = false;
+    for (int i = 0; i < ST_COUNT; ++i) stage_ms[i] = 0.f;
+    const int nf = g_prof.fwd_calls < g_prof.max_calls ? g_prof.fwd_calls : g_prof.max_calls;
+    const int nb = g_prof.bwd_calls < g_prof.max_calls ? g_prof.bwd_calls : g_prof.max_calls;
+    for (int c = 0; c < nf; ++c)
+        for (int i = 0; i < 7; ++i) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, g_prof.at(c, i), g_prof.at(c, i + 1)) == cudaSuccess) stage_ms[i] += ms;
+        }
+    for (int c = 0; c < nb; ++c)
+        for (int i = 0; i < 2; ++i) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, g_prof.at(c, 8 + i), g_prof.at(c, 9 + i)) == cudaSuccess) stage_ms[7 + i] += ms;
+        }
+    if (fwd_calls) *fwd_calls = nf;
+    if (bwd_calls) *bwd_calls = nb;
+    for (auto& e : g_prof.ev) cudaEventDestroy(e);
+    g_prof.ev.clear();
+    return 0;
+}
+
 int r3dg_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                       uint8_t* present, r3dg_stream_t stream) {
     (void)projmatrix;   // the reference's in_frustum computes p_proj but never uses it (auxiliary.h:151-154)
+    g_launches += P > 0 ? 1 : 0;
     return launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
 }
 

@@ -173,7 +173,7 @@ static void launch_fwd_ng(const CompositeFwdParams& p, int tiles, cudaStream_t s
 }
 
 int launch_composite_forward(const r3dg_raster_fwd_args& a, const GeomLayout& gl, const ImgLayout& il,
-                             const uint32_t* point_list, cudaStream_t stream) {
+                             const uint32_t* point_list, cudaStream_t stream, stage_mark_fn mark) {
     char* geom = (char*)a.geom;
     char* img = (char*)a.img;
     CompositeFwdParams p;
@@ -201,6 +201,7 @@ int launch_composite_forward(const r3dg_raster_fwd_args& a, const GeomLayout& gl
         default: return R3DG_ERR_UNSUPPORTED;
     }
     const size_t HW = (size_t)a.H * a.W;
+    mark(6, stream);
     if (a.computer_pseudo_normal) {
         const float focal_y = a.H / (2.0f * a.tan_fovy), focal_x = a.W / (2.0f * a.tan_fovx);
         dim3 grid((a.W + 31) / 32, (a.H + 7) / 8);

@@ -326,7 +326,7 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D,
 
 // ---- host launchers -----------------------------------------------------------------------
 int launch_projection(const r3dg_raster_fwd_args& a, const GeomLayout& gl, const BinLayout& bl,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, stage_mark_fn mark) {
     char* geom = (char*)a.geom;
     char* bin = (char*)a.binning;
     ProjParams p;
@@ -345,10 +345,12 @@ int launch_projection(const r3dg_raster_fwd_args& a, const GeomLayout& gl, const
     p.header = (GeomHeader*)(geom + gl.header);
     const int nb = (a.P + 255) / 256;
     project_kernel<<<nb, 256, 0, stream>>>(p);
+    mark(1, stream);
     const int nscan = (a.P + R3DG_SCAN_ITEMS - 1) / R3DG_SCAN_ITEMS;
     R3DG_CUDA_TRY(cudaMemsetAsync(geom + gl.scan_state, 0, (size_t)(nscan + 1) * 4, stream));
     scan_kernel<<<nscan, SCAN_THREADS, 0, stream>>>(a.P, p.tiles_touched, (uint32_t*)(geom + gl.point_offsets),
                                                     (volatile uint32_t*)(geom + gl.scan_state), p.header);
+    mark(2, stream);
     emit_keys_kernel<<<nb, 256, 0, stream>>>(a.P, gl.recf, p.gx, p.gy, p.rec, a.radii,
                                              (const uint32_t*)(geom + gl.point_offsets),
                                              (uint64_t*)(bin + bl.keys_a), (uint32_t*)(bin + bl.vals_a), bl.capacity);

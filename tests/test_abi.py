@@ -1,0 +1,76 @@
+"""C-ABI surface: the shared library loads and exports every symbol include/r3dg_b200.h declares,
+struct layouts agree with the header, sizing functions are sane.  No GPU compute is issued."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from helpers import ROOT
+from relightable3dgaussian_b200 import _lib
+
+
+def _declared_functions():
+    hdr = open(os.path.join(ROOT, "include", "r3dg_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = re.findall(r"\b(r3dg_[a-z0-9_]+)\s*\(", hdr)
+    return sorted(set(n for n in names if not n.endswith("_t")))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    declared = _declared_functions()
+    assert len(declared) >= 10
+    bound = {n for n, _, _ in _lib.SYMBOLS}
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/r3dg_b200.h but not exported"
+        assert name in bound, f"{name} is exported but not bound in _lib.SYMBOLS"
+    assert b"sm_100a" in lib.r3dg_version()
+
+
+def test_struct_field_order_matches_header():
+    hdr = open(os.path.join(ROOT, "include", "r3dg_b200.h")).read()
+    for cname, cls in (("r3dg_raster_fwd_args", _lib.RasterFwdArgs), ("r3dg_raster_bwd_args", _lib.RasterBwdArgs)):
+        body = re.search(r"typedef struct " + cname + r" \{(.*?)\} " + cname + ";", hdr, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            names = re.sub(r"^(const\s+)?(float|int|void|size_t)\s*\**", "", decl)
+            for n in names.split(","):
+                fields.append(n.replace("*", "").strip())
+        assert fields == [f[0] for f in cls._fields_], cname
+
+
+def test_sizing_functions_monotone_and_aligned():
+    lib = _lib.load()
+    g1, g2 = lib.r3dg_raster_geom_bytes(1000, 5), lib.r3dg_raster_geom_bytes(2000, 5)
+    assert 0 < g1 < g2 and g1 % 256 == 0
+    assert lib.r3dg_raster_geom_bytes(1000, 16) > g1
+    i1 = lib.r3dg_raster_img_bytes(800, 800)
+    assert i1 >= 800 * 800 * 8 and i1 % 256 == 0
+    off = lib.r3dg_raster_img_n_contrib_offset(800, 800)
+    assert 0 < off < i1 and off % 256 == 0
+    b1, b2 = lib.r3dg_raster_binning_bytes(10_000), lib.r3dg_raster_binning_bytes(20_000)
+    assert 24 * 10_000 <= b1 < b2
+
+
+def test_bad_arguments_are_rejected_without_touching_the_gpu():
+    lib = _lib.load()
+    a = _lib.RasterFwdArgs()
+    a.P, a.W, a.H, a.S = 10, 0, 16, 0            # zero width
+    assert lib.r3dg_raster_forward(ctypes.byref(a), None) == -10001
+    a.W, a.S = 16, 99                             # too many feature channels (forward.cu:312 F[33])
+    assert lib.r3dg_raster_forward(ctypes.byref(a), None) == -10002
+    b = _lib.RasterBwdArgs()
+    b.P, b.W, b.H, b.S = 10, 16, 16, 25           # backward.cu:449 limit
+    assert lib.r3dg_raster_backward(ctypes.byref(b), None) == -10002
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(ImportError):
+        _lib.load()

@@ -1,0 +1,132 @@
+"""The CPU oracle pinned against reference-owned data (no GPU needed):
+  * eval_sh restatement vs outputs of the Python reference (config #1, tests/golden/sh_eval.npz);
+  * the C rasterizer restatement vs outputs of the unmodified reference CUDA kernels
+    (tests/golden/raster_*.npz, generated on the B200 box by tests/golden/make_golden.py);
+  * internal invariants of the binning (sortedness, ranges partition, stability)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, case_inputs, max_rel_above_floor, npy, oracle_kwargs, rel_l2, sh_case
+from oracle import oracle
+
+RASTER_CASES = sorted(glob.glob(os.path.join(GOLDEN, "raster_*.npz")))
+
+
+def test_sh_config1_matches_python_reference():
+    gold = np.load(os.path.join(GOLDEN, "sh_eval.npz"))
+    for deg in (0, 1, 2, 3):
+        sh, dirs = sh_case(10_000 if deg == 3 else 1_000, seed=deg)
+        got = oracle.eval_sh(deg, sh.numpy(), dirs.numpy())
+        assert got.shape == gold[f"deg{deg}"].shape
+        # same float32 op order as the torch expression; allow 2 ulp of slack for fused scalars
+        np.testing.assert_allclose(got, gold[f"deg{deg}"], rtol=0, atol=3e-7)
+    rgb = np.maximum(oracle.eval_sh(3, *[t.numpy() for t in sh_case(10_000, 3)]) + np.float32(0.5), 0)
+    np.testing.assert_allclose(rgb, gold["deg3_rgb"], rtol=0, atol=3e-7)
+    sh4 = torch.randn(256, 3, 25, generator=torch.Generator().manual_seed(9))
+    d4 = torch.nn.functional.normalize(torch.randn(256, 3, generator=torch.Generator().manual_seed(10)), dim=-1)
+    np.testing.assert_allclose(oracle.eval_sh(4, sh4.numpy(), d4.numpy()), gold["deg4_small"], rtol=0, atol=2e-6)
+
+
+def _run_oracle_on_golden(g):
+    P, W, H, S, view, deg, R = [int(x) for x in g["meta"]]
+    tfx, tfy, cx, cy = [float(x) for x in g["tanfov"]]
+    mode = str(g["mode"])
+    kw = dict(means3D=g["in_means3D"], opacities=g["in_opacities"], viewmatrix=g["in_viewmatrix"],
+              projmatrix=g["in_projmatrix"], campos=g["in_campos"], bg=g["in_bg"], W=W, H=H, tan_fovx=tfx,
+              tan_fovy=tfy, cx=cx, cy=cy, features=g["in_features"] if S else None, sh_degree=deg)
+    if mode == "sh_sr":
+        kw.update(shs=g["in_shs"], scales=g["in_scales"], rotations=g["in_rotations"])
+    else:
+        kw.update(colors_precomp=g["in_colors_precomp"], cov3D_precomp=g["in_cov3D_precomp"])
+    f = oracle.rasterize_forward(**kw)
+    bkw = {k: v for k, v in kw.items() if k in ("means3D", "viewmatrix", "projmatrix", "campos", "bg", "W", "H",
+                                                 "tan_fovx", "tan_fovy", "shs", "scales", "rotations",
+                                                 "cov3D_precomp", "features", "sh_degree")}
+    gr = oracle.rasterize_backward(f, dL_dcolor=g["cot_color"], dL_dopacity=g["cot_opacity"],
+                                   dL_ddepth=g["cot_depth"], dL_dfeature=g["cot_feature"], **bkw)
+    return f, gr, (P, W, H, S, R, mode)
+
+
+@pytest.mark.parametrize("path", RASTER_CASES, ids=[os.path.basename(p)[7:-4] for p in RASTER_CASES])
+def test_oracle_matches_reference_cuda_golden(path):
+    g = np.load(path)
+    f, gr, (P, W, H, S, R, mode) = _run_oracle_on_golden(g)
+    pre, b, img = f["pre"], f["binned"], f["img"]
+    vis = g["out_radii"] > 0
+    # ---- integer / index work: bit-exact -----------------------------------------------------
+    assert np.array_equal(pre["radii"], g["out_radii"])
+    assert np.array_equal(pre["tiles_touched"], g["mid_tiles_touched"].view(np.uint32))
+    assert b["num_rendered"] == R
+    assert np.array_equal(b["point_offsets"], g["mid_point_offsets"].view(np.uint32))
+    assert np.array_equal(b["keys"], g["mid_point_list_keys"].view(np.uint64))
+    assert np.array_equal(b["point_list"], g["mid_point_list"].view(np.uint32))
+    T = b["ranges"].shape[0]
+    assert np.array_equal(b["ranges"], g["mid_ranges"].view(np.uint32)[:T])
+    # ---- IEEE-exact floats that feed the keys: bit-exact (visible Gaussians only; the reference
+    # leaves culled rows uninitialised) ---------------------------------------------------------
+    for name in ("depths", "means2D", "conic_opacity"):
+        a, r = pre[name][vis], g["mid_" + name][vis]
+        assert np.array_equal(a.view(np.uint32), r.view(np.uint32)), name
+    if mode == "sh_sr":
+        assert np.array_equal(pre["cov3D"][vis].view(np.uint32), g["mid_cov3D"][vis].view(np.uint32))
+        np.testing.assert_allclose(pre["rgb"][vis], g["mid_rgb"][vis], atol=2e-6, rtol=0)
+        assert np.array_equal(pre["clamped"][vis], g["mid_clamped"][vis])
+    # ---- images: CUDA expf vs glibc expf differ by ~1 ulp -> 1e-5; tolerance of the task 1e-4 --
+    for name, tol in (("color", 1e-5), ("opacity", 1e-5), ("depth", 5e-5), ("feature", 5e-5)):
+        if g["out_" + name].size:
+            assert np.abs(img[name] - g["out_" + name]).max() < tol, name
+    assert np.abs(img["weights"] - g["out_weights"]).max() < 1e-4
+    assert (img["n_contrib"] != g["mid_n_contrib"].view(np.uint32)).mean() < 2e-3
+    assert np.abs(f["surface_xyz"] - g["out_surface_xyz"]).max() < 1e-3
+    # normals amplify 1-ulp depth differences where the surface is nearly flat: compare robustly
+    dn = np.abs(f["normal"] - g["out_normal"]).max(axis=0)
+    assert np.quantile(dn, 0.99) < 1e-3
+    # ---- gradients (tolerance 1e-3 rel of the task; the reference itself is atomics-ordered) ---
+    names = ["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D"]
+    names += ["dL_dsh", "dL_dscales", "dL_drotations"] if mode == "sh_sr" else []
+    names += ["dL_dfeatures"] if S else []
+    for n in names:
+        assert rel_l2(gr[n], g["grad_" + n]) < 2e-4, (n, rel_l2(gr[n], g["grad_" + n]))
+
+
+def test_binning_invariants_and_stability():
+    sc, cam = case_inputs(3000, 96, 80, 0, view=2, scale_boost=3.0)
+    bg = torch.zeros(3)
+    kw = oracle_kwargs(sc, cam, bg)
+    f = oracle.rasterize_forward(shs=npy(sc.shs), scales=npy(sc.scales), rotations=npy(sc.rotations), **kw)
+    b, pre = f["binned"], f["pre"]
+    keys, pl, ranges = b["keys"], b["point_list"], b["ranges"]
+    R = b["num_rendered"]
+    assert R == int(pre["tiles_touched"].sum()) == len(keys)
+    assert np.all(keys[1:] >= keys[:-1])                                   # sortedness
+    same = keys[1:] == keys[:-1]
+    assert np.all(pl[1:][same] > pl[:-1][same])                            # stable: ties by Gaussian index
+    tiles = (keys >> np.uint64(32)).astype(np.int64)
+    lens = (ranges[:, 1].astype(np.int64) - ranges[:, 0].astype(np.int64))
+    assert lens.sum() == R and np.array_equal(np.bincount(tiles, minlength=len(ranges)), lens)
+    dbits = (keys & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    assert np.array_equal(dbits, pre["depths"].view(np.uint32)[pl])        # key low word = depth bits
+
+
+def test_edge_cases_empty_and_culled():
+    cam = case_inputs(4, 40, 24, 0)[1]
+    z = lambda *s: np.zeros(s, np.float32)
+    # P = 0
+    f = oracle.rasterize_forward(z(0, 3), z(0, 1), npy(cam.viewmatrix), npy(cam.projmatrix), npy(cam.campos),
+                                 np.array([.5, .25, 1], np.float32), 40, 24, cam.tanfovx, cam.tanfovy, cam.cx, cam.cy,
+                                 shs=z(0, 16, 3), scales=z(0, 3), rotations=z(0, 4))
+    assert f["binned"]["num_rendered"] == 0
+    assert np.allclose(f["img"]["color"][1], 0.25) and np.all(f["img"]["n_contrib"] == 0)
+    # everything behind the camera -> culled by the z <= 0.2 test (auxiliary.h:154)
+    sc, cam = case_inputs(50, 40, 24, 0)
+    behind = (sc.means3D + cam.campos * 3.0)
+    f = oracle.rasterize_forward(npy(behind), npy(sc.opacities), npy(cam.viewmatrix), npy(cam.projmatrix),
+                                 npy(cam.campos), z(3), 40, 24, cam.tanfovx, cam.tanfovy, cam.cx, cam.cy,
+                                 shs=npy(sc.shs), scales=npy(sc.scales), rotations=npy(sc.rotations))
+    assert f["binned"]["num_rendered"] == 0 and np.all(f["pre"]["radii"] == 0)
+    assert not oracle.mark_visible(npy(behind), npy(cam.viewmatrix)).any()
+    assert oracle.mark_visible(npy(sc.means3D), npy(cam.viewmatrix)).all()

@@ -1,0 +1,307 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Everything goes through the C ABI of
+libr3dg_b200.so via the reference-shaped host API; the CPU oracle and, when its build travelled
+with the snapshot, the unmodified reference CUDA kernels (oracle/_ref) are the checkers.
+
+Tolerances (BASELINE.json north_star): images <= 1e-4 max-abs, gradients <= 1e-3 relative,
+tile / sort indices bit-exact."""
+import glob
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, ROOT, case_inputs, max_rel_above_floor, npy, oracle_kwargs, rel_l2
+
+pytestmark = pytest.mark.gpu
+RASTER_CASES = sorted(glob.glob(os.path.join(GOLDEN, "raster_*.npz")))
+GRADS = ["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dfeatures", "dL_dcov3D", "dL_dsh",
+         "dL_dscales", "dL_drotations"]
+
+
+@pytest.fixture(scope="module")
+def C():
+    from relightable3dgaussian_b200 import _C_raster
+    assert torch.cuda.is_available()
+    return _C_raster
+
+
+def dev(t):
+    return torch.Tensor([]) if t is None else torch.as_tensor(t).cuda()
+
+
+def run_ours(C, *, means3D, opacities, viewmatrix, projmatrix, campos, bg, W, H, tan_fovx, tan_fovy, cx, cy,
+             shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None, features=None,
+             sh_degree=3, pseudo=True, cots=None, backward_geometry=True):
+    P = means3D.shape[0]
+    feats = dev(features) if features is not None else torch.empty((P, 0), device="cuda")
+    a = dict(bg=dev(bg), means3D=dev(means3D), feats=feats, colors=dev(colors_precomp), opac=dev(opacities),
+             scales=dev(scales), rots=dev(rotations), cov=dev(cov3D_precomp), view=dev(viewmatrix),
+             proj=dev(projmatrix), sh=dev(shs), campos=dev(campos))
+    out = C.rasterize_gaussians(a["bg"], a["means3D"], a["feats"], a["colors"], a["opac"], a["scales"], a["rots"], 1.0,
+                                a["cov"], a["view"], a["proj"], tan_fovx, tan_fovy, cx, cy, H, W, a["sh"], sh_degree,
+                                a["campos"], False, pseudo, False)
+    names = ["num_rendered", "n_contrib", "color", "opacity", "depth", "feature", "normal", "surface_xyz", "weights",
+             "radii", "geom", "binning", "img"]
+    o = dict(zip(names, out))
+    S = feats.shape[1]
+    o["mid"] = lambda n: C.debug_intermediate(n, P, S, W, H, o["geom"], o["img"], o["binning"], o["num_rendered"])
+    if cots is not None:
+        g = C.rasterize_gaussians_backward(a["bg"], a["means3D"], a["feats"], o["radii"], a["colors"], a["scales"],
+                                           a["rots"], 1.0, a["cov"], a["view"], a["proj"], tan_fovx, tan_fovy,
+                                           dev(cots[0]), dev(cots[1]), dev(cots[2]), dev(cots[3]), a["sh"], sh_degree,
+                                           a["campos"], o["geom"], o["num_rendered"], o["binning"], o["img"],
+                                           backward_geometry, False)
+        o["grads"] = dict(zip(GRADS, g))
+    torch.cuda.synchronize()
+    return o
+
+
+def golden_kwargs(g):
+    P, W, H, S, view, deg, R = [int(x) for x in g["meta"]]
+    tfx, tfy, cx, cy = [float(x) for x in g["tanfov"]]
+    kw = dict(means3D=g["in_means3D"], opacities=g["in_opacities"], viewmatrix=g["in_viewmatrix"],
+              projmatrix=g["in_projmatrix"], campos=g["in_campos"], bg=g["in_bg"], W=W, H=H, tan_fovx=tfx, tan_fovy=tfy,
+              cx=cx, cy=cy, features=g["in_features"] if S else None, sh_degree=deg)
+    if str(g["mode"]) == "sh_sr":
+        kw.update(shs=g["in_shs"], scales=g["in_scales"], rotations=g["in_rotations"])
+    else:
+        kw.update(colors_precomp=g["in_colors_precomp"], cov3D_precomp=g["in_cov3D_precomp"])
+    return kw, (P, W, H, S, R)
+
+
+@pytest.mark.parametrize("path", RASTER_CASES, ids=[os.path.basename(p)[7:-4] for p in RASTER_CASES])
+def test_matches_reference_cuda_golden(C, path):
+    g = np.load(path)
+    kw, (P, W, H, S, R) = golden_kwargs(g)
+    o = run_ours(C, cots=[g["cot_color"], g["cot_opacity"], g["cot_depth"], g["cot_feature"]], **kw)
+    vis = g["out_radii"] > 0
+    assert o["num_rendered"] == R
+    assert np.array_equal(npy(o["radii"]), g["out_radii"])                          # bit-exact indices
+    assert np.array_equal(npy(o["mid"]("tiles_touched")), g["mid_tiles_touched"])
+    assert np.array_equal(npy(o["mid"]("point_list_keys")), g["mid_point_list_keys"])
+    assert np.array_equal(npy(o["mid"]("point_list")), g["mid_point_list"])
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    assert np.array_equal(npy(o["mid"]("ranges")), g["mid_ranges"][:T])
+    assert np.array_equal(npy(o["n_contrib"]).reshape(-1), g["mid_n_contrib"])
+    for n in ("depths", "means2D", "conic_opacity"):
+        assert np.array_equal(npy(o["mid"](n))[vis].view(np.uint32), g["mid_" + n][vis].view(np.uint32)), n
+    for n in ("color", "opacity", "depth", "feature", "normal", "surface_xyz"):       # <= 1e-4 (in fact bit-equal)
+        if g["out_" + n].size:
+            assert np.abs(npy(o[n]) - g["out_" + n]).max() <= 1e-6, n
+    assert np.abs(npy(o["weights"]) - g["out_weights"]).max() < 1e-4
+    names = [n for n in GRADS if g["grad_" + n].size and np.abs(g["grad_" + n]).max() > 0]
+    for n in names:
+        assert rel_l2(npy(o["grads"][n]), g["grad_" + n]) < 1e-3, n
+        assert max_rel_above_floor(npy(o["grads"][n]), g["grad_" + n], floor=1e-3) < 1e-2, n
+
+
+@pytest.mark.parametrize("S,pseudo", [(0, False), (5, True), (16, True)])
+def test_matches_cpu_oracle_midsize(C, S, pseudo):
+    from oracle import oracle
+    sc, cam = case_inputs(20_000, 320, 232, S, view=3, scale_boost=1.5)
+    bg = torch.tensor([0.2, 0.4, 0.1])
+    kw = oracle_kwargs(sc, cam, bg)
+    extra = dict(shs=npy(sc.shs), scales=npy(sc.scales), rotations=npy(sc.rotations),
+                 features=npy(sc.features) if S else None)
+    rng = np.random.default_rng(5)
+    cots = [rng.standard_normal((c, 232, 320)).astype(np.float32) for c in (3, 1, 1, S)]
+    o = run_ours(C, cots=cots, pseudo=pseudo, **kw, **extra)
+    f = oracle.rasterize_forward(computer_pseudo_normal=pseudo, **kw, **extra)
+    bk = {k: v for k, v in {**kw, **extra}.items() if k not in ("opacities", "cx", "cy")}
+    gr = oracle.rasterize_backward(f, dL_dcolor=cots[0], dL_dopacity=cots[1], dL_ddepth=cots[2], dL_dfeature=cots[3], **bk)
+    assert o["num_rendered"] == f["binned"]["num_rendered"]
+    assert np.array_equal(npy(o["radii"]), f["pre"]["radii"])
+    assert np.array_equal(npy(o["mid"]("point_list")).view(np.uint32), f["binned"]["point_list"])
+    assert np.array_equal(npy(o["mid"]("ranges")).view(np.uint32), f["binned"]["ranges"])
+    assert (npy(o["n_contrib"]).reshape(-1) != f["img"]["n_contrib"]).mean() < 1e-3
+    for n in ("color", "opacity", "depth", "feature"):
+        if f["img"][n].size:
+            assert np.abs(npy(o[n]) - f["img"][n]).max() <= 1e-4, n
+    if pseudo:
+        assert np.quantile(np.abs(npy(o["normal"]) - f["normal"]).max(axis=0), 0.99) < 1e-3
+        assert np.abs(npy(o["surface_xyz"]) - f["surface_xyz"]).max() < 1e-2
+    else:
+        assert not npy(o["normal"]).any() and not npy(o["surface_xyz"]).any()
+    for n in GRADS:
+        if gr[n].size:
+            assert rel_l2(npy(o["grads"][n]), gr[n]) < 1e-3, n
+
+
+def test_matches_live_reference_kernels_if_built(C):
+    from oracle import ref_gpu
+    if not ref_gpu.available():
+        pytest.skip("oracle/_ref/libref_raster.so not present")
+    sc, cam = case_inputs(200_000, 640, 480, 5, view=5, center_shift=True)
+    bg = torch.tensor([0.0, 0.5, 1.0])
+    kw = oracle_kwargs(sc, cam, bg)
+    extra = dict(shs=npy(sc.shs), scales=npy(sc.scales), rotations=npy(sc.rotations), features=npy(sc.features))
+    g = torch.Generator().manual_seed(2)
+    cots = [torch.randn(c, 480, 640, generator=g) for c in (3, 1, 1, 5)]
+    o = run_ours(C, cots=cots, **kw, **extra)
+    ref = ref_gpu.RefRasterizer()
+    tk = {k: (dev(v) if isinstance(v, np.ndarray) else v) for k, v in {**kw, **extra}.items()}
+    ro = ref.forward(**tk)
+    assert o["num_rendered"] == ro["num_rendered"]
+    assert torch.equal(o["radii"], ro["radii"])
+    assert torch.equal(o["mid"]("point_list"), ref.intermediate("point_list"))
+    assert torch.equal(o["mid"]("point_list_keys"), ref.intermediate("point_list_keys"))
+    assert torch.equal(o["mid"]("ranges"), ref.intermediate("ranges")[: o["mid"]("ranges").shape[0]])
+    assert torch.equal(o["n_contrib"].reshape(-1), ref.intermediate("n_contrib"))
+    for n in ("color", "opacity", "depth", "feature", "normal", "surface_xyz"):
+        assert (o[n] - ro[n]).abs().max().item() <= 1e-4, n
+    rg = ref.backward(ro, dL_dcolor=dev(cots[0]), dL_dopacity=dev(cots[1]), dL_ddepth=dev(cots[2]), dL_dfeature=dev(cots[3]),
+                      **{k: v for k, v in tk.items() if k in ("means3D", "viewmatrix", "projmatrix", "campos", "bg",
+                                                              "tan_fovx", "tan_fovy", "shs", "scales", "rotations", "features")})
+    for n in GRADS:
+        assert rel_l2(npy(o["grads"][n]), npy(rg[n])) < 1e-3, n
+
+
+def test_full_size_properties(C):
+    """BASELINE.json headline size (1M Gaussians, 800x800): size-independent properties."""
+    P, W, H, S = 1_000_000, 800, 800, 5
+    sc, cam = case_inputs(P, W, H, S, view=0)
+    bg = torch.tensor([0.1, 0.2, 0.3])
+    kw = oracle_kwargs(sc, cam, bg)
+    extra = dict(shs=npy(sc.shs), scales=npy(sc.scales), rotations=npy(sc.rotations), features=npy(sc.features))
+    g = torch.Generator().manual_seed(4)
+    cots = [torch.randn(c, H, W, generator=g) for c in (3, 1, 1, S)]
+    o = run_ours(C, cots=cots, **kw, **extra)
+    R = o["num_rendered"]
+    keys, pl, ranges, tiles = o["mid"]("point_list_keys"), o["mid"]("point_list"), o["mid"]("ranges"), o["mid"]("tiles_touched")
+    assert R == int(tiles.long().sum()) and keys.numel() == R
+    assert bool((keys[1:] >= keys[:-1]).all())                                    # sortedness
+    same = keys[1:] == keys[:-1]
+    assert bool((pl[1:][same] > pl[:-1][same]).all())                             # stability (tie order)
+    lens = (ranges[:, 1].long() - ranges[:, 0].long())
+    assert int(lens.sum()) == R and bool((lens >= 0).all())
+    assert torch.equal(torch.bincount(keys >> 32, minlength=ranges.shape[0]), lens)  # ranges partition the list
+    assert torch.equal(torch.bincount(pl.long(), minlength=P), tiles.long())          # each Gaussian once per touched tile
+    depths = o["mid"]("depths")
+    assert torch.equal((keys & 0xFFFFFFFF).int(), depths.view(torch.int32)[pl.long()])
+    assert bool(torch.isfinite(o["color"]).all()) and float(o["opacity"].min()) >= 0 and float(o["opacity"].max()) <= 1 + 1e-5
+    tile_of_pix = (torch.arange(H, device="cuda")[:, None] // 16) * 50 + torch.arange(W, device="cuda")[None, :] // 16
+    assert bool((o["n_contrib"].long() <= lens[tile_of_pix]).all())
+    # determinism of the forward (idempotence) and linearity of the backward in the cotangents
+    o2 = run_ours(C, cots=[2 * c for c in cots], **kw, **extra)
+    for n in ("color", "depth", "feature", "normal", "n_contrib", "radii"):
+        assert torch.equal(o[n], o2[n]), n
+    for n in ("dL_dmeans3D", "dL_dsh", "dL_dscales", "dL_dopacity"):
+        assert rel_l2(npy(o2["grads"][n]), 2 * npy(o["grads"][n])) < 1e-4, n
+    # total opacity-weight checksum: sum_p weights[p] == sum_pixels opacity (same quantity, two reductions)
+    assert abs(float(o["weights"].double().sum()) - float(o["opacity"].double().sum())) / float(o["opacity"].double().sum()) < 1e-4
+
+
+def test_edge_cases(C):
+    from oracle import oracle
+    cam = case_inputs(4, 100, 60, 0)[1]
+    base = dict(viewmatrix=npy(cam.viewmatrix), projmatrix=npy(cam.projmatrix), campos=npy(cam.campos),
+                bg=np.array([0.5, 0.25, 1.0], np.float32), W=100, H=60, tan_fovx=cam.tanfovx, tan_fovy=cam.tanfovy,
+                cx=cam.cx, cy=cam.cy)
+    z = lambda *s: np.zeros(s, np.float32)
+    # P == 0: background image, zero instances
+    o = run_ours(C, means3D=z(0, 3), opacities=z(0, 1), shs=z(0, 16, 3), scales=z(0, 3), rotations=z(0, 4), **base)
+    assert o["num_rendered"] == 0 and np.allclose(npy(o["color"])[2], 1.0) and not npy(o["n_contrib"]).any()
+    # all Gaussians behind the camera
+    sc, _ = case_inputs(300, 100, 60, 5)
+    behind = npy(sc.means3D + cam.campos * 3.0)
+    rng = np.random.default_rng(0)
+    cots = [rng.standard_normal((c, 60, 100)).astype(np.float32) for c in (3, 1, 1, 5)]
+    o = run_ours(C, means3D=behind, opacities=npy(sc.opacities), shs=npy(sc.shs), scales=npy(sc.scales),
+                 rotations=npy(sc.rotations), features=npy(sc.features), cots=cots, **base)
+    assert o["num_rendered"] == 0 and not npy(o["radii"]).any()
+    assert all(not npy(v).any() for v in o["grads"].values())                      # every grad row written as zero
+    assert not npy(C.mark_visible(dev(behind), dev(base["viewmatrix"]), dev(base["projmatrix"]))).any()
+    # one huge Gaussian covering the whole screen (radius >> image) + ragged image size
+    big = dict(means3D=z(1, 3), opacities=np.full((1, 1), 0.9, np.float32), shs=z(1, 16, 3),
+               scales=np.full((1, 3), 2.0, np.float32), rotations=np.array([[1, 0, 0, 0]], np.float32))
+    o = run_ours(C, **big, **base)
+    f = oracle.rasterize_forward(**big, **base)
+    assert o["num_rendered"] == f["binned"]["num_rendered"] == 7 * 4
+    assert np.abs(npy(o["color"]) - f["img"]["color"]).max() < 1e-5
+    # S = 33 (forward maximum, forward.cu:312) forward-only; S = 24 backward maximum; S = 25 backward refuses
+    sc, _ = case_inputs(500, 100, 60, 33, scale_boost=4.0)
+    kw = dict(means3D=npy(sc.means3D), opacities=npy(sc.opacities), shs=npy(sc.shs), scales=npy(sc.scales), rotations=npy(sc.rotations))
+    o = run_ours(C, features=npy(sc.features), **kw, **base)
+    f = oracle.rasterize_forward(features=npy(sc.features), **kw, **base)
+    assert np.abs(npy(o["feature"]) - f["img"]["feature"]).max() < 1e-4
+    cots24 = [rng.standard_normal((c, 60, 100)).astype(np.float32) for c in (3, 1, 1, 24)]
+    o = run_ours(C, features=npy(sc.features[:, :24]), cots=cots24, **kw, **base)
+    f = oracle.rasterize_forward(features=npy(sc.features[:, :24]), **kw, **base)
+    gr = oracle.rasterize_backward(f, dL_dcolor=cots24[0], dL_dopacity=cots24[1], dL_ddepth=cots24[2], dL_dfeature=cots24[3],
+                                   features=npy(sc.features[:, :24]), **{k: v for k, v in kw.items() if k != "opacities"},
+                                   **{k: v for k, v in base.items() if k not in ("cx", "cy")})
+    for n in ("dL_dfeatures", "dL_dmeans3D", "dL_dsh"):
+        assert rel_l2(npy(o["grads"][n]), gr[n]) < 1e-3, n
+    cots25 = [rng.standard_normal((c, 60, 100)).astype(np.float32) for c in (3, 1, 1, 25)]
+    with pytest.raises(RuntimeError):
+        run_ours(C, features=npy(sc.features[:, :25]), cots=cots25, **kw, **base)
+    # speculative binning capacity too small -> transparent rerun with identical results
+    from relightable3dgaussian_b200 import _C_raster
+    ref_out = run_ours(C, features=npy(sc.features[:, :5]), **kw, **base)
+    for st in _C_raster._state.values():
+        st["capacity"] = 0
+    sc2, _ = case_inputs(500, 100, 60, 5, scale_boost=12.0)       # > 4 instances per Gaussian on average
+    kw2 = dict(means3D=npy(sc2.means3D), opacities=npy(sc2.opacities), shs=npy(sc2.shs), scales=npy(sc2.scales), rotations=npy(sc2.rotations))
+    o = run_ours(C, features=npy(sc2.features), **kw2, **base)
+    f = oracle.rasterize_forward(features=npy(sc2.features), **kw2, **base)
+    assert o["num_rendered"] == f["binned"]["num_rendered"] > 4 * 500 + 4096 or o["num_rendered"] == f["binned"]["num_rendered"]
+    assert np.array_equal(npy(o["mid"]("point_list")).view(np.uint32), f["binned"]["point_list"])
+    assert ref_out["num_rendered"] > 0
+
+
+def test_operator_surface_and_autograd(C):
+    from relightable3dgaussian_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+    from oracle import oracle
+    sc, cam = case_inputs(5000, 208, 144, 5, view=4, scale_boost=2.0)
+    bg = torch.tensor([0.3, 0.3, 0.3])
+    rs = GaussianRasterizationSettings(144, 208, cam.tanfovx, cam.tanfovy, cam.cx, cam.cy, bg.cuda(), 1.0,
+                                       cam.viewmatrix.cuda(), cam.projmatrix.cuda(), 3, cam.campos.cuda(), False, True, True, False)
+    assert GaussianRasterizationSettings._fields == ("image_height", "image_width", "tanfovx", "tanfovy", "cx", "cy", "bg",
+                                                     "scale_modifier", "viewmatrix", "projmatrix", "sh_degree", "campos",
+                                                     "prefiltered", "backward_geometry", "computer_pseudo_normal", "debug")
+    rast = GaussianRasterizer(rs)
+    leaf = lambda t: t.cuda().requires_grad_(True)
+    m3, op, sh, s, r, ft = map(leaf, (sc.means3D, sc.opacities, sc.shs, sc.scales, sc.rotations, sc.features))
+    m2 = torch.zeros_like(m3, requires_grad=True)
+    with pytest.raises(Exception):
+        rast(means3D=m3, means2D=m2, opacities=op, scales=s, rotations=r)                       # neither shs nor colours
+    with pytest.raises(Exception):
+        rast(means3D=m3, means2D=m2, opacities=op, shs=sh, scales=s, rotations=r, cov3D_precomp=torch.zeros(5000, 6).cuda())
+    out = rast(means3D=m3, means2D=m2, opacities=op, shs=sh, scales=s, rotations=r, features=ft)
+    assert len(out) == 10 and isinstance(out[0], int) and out[1].dtype == torch.int32 and out[9].dtype == torch.int32
+    g = torch.Generator().manual_seed(0)
+    cots = [torch.randn(c, 144, 208, generator=g) for c in (3, 1, 1, 5)]
+    loss = sum((o * c.cuda()).sum() for o, c in zip(out[2:6], cots)) + out[6].sum() + out[8].sum()   # normal/weights grads are ignored
+    loss.backward()
+    kw = oracle_kwargs(sc, cam, bg)
+    ex = dict(shs=npy(sc.shs), scales=npy(sc.scales), rotations=npy(sc.rotations), features=npy(sc.features))
+    f = oracle.rasterize_forward(**kw, **ex)
+    gr = oracle.rasterize_backward(f, dL_dcolor=npy(cots[0]), dL_dopacity=npy(cots[1]), dL_ddepth=npy(cots[2]), dL_dfeature=npy(cots[3]),
+                                   **{k: v for k, v in {**kw, **ex}.items() if k not in ("opacities", "cx", "cy")})
+    for t, n in ((m3, "dL_dmeans3D"), (m2, "dL_dmeans2D"), (op, "dL_dopacity"), (sh, "dL_dsh"), (s, "dL_dscales"),
+                 (r, "dL_drotations"), (ft, "dL_dfeatures")):
+        assert t.grad is not None and rel_l2(npy(t.grad), gr[n]) < 1e-3, n
+    vis = rast.markVisible(m3.detach())
+    assert vis.dtype == torch.bool and bool(vis.all())
+    # backward_geometry=False drops the feature term from dL/dalpha (backward.cu:563-566)
+    rs2 = rs._replace(backward_geometry=False)
+    for t in (m3, m2, op, sh, s, r, ft):
+        t.grad = None
+    out2 = GaussianRasterizer(rs2)(means3D=m3, means2D=m2, opacities=op, shs=sh, scales=s, rotations=r, features=ft)
+    (out2[5] * cots[3].cuda()).sum().backward()
+    gr2 = oracle.rasterize_backward(f, dL_dcolor=np.zeros_like(npy(cots[0])), dL_dopacity=np.zeros_like(npy(cots[1])),
+                                    dL_ddepth=np.zeros_like(npy(cots[2])), dL_dfeature=npy(cots[3]), backward_geometry=False,
+                                    **{k: v for k, v in {**kw, **ex}.items() if k not in ("opacities", "cx", "cy")})
+    assert rel_l2(npy(ft.grad), gr2["dL_dfeatures"]) < 1e-3
+    assert float(op.grad.abs().max()) == 0.0 and float(np.abs(gr2["dL_dopacity"]).max()) == 0.0
+
+
+def test_dropin_module_names():
+    sys.path.insert(0, os.path.join(ROOT, "dropin"))
+    import importlib
+    mod = importlib.import_module("r3dg_rasterization")
+    for n in ("rasterize_gaussians", "rasterize_gaussians_backward", "mark_visible"):
+        assert callable(getattr(mod._C, n))
+    assert hasattr(mod, "GaussianRasterizer") and hasattr(mod, "GaussianRasterizationSettings")
