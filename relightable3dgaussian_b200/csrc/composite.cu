@@ -34,9 +34,11 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const CompositeFwdPa
     __shared__ float4 sA[256], sB[256];
     __shared__ float4 sC[NG][256];
     __shared__ int sId[256];
+    __shared__ uint32_t sBits[8][8];          // [pixel block (= consumer warp)][32-entry group of the batch]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
     const int tx = tile % p.gx, ty = tile / p.gx;
+    const float tile_x0 = (float)(tx * R3DG_TILE), tile_y0 = (float)(ty * R3DG_TILE);
     const int px = tx * R3DG_TILE + (warp & 1) * 8 + (lane & 7);
     const int py = ty * R3DG_TILE + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = px < p.W && py < p.H;
@@ -50,24 +52,37 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const CompositeFwdPa
     float C[4 * NG];
 #pragma unroll
     for (int i = 0; i < 4 * NG; ++i) C[i] = 0.0f;
-    uint32_t contributor = 0, last_contributor = 0;
+    uint32_t last_contributor = 0;
     bool done = !inside;
 
     for (int base = 0; base < toDo; base += 256) {
         if (__syncthreads_and(done)) break;
         const int n = min(256, toDo - base);
+        unsigned tm = 0u;
         if (tid < n) {
             const uint32_t id = p.point_list[range.x + base + tid];
             const float4* r = rec4 + (size_t)id * rec4n;
+            const float4 A = r[0], B = r[1];
             sId[tid] = (int)id;
-            sA[tid] = r[0];
-            sB[tid] = r[1];
+            sA[tid] = A;
+            sB[tid] = B;
 #pragma unroll
             for (int g = 0; g < NG; ++g) sC[g][tid] = r[2 + g];
+            tm = touch_mask(A, B, tile_x0, tile_y0);
+        }
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t word = __ballot_sync(0xffffffffu, (tm >> w) & 1u);
+            if (lane == 0) sBits[w][warp] = word;
         }
         __syncthreads();
         if (__all_sync(0xffffffffu, done)) continue;
-        for (int j = 0; j < n; ++j) {
+        bool warp_done = false;
+        for (int k = 0; k < 8 && !warp_done; ++k) {
+          uint32_t word = sBits[warp][k];
+          while (word) {
+            const int j = k * 32 + __ffs(word) - 1;
+            word &= word - 1;
             const float4 a = sA[j];
             const float4 b = sB[j];
             const float dx = sub_(a.x, pxf), dy = sub_(a.y, pyf);
@@ -77,7 +92,6 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const CompositeFwdPa
             const float alpha = fminf(0.99f, mul_(b.y, expf(power)));
             const float test_T = mul_(T, sub_(1.0f, alpha));
             bool valid = !done && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-            if (!done) contributor++;
             if (valid && test_T < 0.0001f) { done = true; valid = false; }
             float w = 0.0f;
             if (valid) {
@@ -93,14 +107,15 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const CompositeFwdPa
                 Dp = fma_(w, b.z, Dp);
                 Op = add_(Op, w);
                 T = test_T;
-                last_contributor = contributor;
+                last_contributor = (uint32_t)(base + j + 1);      // 1-based position in the tile list
             }
             if (__any_sync(0xffffffffu, valid)) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
                 if (lane == 0) atomicAdd(&p.out_weights[sId[j]], w);
             }
-            if (__all_sync(0xffffffffu, done)) break;
+            if (__all_sync(0xffffffffu, done)) { warp_done = true; break; }
+          }
         }
     }
     if (inside) {

@@ -61,9 +61,11 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const CompositeBwdPa
     __shared__ float4 sC[NG][256];
     __shared__ int sId[256];
     __shared__ int sMax[8];
+    __shared__ uint32_t sBits[8][8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
     const int tx = tile % p.gx, ty = tile / p.gx;
+    const float tile_x0 = (float)(tx * R3DG_TILE), tile_y0 = (float)(ty * R3DG_TILE);
     const int px = tx * R3DG_TILE + (warp & 1) * 8 + (lane & 7);
     const int py = ty * R3DG_TILE + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = px < p.W && py < p.H;
@@ -108,19 +110,31 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const CompositeBwdPa
     for (int base = 0; base < total; base += 256) {
         __syncthreads();
         const int n = min(256, total - base);
+        unsigned tm = 0u;
         if (tid < n) {
             const uint32_t id = p.point_list[range.x + (total - 1 - (base + tid))];
             const float4* r = rec4 + (size_t)id * rec4n;
+            const float4 A = r[0], B = r[1];
             sId[tid] = (int)id;
-            sA[tid] = r[0];
-            sB[tid] = r[1];
+            sA[tid] = A;
+            sB[tid] = B;
 #pragma unroll
             for (int g = 0; g < NG; ++g) sC[g][tid] = r[2 + g];
+            tm = touch_mask(A, B, tile_x0, tile_y0);
+        }
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t word = __ballot_sync(0xffffffffu, (tm >> w) & 1u);
+            if (lane == 0) sBits[w][warp] = word;
         }
         __syncthreads();
         // this warp can skip the batch if none of its pixels reaches that deep
         if (total - 1 - base - (n - 1) >= wmax) continue;
-        for (int j = 0; j < n; ++j) {
+        for (int kk = 0; kk < 8; ++kk) {
+          uint32_t word = sBits[warp][kk];
+          while (word) {
+            const int j = kk * 32 + __ffs(word) - 1;
+            word &= word - 1;
             const int k = total - 1 - (base + j);            // 0-based list position == contributor
             if (k >= wmax) continue;                         // warp-uniform
             const float4 a = sA[j];
@@ -190,6 +204,7 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const CompositeBwdPa
                 const int comp = lane >> 3;
                 if ((lane & 7) == 0 && V0 + comp < V) atomicAdd(grow + V0 + comp, r1);
             }
+          }
         }
     }
 }

@@ -121,12 +121,10 @@ def main():
                                            sc_dev.shs, 3, cam_dev.campos, o[10], o[0], o[11], o[12], True, False)
         t_ofb = timeit(ours_fb)
         t_rf = timeit(lambda: ref.forward(**kw))
+        bkw = {k: v for k, v in kw.items() if k in ("means3D", "viewmatrix", "projmatrix", "campos", "bg", "tan_fovx", "tan_fovy", "shs", "scales", "rotations", "features")}
         def ref_fb():
             r = ref.forward(**kw)
-            ref.backward(r, means3D=d(sc.means3D), viewmatrix=d(cam.viewmatrix), projmatrix=d(cam.projmatrix),
-                         campos=d(cam.campos), bg=bg, tan_fovx=cam.tanfovx, tan_fovy=cam.tanfovy, dL_dcolor=dc,
-                         dL_dopacity=do, dL_ddepth=dd, dL_dfeature=df, shs=d(sc.shs), scales=d(sc.scales),
-                         rotations=d(sc.rotations), features=d(sc.features) if S else None)
+            ref.backward(r, dL_dcolor=dc, dL_dopacity=do, dL_ddepth=dd, dL_dfeature=df, **bkw)
         t_rfb = timeit(ref_fb)
         print(json.dumps(dict(P=P, R=R, ours_fwd_ms=t_of, ours_fwdbwd_ms=t_ofb, ref_fwd_ms=t_rf, ref_fwdbwd_ms=t_rfb)))
 
