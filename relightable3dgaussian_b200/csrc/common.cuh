@@ -143,41 +143,37 @@ __device__ __forceinline__ void get_rect(float px, float py, int radius, int gx,
 
 // ---------------------------------------------------------------------------------------------
 // Conservative sub-tile culling.  A tile's 16x16 pixels are owned by 8 warps, each a compact 8x4
-// block; bit w of the returned mask is 0 only if NO pixel of block w can pass the reference's
-// per-pair tests (power <= 0 and alpha >= 1/255, forward.cu:345-354) for this Gaussian:
-// alpha >= 1/255  =>  q(d) = a dx^2 + 2b dx dy + c dy^2 <= tau = 2 ln(255 o).  The minimum of the
-// convex quadratic over the block's (continuous) rectangle is found on its four edges; a slack of
-// 1 + 1e-5 * |largest term| (>> fp32 rounding of either evaluation) keeps the test conservative,
-// so skipped pairs are exactly pairs the reference's arithmetic would have rejected and the
-// per-pixel results stay bit-identical.  Non-positive-definite or NaN conics are never culled.
+// pixel block.  touch_block() returns false only if NO pixel of the block whose first pixel is
+// (X0, Y0) can pass the reference's per-pair tests (power <= 0 and alpha >= 1/255,
+// forward.cu:345-354) for this Gaussian:  alpha >= 1/255  =>  q(d) = a dx^2 + 2b dx dy + c dy^2
+// <= tau = 2 ln(255 o).  The minimum of the convex quadratic over the block's (continuous)
+// rectangle is found on its four edges; a slack of 1 + 1e-5 * |largest term| (>> fp32 rounding of
+// either evaluation) keeps the test conservative, so skipped pairs are exactly pairs the
+// reference's arithmetic would have rejected and per-pixel results stay bit-identical.
+// Non-positive-definite or NaN conics are never culled.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned touch_mask(const float4 A, const float4 B, float tile_x0, float tile_y0) {
+__device__ __forceinline__ bool touch_block(const float4 A, const float4 B, float X0, float Y0) {
     const float gx = A.x, gy = A.y, ca = A.z, cb = A.w, cc = B.x, op = B.y;
-    if (op < 1.0f / 255.0f) return 0u;                       // alpha <= op < 1/255 everywhere
-    if (!(ca > 0.0f && cc > 0.0f && ca * cc - cb * cb > 0.0f)) return 0xffu;
-    const float tau = 2.0f * logf(255.0f * op);
-    if (!(tau >= 0.0f)) return 0xffu;                         // NaN opacity etc.
-    const float rc = -cb / cc, ra = -cb / ca;
-    unsigned mask = 0u;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-        const float X0 = tile_x0 + (float)((w & 1) * 8), Y0 = tile_y0 + (float)((w >> 1) * 4);
-        const float u0 = gx - (X0 + 7.0f), u1 = gx - X0, v0 = gy - (Y0 + 3.0f), v1 = gy - Y0;
-        const bool inside = u0 <= 0.0f && u1 >= 0.0f && v0 <= 0.0f && v1 >= 0.0f;
-        auto edge_u = [&](float U) {
-            const float v = fminf(fmaxf(rc * U, v0), v1);
-            return ca * U * U + 2.0f * cb * U * v + cc * v * v;
-        };
-        auto edge_v = [&](float V) {
-            const float u = fminf(fmaxf(ra * V, u0), u1);
-            return ca * u * u + 2.0f * cb * u * V + cc * V * V;
-        };
-        const float qmin = fminf(fminf(edge_u(u0), edge_u(u1)), fminf(edge_v(v0), edge_v(v1)));
-        const float um = fmaxf(fabsf(u0), fabsf(u1)), vm = fmaxf(fabsf(v0), fabsf(v1));
-        const float slack = 1.0f + 1e-5f * (ca * um * um + cc * vm * vm + 2.0f * fabsf(cb) * um * vm);
-        if (inside || !(qmin > tau + slack)) mask |= 1u << w;
-    }
-    return mask;
+    if (op < 1.0f / 255.0f) return false;                    // alpha <= op < 1/255 everywhere
+    if (!(ca > 0.0f && cc > 0.0f && ca * cc - cb * cb > 0.0f)) return true;
+    const float tau = 2.0f * __logf(255.0f * op) ;
+    if (!(tau >= 0.0f)) return true;                          // NaN opacity etc.
+    const float u0 = gx - (X0 + 7.0f), u1 = gx - X0, v0 = gy - (Y0 + 3.0f), v1 = gy - Y0;
+    if (u0 <= 0.0f && u1 >= 0.0f && v0 <= 0.0f && v1 >= 0.0f) return true;   // centre inside the block
+    const float rc = __fdividef(-cb, cc), ra = __fdividef(-cb, ca);
+    auto edge_u = [&](float U) {
+        const float v = fminf(fmaxf(rc * U, v0), v1);
+        return ca * U * U + 2.0f * cb * U * v + cc * v * v;
+    };
+    auto edge_v = [&](float V) {
+        const float u = fminf(fmaxf(ra * V, u0), u1);
+        return ca * u * u + 2.0f * cb * u * V + cc * V * V;
+    };
+    const float qmin = fminf(fminf(edge_u(u0), edge_u(u1)), fminf(edge_v(v0), edge_v(v1)));
+    const float um = fmaxf(fabsf(u0), fabsf(u1)), vm = fmaxf(fabsf(v0), fabsf(v1));
+    // slack also absorbs the approximate log/divide above (relative error ~1e-6 of tau <= ~12)
+    const float slack = 1.0f + 1e-5f * (ca * um * um + cc * vm * vm + 2.0f * fabsf(cb) * um * vm);
+    return !(qmin > tau + slack);
 }
 
 }  // namespace r3dg

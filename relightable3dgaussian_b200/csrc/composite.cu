@@ -2,17 +2,22 @@
 // and the surface-xyz / pseudo-normal pass (K8+K9, forward.cu:398-491, fused into one kernel).
 //
 // B200 design notes
-//  * one CTA per 16x16 tile, each warp owns a compact 8x4 pixel block so that early-outs and the
-//    per-Gaussian weight reduction are warp-uniform;
-//  * a batch of 256 instances is staged into shared memory as float4 SoA from ONE packed record
-//    per Gaussian (16B vector loads, conflict-free stores, broadcast reads in the pixel loop);
-//    the reference re-reads colour / feature / depth from global memory per (pixel, Gaussian);
+//  * each warp owns a compact 8x4 pixel block of a 16x16 tile and walks the tile's sorted list
+//    AUTONOMOUSLY: no CTA barrier, per-warp early termination, a register software pipeline that
+//    keeps the next 32-entry chunk (ids two chunks ahead, records one ahead) in flight while the
+//    current chunk is composited (the reference's CTA-wide fetch/compute lock-step spent ~half
+//    of its stall samples at the barrier);
+//  * per chunk each lane fetches ONE packed record (16B vector loads of 2 sectors, instead of the
+//    reference's five arrays), tests it against the warp's pixel block with an exact-conservative
+//    ellipse/rectangle test and a ballot yields the bitmap of entries worth compositing; the
+//    record is staged in a warp-private shared-memory slab and broadcast-read in the pixel loop;
 //  * accumulators live in registers (template on the number of float4 channel groups) — the
 //    reference's runtime-indexed F[33] spills to local memory;
 //  * out_weights: one atomic per (warp, Gaussian) after a shuffle reduction instead of one per
 //    (pixel, Gaussian);
 //  * per-pixel arithmetic keeps the association of the reference binary, so n_contrib and the
 //    images are bit-identical to it for identical lists.
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -29,24 +34,27 @@ struct CompositeFwdParams {
     float *out_color, *out_opacity, *out_depth, *out_feature, *out_weights;
 };
 
-template <int NG>
-__global__ void __launch_bounds__(256) composite_fwd_kernel(const CompositeFwdParams p) {
-    __shared__ float4 sA[256], sB[256];
-    __shared__ float4 sC[NG][256];
-    __shared__ int sId[256];
-    __shared__ uint32_t sBits[8][8];          // [pixel block (= consumer warp)][32-entry group of the batch]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.x;
+// NW = warps per CTA: 8 (one CTA per tile) or 4 (two CTAs per tile).  Warps are autonomous: no
+// CTA-wide barrier anywhere; the CTA only exists so that the warps of a tile share L1 lines.
+template <int NG, int NW>
+__global__ void __launch_bounds__(32 * NW) composite_fwd_kernel(const CompositeFwdParams p) {
+    constexpr int RG = 2 + NG;                       // float4 groups per record
+    __shared__ float4 sRec[NW][RG][32];              // this warp's current 32-entry chunk, SoA
+    __shared__ int sId[NW][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int PARTS = 8 / NW;
+    const int tile = blockIdx.x / PARTS;
+    const int wb = (blockIdx.x % PARTS) * NW + warp;          // pixel block 0..7 inside the tile
     const int tx = tile % p.gx, ty = tile / p.gx;
-    const float tile_x0 = (float)(tx * R3DG_TILE), tile_y0 = (float)(ty * R3DG_TILE);
-    const int px = tx * R3DG_TILE + (warp & 1) * 8 + (lane & 7);
-    const int py = ty * R3DG_TILE + (warp >> 1) * 4 + (lane >> 3);
+    const int bx0 = tx * R3DG_TILE + (wb & 1) * 8, by0 = ty * R3DG_TILE + (wb >> 1) * 4;
+    const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
     const bool inside = px < p.W && py < p.H;
     const float pxf = (float)px, pyf = (float)py;
     const uint2 range = p.ranges[tile];
     const int toDo = (int)(range.y - range.x);
     const float4* __restrict__ rec4 = reinterpret_cast<const float4*>(p.rec);
     const int rec4n = p.recf >> 2;
+    const uint32_t* __restrict__ plist = p.point_list + range.x;
 
     float T = 1.0f, Dp = 0.0f, Op = 0.0f;
     float C[4 * NG];
@@ -55,36 +63,38 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const CompositeFwdPa
     uint32_t last_contributor = 0;
     bool done = !inside;
 
-    for (int base = 0; base < toDo; base += 256) {
-        if (__syncthreads_and(done)) break;
-        const int n = min(256, toDo - base);
-        unsigned tm = 0u;
-        if (tid < n) {
-            const uint32_t id = p.point_list[range.x + base + tid];
-            const float4* r = rec4 + (size_t)id * rec4n;
-            const float4 A = r[0], B = r[1];
-            sId[tid] = (int)id;
-            sA[tid] = A;
-            sB[tid] = B;
+    // software pipeline: ids two chunks ahead, records one chunk ahead (registers)
+    uint32_t id_cur = lane < toDo ? plist[lane] : 0u;
+    float4 r[RG];
 #pragma unroll
-            for (int g = 0; g < NG; ++g) sC[g][tid] = r[2 + g];
-            tm = touch_mask(A, B, tile_x0, tile_y0);
-        }
+    for (int g = 0; g < RG; ++g) r[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < toDo) {
 #pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            const uint32_t word = __ballot_sync(0xffffffffu, (tm >> w) & 1u);
-            if (lane == 0) sBits[w][warp] = word;
+        for (int g = 0; g < RG; ++g) r[g] = rec4[(size_t)id_cur * rec4n + g];
+    }
+    uint32_t id_nxt = 32 + lane < toDo ? plist[32 + lane] : 0u;
+
+    bool all_done = __all_sync(0xffffffffu, done);
+    for (int base = 0; base < toDo && !all_done; base += 32) {
+        const int n = min(32, toDo - base);
+        __syncwarp();
+        sId[warp][lane] = (int)id_cur;
+#pragma unroll
+        for (int g = 0; g < RG; ++g) sRec[warp][g][lane] = r[g];
+        uint32_t word = __ballot_sync(0xffffffffu, lane < n && touch_block(r[0], r[1], (float)bx0, (float)by0));
+        // prefetch: records of the next chunk, ids of the one after
+        id_cur = id_nxt;
+        if (base + 32 + lane < toDo) {
+#pragma unroll
+            for (int g = 0; g < RG; ++g) r[g] = rec4[(size_t)id_cur * rec4n + g];
         }
-        __syncthreads();
-        if (__all_sync(0xffffffffu, done)) continue;
-        bool warp_done = false;
-        for (int k = 0; k < 8 && !warp_done; ++k) {
-          uint32_t word = sBits[warp][k];
-          while (word) {
-            const int j = k * 32 + __ffs(word) - 1;
+        id_nxt = base + 64 + lane < toDo ? plist[base + 64 + lane] : 0u;
+        __syncwarp();
+        while (word) {
+            const int j = __ffs(word) - 1;
             word &= word - 1;
-            const float4 a = sA[j];
-            const float4 b = sB[j];
+            const float4 a = sRec[warp][0][j];
+            const float4 b = sRec[warp][1][j];
             const float dx = sub_(a.x, pxf), dy = sub_(a.y, pyf);
             // power = -0.5f*(ca*dx*dx + cc*dy*dy) - cb*dx*dy  (forward.cu:344) as compiled
             const float q = fma_(dx, mul_(dx, a.z), mul_(dy, mul_(dy, b.x)));
@@ -98,7 +108,7 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const CompositeFwdPa
                 w = mul_(T, alpha);
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
-                    const float4 c = sC[g][j];
+                    const float4 c = sRec[warp][2 + g][j];
                     C[4 * g + 0] = fma_(w, c.x, C[4 * g + 0]);
                     C[4 * g + 1] = fma_(w, c.y, C[4 * g + 1]);
                     C[4 * g + 2] = fma_(w, c.z, C[4 * g + 2]);
@@ -112,10 +122,9 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const CompositeFwdPa
             if (__any_sync(0xffffffffu, valid)) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
-                if (lane == 0) atomicAdd(&p.out_weights[sId[j]], w);
+                if (lane == 0) atomicAdd(&p.out_weights[sId[warp][j]], w);
             }
-            if (__all_sync(0xffffffffu, done)) { warp_done = true; break; }
-          }
+            if (__all_sync(0xffffffffu, done)) { all_done = true; break; }
         }
     }
     if (inside) {
@@ -183,8 +192,14 @@ __global__ void __launch_bounds__(256) surface_normal_kernel(int W, int H, const
 }
 
 template <int NG>
-static void launch_fwd_ng(const CompositeFwdParams& p, int tiles, cudaStream_t stream) {
-    composite_fwd_kernel<NG><<<tiles, 256, 0, stream>>>(p);
+static void launch_fwd_ng(const CompositeFwdParams& p, int tiles, int nw, cudaStream_t stream) {
+    if (nw == 4) composite_fwd_kernel<NG, 4><<<tiles * 2, 128, 0, stream>>>(p);
+    else composite_fwd_kernel<NG, 8><<<tiles, 256, 0, stream>>>(p);
+}
+int composite_nw() {
+    static int nw = 0;
+    if (nw == 0) { const char* e = getenv("R3DG_COMPOSITE_NW"); nw = (e && atoi(e) == 8) ? 8 : 4; }
+    return nw;
 }
 
 int launch_composite_forward(const r3dg_raster_fwd_args& a, const GeomLayout& gl, const ImgLayout& il,
@@ -204,15 +219,15 @@ int launch_composite_forward(const r3dg_raster_fwd_args& a, const GeomLayout& gl
     p.out_feature = a.out_feature; p.out_weights = a.out_weights;
     const int tiles = p.gx * gy;
     switch (num_groups(a.S)) {
-        case 1: launch_fwd_ng<1>(p, tiles, stream); break;
-        case 2: launch_fwd_ng<2>(p, tiles, stream); break;
-        case 3: launch_fwd_ng<3>(p, tiles, stream); break;
-        case 4: launch_fwd_ng<4>(p, tiles, stream); break;
-        case 5: launch_fwd_ng<5>(p, tiles, stream); break;
-        case 6: launch_fwd_ng<6>(p, tiles, stream); break;
-        case 7: launch_fwd_ng<7>(p, tiles, stream); break;
-        case 8: launch_fwd_ng<8>(p, tiles, stream); break;
-        case 9: launch_fwd_ng<9>(p, tiles, stream); break;
+        case 1: launch_fwd_ng<1>(p, tiles, composite_nw(), stream); break;
+        case 2: launch_fwd_ng<2>(p, tiles, composite_nw(), stream); break;
+        case 3: launch_fwd_ng<3>(p, tiles, composite_nw(), stream); break;
+        case 4: launch_fwd_ng<4>(p, tiles, composite_nw(), stream); break;
+        case 5: launch_fwd_ng<5>(p, tiles, composite_nw(), stream); break;
+        case 6: launch_fwd_ng<6>(p, tiles, composite_nw(), stream); break;
+        case 7: launch_fwd_ng<7>(p, tiles, composite_nw(), stream); break;
+        case 8: launch_fwd_ng<8>(p, tiles, composite_nw(), stream); break;
+        case 9: launch_fwd_ng<9>(p, tiles, composite_nw(), stream); break;
         default: return R3DG_ERR_UNSUPPORTED;
     }
     const size_t HW = (size_t)a.H * a.W;

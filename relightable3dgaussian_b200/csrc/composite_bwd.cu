@@ -6,8 +6,9 @@
 //    ("reduce-scatter": ~V shuffles for V values instead of 5V), after which 16/32 lanes each
 //    hold one finished component and add the whole per-Gaussian gradient row with ONE vectorised
 //    atomic instruction into a packed [P][RECF] row (2-4 sectors);
-//  * the traversal starts at the tile's largest n_contrib instead of the end of the tile list —
-//    entries behind every pixel's last contributor are never loaded;
+//  * warps are autonomous (no CTA barrier; see composite.cu): each starts at ITS pixel block's
+//    largest n_contrib instead of the end of the tile list — entries behind every pixel's last
+//    contributor are never loaded — and skips entries its block cannot see via touch_block();
 //  * per-pixel state is register resident (template on channel groups); the reference keeps three
 //    float[24] arrays in local memory and 36 KB of shared memory per CTA;
 //  * gradients differ from the reference only by fp32 summation order (the reference's own
@@ -51,42 +52,37 @@ __device__ __forceinline__ float reduce_scatter(float (&v)[N], int lane) {
     return r;
 }
 
-template <int NG>
-__global__ void __launch_bounds__(256) composite_bwd_kernel(const CompositeBwdParams p) {
+template <int NG, int NW>
+__global__ void __launch_bounds__(32 * NW) composite_bwd_kernel(const CompositeBwdParams p) {
     constexpr int NC = 4 * NG;              // padded channel count {r,g,b,f...}
     constexpr int V = 8 + NC;               // gradient row width
     constexpr int V0 = V <= 16 ? 16 : 32;   // first butterfly chunk
     constexpr int V1 = V > 32 ? 4 : 0;      // tail chunk (only V == 36)
-    __shared__ float4 sA[256], sB[256];
-    __shared__ float4 sC[NG][256];
-    __shared__ int sId[256];
-    __shared__ int sMax[8];
-    __shared__ uint32_t sBits[8][8];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.x;
+    constexpr int RG = 2 + NG;
+    __shared__ float4 sRec[NW][RG][32];
+    __shared__ int sId[NW][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int PARTS = 8 / NW;
+    const int tile = blockIdx.x / PARTS;
+    const int wb = (blockIdx.x % PARTS) * NW + warp;
     const int tx = tile % p.gx, ty = tile / p.gx;
-    const float tile_x0 = (float)(tx * R3DG_TILE), tile_y0 = (float)(ty * R3DG_TILE);
-    const int px = tx * R3DG_TILE + (warp & 1) * 8 + (lane & 7);
-    const int py = ty * R3DG_TILE + (warp >> 1) * 4 + (lane >> 3);
+    const int bx0 = tx * R3DG_TILE + (wb & 1) * 8, by0 = ty * R3DG_TILE + (wb >> 1) * 4;
+    const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
     const bool inside = px < p.W && py < p.H;
     const float pxf = (float)px, pyf = (float)py;
     const uint2 range = p.ranges[tile];
     const size_t HW = (size_t)p.H * p.W, pix = (size_t)p.W * py + px;
     const float4* __restrict__ rec4 = reinterpret_cast<const float4*>(p.rec);
     const int rec4n = p.recf >> 2;
+    const uint32_t* __restrict__ plist = p.point_list + range.x;
 
     const float T_final = inside ? p.final_T[pix] : 0.0f;
     float T = T_final;
     const int last_contributor = inside ? p.n_contrib[pix] : 0;
-    // tile-wide maximum of n_contrib: nothing behind it contributes to any pixel
-    int wmax = last_contributor;
+    // nothing behind the warp's deepest last contributor matters to this warp
+    int total = last_contributor;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-    if (lane == 0) sMax[warp] = wmax;
-    __syncthreads();
-    int total = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) total = max(total, sMax[w]);
+    for (int o = 16; o > 0; o >>= 1) total = max(total, __shfl_xor_sync(0xffffffffu, total, o));
     total = min(total, (int)(range.y - range.x));
 
     float dpix[NC], accum[NC], lastc[NC];
@@ -107,38 +103,38 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const CompositeBwdPa
     const float ddelx_dx = 0.5f * p.W, ddely_dy = 0.5f * p.H;
     const bool geo = p.backward_geometry != 0;
 
-    for (int base = 0; base < total; base += 256) {
-        __syncthreads();
-        const int n = min(256, total - base);
-        unsigned tm = 0u;
-        if (tid < n) {
-            const uint32_t id = p.point_list[range.x + (total - 1 - (base + tid))];
-            const float4* r = rec4 + (size_t)id * rec4n;
-            const float4 A = r[0], B = r[1];
-            sId[tid] = (int)id;
-            sA[tid] = A;
-            sB[tid] = B;
+    // back-to-front: chunk entry `lane` of the chunk starting at `base` is list position
+    // total-1-(base+lane).  Pipeline as in the forward.
+    uint32_t id_cur = lane < total ? plist[total - 1 - lane] : 0u;
+    float4 r[RG];
 #pragma unroll
-            for (int g = 0; g < NG; ++g) sC[g][tid] = r[2 + g];
-            tm = touch_mask(A, B, tile_x0, tile_y0);
-        }
+    for (int g = 0; g < RG; ++g) r[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < total) {
 #pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            const uint32_t word = __ballot_sync(0xffffffffu, (tm >> w) & 1u);
-            if (lane == 0) sBits[w][warp] = word;
+        for (int g = 0; g < RG; ++g) r[g] = rec4[(size_t)id_cur * rec4n + g];
+    }
+    uint32_t id_nxt = 32 + lane < total ? plist[total - 1 - (32 + lane)] : 0u;
+
+    for (int base = 0; base < total; base += 32) {
+        const int n = min(32, total - base);
+        __syncwarp();
+        sId[warp][lane] = (int)id_cur;
+#pragma unroll
+        for (int g = 0; g < RG; ++g) sRec[warp][g][lane] = r[g];
+        uint32_t word = __ballot_sync(0xffffffffu, lane < n && touch_block(r[0], r[1], (float)bx0, (float)by0));
+        id_cur = id_nxt;
+        if (base + 32 + lane < total) {
+#pragma unroll
+            for (int g = 0; g < RG; ++g) r[g] = rec4[(size_t)id_cur * rec4n + g];
         }
-        __syncthreads();
-        // this warp can skip the batch if none of its pixels reaches that deep
-        if (total - 1 - base - (n - 1) >= wmax) continue;
-        for (int kk = 0; kk < 8; ++kk) {
-          uint32_t word = sBits[warp][kk];
-          while (word) {
-            const int j = kk * 32 + __ffs(word) - 1;
+        id_nxt = base + 64 + lane < total ? plist[total - 1 - (base + 64 + lane)] : 0u;
+        __syncwarp();
+        while (word) {
+            const int j = __ffs(word) - 1;
             word &= word - 1;
             const int k = total - 1 - (base + j);            // 0-based list position == contributor
-            if (k >= wmax) continue;                         // warp-uniform
-            const float4 a = sA[j];
-            const float4 b = sB[j];
+            const float4 a = sRec[warp][0][j];
+            const float4 b = sRec[warp][1][j];
             const float dx = sub_(a.x, pxf), dy = sub_(a.y, pyf);
             const float q = fma_(dx, mul_(dx, a.z), mul_(dy, mul_(dy, b.x)));
             const float power = fma_(q, -0.5f, -mul_(dy, mul_(dx, a.w)));
@@ -158,7 +154,7 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const CompositeBwdPa
                 float dL_dalpha = 0.0f;
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
-                    const float4 c4 = sC[g][j];
+                    const float4 c4 = sRec[warp][2 + g][j];
                     const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -192,7 +188,7 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const CompositeBwdPa
                 v0[5] = -0.5f * gdx * dy * dL_dG;
                 v0[6] = -0.5f * gdy * dy * dL_dG;
             }
-            float* grow = p.grad + (size_t)sId[j] * p.recf;
+            float* grow = p.grad + (size_t)sId[warp][j] * p.recf;
             const float r0 = reduce_scatter<V0>(v0, lane);
             {
                 constexpr int SH = V0 == 32 ? 0 : 1;            // lanes per component - 1 (log2)
@@ -204,14 +200,15 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const CompositeBwdPa
                 const int comp = lane >> 3;
                 if ((lane & 7) == 0 && V0 + comp < V) atomicAdd(grow + V0 + comp, r1);
             }
-          }
         }
     }
 }
 
+int composite_nw();
 template <int NG>
 static void launch_bwd_ng(const CompositeBwdParams& p, int tiles, cudaStream_t stream) {
-    composite_bwd_kernel<NG><<<tiles, 256, 0, stream>>>(p);
+    if (composite_nw() == 4) composite_bwd_kernel<NG, 4><<<tiles * 2, 128, 0, stream>>>(p);
+    else composite_bwd_kernel<NG, 8><<<tiles, 256, 0, stream>>>(p);
 }
 
 int launch_composite_backward(const r3dg_raster_bwd_args& a, const GeomLayout& gl, const ImgLayout& il,
