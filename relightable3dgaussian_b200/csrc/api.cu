@@ -82,12 +82,12 @@ int r3dg_raster_forward(const r3dg_raster_fwd_args* a, r3dg_stream_t stream_) {
         g_launches += 3 + 2 + passes;
     }
     prof_mark(true, 4, stream);
-    const bool in_b = (passes & 1) != 0;
-    const uint64_t* keys_sorted = (const uint64_t*)(bin + (in_b ? bl.keys_b : bl.keys_a));
-    const uint32_t* point_list = (const uint32_t*)(bin + (in_b ? bl.vals_b : bl.vals_a));
-    if ((rc = launch_tile_ranges(geom + gl.header, capacity, keys_sorted, img + il.ranges, tiles, num_sms(), stream)) != 0) return rc;
+    const uint32_t* vals_a = (const uint32_t*)(bin + bl.vals_a);
+    const uint32_t* vals_b = (const uint32_t*)(bin + bl.vals_b);
+    if ((rc = launch_tile_ranges(geom + gl.header, capacity, (const uint64_t*)(bin + bl.keys_a), (const uint64_t*)(bin + bl.keys_b),
+                                 img + il.ranges, tiles, num_sms(), stream)) != 0) return rc;
     prof_mark(true, 5, stream);
-    if ((rc = launch_composite_forward(*a, gl, il, point_list, stream, [](int i, cudaStream_t s) { prof_mark(true, i, s); })) != 0) return rc;
+    if ((rc = launch_composite_forward(*a, gl, il, vals_a, vals_b, stream, [](int i, cudaStream_t s) { prof_mark(true, i, s); })) != 0) return rc;
     prof_mark(true, 7, stream);
     g_launches += 2 + (a->computer_pseudo_normal ? 1 : 0);
     if (g_prof.on) g_prof.fwd_calls++;
@@ -112,11 +112,9 @@ int r3dg_raster_backward(const r3dg_raster_bwd_args* a, r3dg_stream_t stream_) {
     if (capacity < 1) return R3DG_ERR_BAD_ARG;
     const BinLayout bl(capacity);
     char* bin = (char*)a->binning;
-    const bool in_b = (sort_passes(a->W, a->H) & 1) != 0;
-    const uint32_t* point_list = (const uint32_t*)(bin + (in_b ? bl.vals_b : bl.vals_a));
     int rc = 0;
     prof_mark(false, 8, stream);
-    if ((rc = launch_composite_backward(*a, gl, il, point_list, stream)) != 0) return rc;
+    if ((rc = launch_composite_backward(*a, gl, il, (const uint32_t*)(bin + bl.vals_a), (const uint32_t*)(bin + bl.vals_b), stream)) != 0) return rc;
     prof_mark(false, 9, stream);
     if ((rc = launch_projection_backward(*a, gl, stream)) != 0) return rc;
     prof_mark(false, 10, stream);
@@ -227,7 +225,10 @@ long long r3dg_raster_debug_copy(int id, int P, int S, int W, int H, const void*
             const long long capacity = bin_capacity_for_bytes(binning_bytes);
             if (capacity < 1) return -1;
             const BinLayout bl(capacity);
-            const bool in_b = (sort_passes(W, H) & 1) != 0;
+            GeomHeader h;     // debug path: one blocking read of the header to learn the result buffer
+            if (cudaStreamSynchronize(stream) != cudaSuccess ||
+                cudaMemcpy(&h, geom + gl.header, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+            const bool in_b = (h.sort_exec & 1u) != 0;
             // caller limits the copy to R entries through max_bytes
             if (id == 9) return copy(bin + (in_b ? bl.vals_b : bl.vals_a), (size_t)max_bytes);
             return copy(bin + (in_b ? bl.keys_b : bl.keys_a), (size_t)max_bytes);

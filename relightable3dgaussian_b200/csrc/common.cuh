@@ -31,9 +31,10 @@ struct GeomHeader {               // first 256 bytes of the geometry buffer
     uint32_t num_rendered;        // R = total (tile, Gaussian) instances (may exceed capacity)
     uint32_t scan_ticket;         // dynamic block id for the chained scan
     uint32_t sort_ticket[8];      // dynamic tile id per radix pass
-    uint32_t depth_or;            // OR / AND of visible depth bit patterns (pass skipping)
-    uint32_t depth_and;
-    uint32_t pad[52];
+    uint32_t depth_or;            // OR of visible depth bit patterns
+    uint32_t depth_nor;           // OR of their complements: bit varies across keys iff set in both
+    uint32_t sort_exec;           // number of radix passes actually executed (parity = result buffer)
+    uint32_t pad[51];
 };
 static_assert(sizeof(GeomHeader) == 256, "header size");
 
@@ -101,6 +102,24 @@ inline __host__ long long bin_capacity_for_bytes(size_t bytes) {
         if (BinLayout(mid).total <= bytes) lo = mid; else hi = mid - 1;
     }
     return lo;
+}
+
+// Radix passes over the 64-bit key (tile << 32 | depth bits).  A depth digit whose bits are
+// identical in every key is a no-op for a stable sort and is skipped on the device; the k-th
+// EXECUTED pass reads buffer (k & 1) and writes buffer (~k & 1), so the result lives in buffer
+// (sort_exec & 1) where sort_exec is only known on the device.
+__device__ __forceinline__ int sort_digit_of_slot(uint32_t depth_diff, int passes, int slot) {
+    int k = 0;
+    for (int p = 0; p < passes; ++p) {
+        const bool needed = p >= 4 || ((depth_diff >> (8 * p)) & 0xffu) != 0u;
+        if (needed) { if (k == slot) return p; ++k; }
+    }
+    return -1;
+}
+__device__ __forceinline__ int sort_num_exec(uint32_t depth_diff, int passes) {
+    int k = 0;
+    for (int p = 0; p < passes; ++p) k += (p >= 4 || ((depth_diff >> (8 * p)) & 0xffu) != 0u) ? 1 : 0;
+    return k;
 }
 
 // getHigherMsb (reference rasterizer_impl.cu:35-50): bits needed for tile ids.

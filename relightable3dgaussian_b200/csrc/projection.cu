@@ -59,9 +59,11 @@ __device__ __forceinline__ void cov3d_from_scale_rot(const float* __restrict__ s
 }
 
 // SH -> RGB (forward.cu:20-71).  sh rows are [M][3] floats.
+// `sh` points at coefficient 0 / channel 0 of this Gaussian; consecutive floats of its [M][3] row
+// are `stride` apart (1 in global memory, PROJ_THREADS+1 in the transposed shared-memory slab).
 __device__ __forceinline__ void sh_to_rgb(int deg, float px, float py, float pz,
                                           const float* __restrict__ campos,
-                                          const float* __restrict__ sh, float* rgb,
+                                          const float* __restrict__ sh, int stride, float* rgb,
                                           unsigned& clamped_bits) {
     const float dx = px - campos[0], dy = py - campos[1], dz = pz - campos[2];
     const float len = sqrt_(dot3_(dx, dx, dy, dy, dz, dz));
@@ -88,12 +90,12 @@ __device__ __forceinline__ void sh_to_rgb(int deg, float px, float py, float pz,
     const int n = (deg + 1) * (deg + 1);
     float res[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) res[c] = w[0] * sh[c];
+    for (int c = 0; c < 3; ++c) res[c] = w[0] * sh[c * stride];
 #pragma unroll
     for (int k = 1; k < 16; ++k) {
         if (k < n) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) res[c] = fmaf(w[k], sh[3 * k + c], res[c]);
+            for (int c = 0; c < 3; ++c) res[c] = fmaf(w[k], sh[(3 * k + c) * stride], res[c]);
         }
     }
     clamped_bits = 0;
@@ -119,84 +121,129 @@ struct ProjParams {
     GeomHeader* header;
 };
 
-__global__ void __launch_bounds__(256) project_kernel(const ProjParams p) {
+#define PROJ_THREADS 128
+// Cooperative, coalesced load of the block's [nvalid][rowf] float slab into a transposed shared
+// slab s[k * (PROJ_THREADS + 1) + t] (conflict-free column access by thread t).
+__device__ __forceinline__ void load_rows_transposed(float* s, const float* __restrict__ src, int nvalid, int rowf) {
+    const int total = nvalid * rowf;
+    if ((rowf & 3) == 0) {
+        const float4* src4 = reinterpret_cast<const float4*>(src);
+        for (int i4 = threadIdx.x; i4 < total / 4; i4 += PROJ_THREADS) {
+            const float4 v = src4[i4];
+            const int i = 4 * i4, t = i / rowf, k = i - t * rowf;
+            s[(k + 0) * (PROJ_THREADS + 1) + t] = v.x; s[(k + 1) * (PROJ_THREADS + 1) + t] = v.y;
+            s[(k + 2) * (PROJ_THREADS + 1) + t] = v.z; s[(k + 3) * (PROJ_THREADS + 1) + t] = v.w;
+        }
+    } else {
+        for (int i = threadIdx.x; i < total; i += PROJ_THREADS) {
+            const int t = i / rowf, k = i - t * rowf;
+            s[k * (PROJ_THREADS + 1) + t] = src[i];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjParams p) {
+    extern __shared__ float sSH[];                 // [3M][PROJ_THREADS + 1] when SHs are given
     __shared__ float sV[16], sPr[16], sCam[3];
     if (threadIdx.x < 16) { sV[threadIdx.x] = p.viewmatrix[threadIdx.x]; sPr[threadIdx.x] = p.projmatrix[threadIdx.x]; }
     if (threadIdx.x < 3) sCam[threadIdx.x] = p.campos[threadIdx.x];
     __syncthreads();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= p.P) return;
-    p.radii[idx] = 0;
-    p.tiles_touched[idx] = 0;
-    p.out_weights[idx] = 0.0f;
-    const float px = p.means3D[3 * idx], py = p.means3D[3 * idx + 1], pz = p.means3D[3 * idx + 2];
-    const float tz = xform_row_(sV, 2, px, py, pz);
-    if (tz <= 0.2f) {                                  // auxiliary.h:154 (x/y frustum test is disabled there)
-        if (p.prefiltered) { printf("Point is filtered although prefiltered is set. This shouldn't happen!"); __trap(); }
-        return;
+    bool alive = idx < p.P;
+    float px = 0.f, py = 0.f, pz = 0.f, tz = 1.f;
+    if (alive) {
+        p.radii[idx] = 0;
+        p.tiles_touched[idx] = 0;
+        p.out_weights[idx] = 0.0f;
+        px = p.means3D[3 * (size_t)idx]; py = p.means3D[3 * (size_t)idx + 1]; pz = p.means3D[3 * (size_t)idx + 2];
+        tz = xform_row_(sV, 2, px, py, pz);
+        if (tz <= 0.2f) {                              // auxiliary.h:154 (x/y frustum test is disabled there)
+            if (p.prefiltered) { printf("Point is filtered although prefiltered is set. This shouldn't happen!"); __trap(); }
+            alive = false;
+        }
     }
-    const float hx = xform_row_(sPr, 0, px, py, pz);
-    const float hy = xform_row_(sPr, 1, px, py, pz);
-    const float hw = xform_row_(sPr, 3, px, py, pz);
-    const float p_w = rcp_(add_(hw, 0.0000001f));
-    const float projx = mul_(hx, p_w), projy = mul_(hy, p_w);
-
-    float c6[6];
-    if (p.cov3D_precomp) {
+    float pix_x = 0.f, pix_y = 0.f, con_a = 0.f, con_b = 0.f, con_c = 0.f;
+    int my_radius = 0, x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    if (alive) {
+        const float hx = xform_row_(sPr, 0, px, py, pz);
+        const float hy = xform_row_(sPr, 1, px, py, pz);
+        const float hw = xform_row_(sPr, 3, px, py, pz);
+        const float p_w = rcp_(add_(hw, 0.0000001f));
+        const float projx = mul_(hx, p_w), projy = mul_(hy, p_w);
+        float c6[6];
+        if (p.cov3D_precomp) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) c6[i] = p.cov3D_precomp[6 * (size_t)idx + i];
-    } else {
-        const float4 q = *reinterpret_cast<const float4*>(p.rotations + 4 * (size_t)idx);
-        const float s3[3] = {p.scales[3 * (size_t)idx], p.scales[3 * (size_t)idx + 1], p.scales[3 * (size_t)idx + 2]};
-        cov3d_from_scale_rot(s3, p.scale_modifier, q, c6);
-    }
-    // computeCov2D (forward.cu:74-113), association as compiled
-    const float tx = xform_row_(sV, 0, px, py, pz), ty = xform_row_(sV, 1, px, py, pz);
-    const float limx = mul_(p.tan_fovx, 1.3f), limy = mul_(p.tan_fovy, 1.3f);
-    const float cxz = fminf(fmaxf(div_(tx, tz), -limx), limx);
-    const float cyz = fminf(fmaxf(div_(ty, tz), -limy), limy);
-    const float tz2 = mul_(tz, tz);
-    const float j00 = div_(p.focal_x, tz), j11 = div_(p.focal_y, tz);
-    const float j02 = div_(mul_(mul_(tz, -cxz), p.focal_x), tz2);
-    const float j12 = div_(mul_(mul_(tz, -cyz), p.focal_y), tz2);
-    float T0[3], T1[3];
+            for (int i = 0; i < 6; ++i) c6[i] = p.cov3D_precomp[6 * (size_t)idx + i];
+        } else {
+            const float4 q = *reinterpret_cast<const float4*>(p.rotations + 4 * (size_t)idx);
+            const float s3[3] = {p.scales[3 * (size_t)idx], p.scales[3 * (size_t)idx + 1], p.scales[3 * (size_t)idx + 2]};
+            cov3d_from_scale_rot(s3, p.scale_modifier, q, c6);
+        }
+        // computeCov2D (forward.cu:74-113), association as compiled
+        const float tx = xform_row_(sV, 0, px, py, pz), ty = xform_row_(sV, 1, px, py, pz);
+        const float limx = mul_(p.tan_fovx, 1.3f), limy = mul_(p.tan_fovy, 1.3f);
+        const float cxz = fminf(fmaxf(div_(tx, tz), -limx), limx);
+        const float cyz = fminf(fmaxf(div_(ty, tz), -limy), limy);
+        const float tz2 = mul_(tz, tz);
+        const float j00 = div_(p.focal_x, tz), j11 = div_(p.focal_y, tz);
+        const float j02 = div_(mul_(mul_(tz, -cxz), p.focal_x), tz2);
+        const float j12 = div_(mul_(mul_(tz, -cyz), p.focal_y), tz2);
+        float T0[3], T1[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const float w0 = sV[4 * k + 0], w1 = sV[4 * k + 1], w2 = sV[4 * k + 2];
-        T0[k] = fma_(w2, j02, fma_(w0, j00, mul_(0.0f, w1)));
-        T1[k] = fma_(w2, j12, fma_(0.0f, w0, mul_(w1, j11)));
+        for (int k = 0; k < 3; ++k) {
+            const float w0 = sV[4 * k + 0], w1 = sV[4 * k + 1], w2 = sV[4 * k + 2];
+            T0[k] = fma_(w2, j02, fma_(w0, j00, mul_(0.0f, w1)));
+            T1[k] = fma_(w2, j12, fma_(0.0f, w0, mul_(w1, j11)));
+        }
+        const float a0 = dot3_(T0[0], c6[0], T0[1], c6[1], T0[2], c6[2]);
+        const float a1 = dot3_(T0[0], c6[1], T0[1], c6[3], T0[2], c6[4]);
+        const float a2 = dot3_(T0[0], c6[2], T0[1], c6[4], T0[2], c6[5]);
+        const float b0 = dot3_(T1[0], c6[0], T1[1], c6[1], T1[2], c6[2]);
+        const float b1 = dot3_(T1[0], c6[1], T1[1], c6[3], T1[2], c6[4]);
+        const float b2 = dot3_(T1[0], c6[2], T1[1], c6[4], T1[2], c6[5]);
+        const float cov_a = add_(dot3_(T0[0], a0, T0[1], a1, T0[2], a2), 0.3f);
+        const float cov_c = add_(dot3_(T1[0], b0, T1[1], b1, T1[2], b2), 0.3f);
+        const float cov_b = dot3_(T0[0], b0, T0[1], b1, T0[2], b2);
+        const float det = fma_(cov_a, cov_c, -mul_(cov_b, cov_b));
+        if (det == 0.0f) {
+            alive = false;
+        } else {
+            const float det_inv = rcp_(det);
+            con_a = mul_(cov_c, det_inv); con_b = mul_(cov_b, -det_inv); con_c = mul_(cov_a, det_inv);
+            const float mid = mul_(add_(cov_a, cov_c), 0.5f);
+            const float disc = sqrt_(fmaxf(fma_(mid, mid, -det), 0.1f));
+            const float lam = fmaxf(add_(mid, disc), sub_(mid, disc));
+            my_radius = (int)ceilf(mul_(sqrt_(lam), 3.0f));
+            pix_x = (float)(fma((double)projx + 1.0, (double)p.W, -1.0) * 0.5);   // ndc2Pix, auxiliary.h:41-44
+            pix_y = (float)(fma((double)projy + 1.0, (double)p.H, -1.0) * 0.5);
+            get_rect(pix_x, pix_y, my_radius, p.gx, p.gy, x0, y0, x1, y1);
+            if ((x1 - x0) * (y1 - y0) == 0) alive = false;
+        }
     }
-    const float a0 = dot3_(T0[0], c6[0], T0[1], c6[1], T0[2], c6[2]);
-    const float a1 = dot3_(T0[0], c6[1], T0[1], c6[3], T0[2], c6[4]);
-    const float a2 = dot3_(T0[0], c6[2], T0[1], c6[4], T0[2], c6[5]);
-    const float b0 = dot3_(T1[0], c6[0], T1[1], c6[1], T1[2], c6[2]);
-    const float b1 = dot3_(T1[0], c6[1], T1[1], c6[3], T1[2], c6[4]);
-    const float b2 = dot3_(T1[0], c6[2], T1[1], c6[4], T1[2], c6[5]);
-    const float cov_a = add_(dot3_(T0[0], a0, T0[1], a1, T0[2], a2), 0.3f);
-    const float cov_c = add_(dot3_(T1[0], b0, T1[1], b1, T1[2], b2), 0.3f);
-    const float cov_b = dot3_(T0[0], b0, T0[1], b1, T0[2], b2);
-    const float det = fma_(cov_a, cov_c, -mul_(cov_b, cov_b));
-    if (det == 0.0f) return;
-    const float det_inv = rcp_(det);
-    const float con_a = mul_(cov_c, det_inv), con_b = mul_(cov_b, -det_inv), con_c = mul_(cov_a, det_inv);
-    const float mid = mul_(add_(cov_a, cov_c), 0.5f);
-    const float disc = sqrt_(fmaxf(fma_(mid, mid, -det), 0.1f));
-    const float lam = fmaxf(add_(mid, disc), sub_(mid, disc));
-    const int my_radius = (int)ceilf(mul_(sqrt_(lam), 3.0f));
-    const float pix_x = (float)(fma((double)projx + 1.0, (double)p.W, -1.0) * 0.5);   // ndc2Pix, auxiliary.h:41-44
-    const float pix_y = (float)(fma((double)projy + 1.0, (double)p.H, -1.0) * 0.5);
-    int x0, y0, x1, y1;
-    get_rect(pix_x, pix_y, my_radius, p.gx, p.gy, x0, y0, x1, y1);
-    if ((x1 - x0) * (y1 - y0) == 0) return;
-
-    float rgb[3];
-    unsigned cl = 0;
+    float rgb[3] = {0.f, 0.f, 0.f};
     if (p.colors_precomp == nullptr) {
-        sh_to_rgb(p.D, px, py, pz, sCam, p.shs + (size_t)idx * p.M * 3, rgb, cl);
-        p.clamped[idx] = (uint8_t)cl;
-    } else {
+        // SH rows ([M][3] floats, 192 B at M=16) are staged through a transposed shared slab so the
+        // global reads are fully coalesced 16B vectors instead of 48 strided scalar loads per thread.
+        if (__syncthreads_or(alive)) {
+            const int rowf = 3 * p.M, block_base = blockIdx.x * PROJ_THREADS;
+            load_rows_transposed(sSH, p.shs + (size_t)block_base * rowf, min(PROJ_THREADS, p.P - block_base), rowf);
+            __syncthreads();
+            if (alive) {
+                unsigned cl = 0;
+                sh_to_rgb(p.D, px, py, pz, sCam, sSH + threadIdx.x, PROJ_THREADS + 1, rgb, cl);
+                p.clamped[idx] = (uint8_t)cl;
+            }
+        }
+    } else if (alive) {
         rgb[0] = p.colors_precomp[3 * (size_t)idx]; rgb[1] = p.colors_precomp[3 * (size_t)idx + 1]; rgb[2] = p.colors_precomp[3 * (size_t)idx + 2];
     }
+    {   // which depth-key bits vary across the visible Gaussians (drives radix pass skipping)
+        const uint32_t bits = __float_as_uint(tz);
+        const uint32_t o = __reduce_or_sync(0xffffffffu, alive ? bits : 0u);
+        const uint32_t no = __reduce_or_sync(0xffffffffu, alive ? ~bits : 0u);
+        if ((threadIdx.x & 31) == 0 && (o | no)) { atomicOr(&p.header->depth_or, o); atomicOr(&p.header->depth_nor, no); }
+    }
+    if (!alive) return;
     float4* rec = reinterpret_cast<float4*>(p.rec + (size_t)idx * p.recf);
     rec[0] = make_float4(pix_x, pix_y, con_a, con_b);
     rec[1] = make_float4(con_c, p.opacities[idx], tz, __int_as_float(my_radius));
@@ -301,9 +348,11 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int recf, int gx,
 // ---- identifyTileRanges (rasterizer_impl.cu:116-138) ----------------------------------------
 __global__ void __launch_bounds__(256) tile_ranges_kernel(const GeomHeader* __restrict__ header,
                                                           long long capacity,
-                                                          const uint64_t* __restrict__ keys,
+                                                          const uint64_t* __restrict__ keys_a,
+                                                          const uint64_t* __restrict__ keys_b,
                                                           uint2* __restrict__ ranges) {
     const long long R = min((long long)header->num_rendered, capacity);
+    const uint64_t* __restrict__ keys = (header->sort_exec & 1u) ? keys_b : keys_a;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < R;
          i += (long long)gridDim.x * blockDim.x) {
         const uint32_t cur = (uint32_t)(keys[i] >> 32);
@@ -344,7 +393,8 @@ int launch_projection(const r3dg_raster_fwd_args& a, const GeomLayout& gl, const
     p.clamped = (uint8_t*)(geom + gl.clamped); p.radii = a.radii; p.out_weights = a.out_weights;
     p.header = (GeomHeader*)(geom + gl.header);
     const int nb = (a.P + 255) / 256;
-    project_kernel<<<nb, 256, 0, stream>>>(p);
+    const size_t sh_smem = a.shs ? (size_t)3 * a.M * (PROJ_THREADS + 1) * sizeof(float) : 0;
+    project_kernel<<<(a.P + PROJ_THREADS - 1) / PROJ_THREADS, PROJ_THREADS, sh_smem, stream>>>(p);
     mark(1, stream);
     const int nscan = (a.P + R3DG_SCAN_ITEMS - 1) / R3DG_SCAN_ITEMS;
     R3DG_CUDA_TRY(cudaMemsetAsync(geom + gl.scan_state, 0, (size_t)(nscan + 1) * 4, stream));
@@ -358,10 +408,10 @@ int launch_projection(const r3dg_raster_fwd_args& a, const GeomLayout& gl, const
     return 0;
 }
 
-int launch_tile_ranges(const void* geom_header, long long capacity, const uint64_t* keys, void* ranges,
-                       int num_tiles, int num_sms, cudaStream_t stream) {
+int launch_tile_ranges(const void* geom_header, long long capacity, const uint64_t* keys_a,
+                       const uint64_t* keys_b, void* ranges, int num_tiles, int num_sms, cudaStream_t stream) {
     R3DG_CUDA_TRY(cudaMemsetAsync(ranges, 0, (size_t)num_tiles * 8, stream));
-    tile_ranges_kernel<<<num_sms * 8, 256, 0, stream>>>((const GeomHeader*)geom_header, capacity, keys, (uint2*)ranges);
+    tile_ranges_kernel<<<num_sms * 8, 256, 0, stream>>>((const GeomHeader*)geom_header, capacity, keys_a, keys_b, (uint2*)ranges);
     R3DG_CUDA_TRY(cudaGetLastError());
     return 0;
 }

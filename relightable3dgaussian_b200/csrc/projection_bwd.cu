@@ -48,20 +48,48 @@ __device__ __forceinline__ void cov3d_plain(const float* s3, float mod, const fl
     c6[5] = M[2][0] * M[2][0] + M[2][1] * M[2][1] + M[2][2] * M[2][2];
 }
 
-__global__ void __launch_bounds__(256) projection_bwd_kernel(const ProjBwdParams p) {
+#define PROJ_THREADS 128
+#define SLAB_LD (PROJ_THREADS + 1)
+__global__ void __launch_bounds__(PROJ_THREADS) projection_bwd_kernel(const ProjBwdParams p) {
+    // SH rows (192 B at M=16) travel through a transposed shared slab s[k * SLAB_LD + t]: the
+    // block reads its [128][3M] slab of shs with coalesced 16B vectors, every thread turns its
+    // column into dL/dsh in place, and the slab is written back coalesced (zeros for culled rows).
+    extern __shared__ float sSH[];
     __shared__ float sV[16], sPr[16], sCam[3];
     if (threadIdx.x < 16) { sV[threadIdx.x] = p.viewmatrix[threadIdx.x]; sPr[threadIdx.x] = p.projmatrix[threadIdx.x]; }
     if (threadIdx.x < 3) sCam[threadIdx.x] = p.campos[threadIdx.x];
     __syncthreads();
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= p.P) return;
+    const int idx_raw = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = idx_raw < p.P;
+    const int idx = in_range ? idx_raw : p.P - 1;      // clamp: out-of-range threads only help with the slab
+    const int rowf = 3 * p.M, block_base = blockIdx.x * PROJ_THREADS;
+    const int nvalid = min(PROJ_THREADS, p.P - block_base);
+    if (p.shs) {
+        const int total = nvalid * rowf;
+        const float* src = p.shs + (size_t)block_base * rowf;
+        if ((rowf & 3) == 0) {
+            const float4* src4 = reinterpret_cast<const float4*>(src);
+            for (int i4 = threadIdx.x; i4 < total / 4; i4 += PROJ_THREADS) {
+                const float4 v = src4[i4];
+                const int i = 4 * i4, t = i / rowf, k = i - t * rowf;
+                sSH[(k + 0) * SLAB_LD + t] = v.x; sSH[(k + 1) * SLAB_LD + t] = v.y;
+                sSH[(k + 2) * SLAB_LD + t] = v.z; sSH[(k + 3) * SLAB_LD + t] = v.w;
+            }
+        } else {
+            for (int i = threadIdx.x; i < total; i += PROJ_THREADS) {
+                const int t = i / rowf, k = i - t * rowf;
+                sSH[k * SLAB_LD + t] = src[i];
+            }
+        }
+        __syncthreads();
+    }
     const float* V = sV;
     const float* proj = sPr;
     const float4* rec4 = reinterpret_cast<const float4*>(p.rec + (size_t)idx * p.recf);
     const float4* g4 = reinterpret_cast<const float4*>(p.grad + (size_t)idx * p.recf);
     // radius lives in the record only for Gaussians that passed every cull; read it from there
     // is unsafe for culled ones (row never written) -> visibility comes from tiles/radii arrays.
-    const bool visible = p.radii_rec[idx] > 0;
+    const bool visible = in_range && p.radii_rec[idx] > 0;
 
     float dmean2[3] = {0, 0, 0}, dcol[3] = {0, 0, 0}, dop = 0, dmean3[3] = {0, 0, 0};
     float dcov[6] = {0, 0, 0, 0, 0, 0}, dscale[3] = {0, 0, 0}, drot[4] = {0, 0, 0, 0};
@@ -69,7 +97,7 @@ __global__ void __launch_bounds__(256) projection_bwd_kernel(const ProjBwdParams
     if (visible) { gA = g4[0]; gB = g4[1]; }
 
     // feature gradients: straight copy-out of the packed row
-    if (p.S > 0) {
+    if (p.S > 0 && in_range) {
         float* df = p.dL_dfeatures + (size_t)idx * p.S;
         for (int c = 0; c < p.S; ++c) df[c] = visible ? p.grad[(size_t)idx * p.recf + 11 + c] : 0.0f;
     }
@@ -169,8 +197,7 @@ __global__ void __launch_bounds__(256) projection_bwd_kernel(const ProjBwdParams
             const float dox = mx - sCam[0], doy = my - sCam[1], doz = mz - sCam[2];
             const float len = sqrtf(dox * dox + doy * doy + doz * doz);
             const float x = dox / len, y = doy / len, z = doz / len;
-            const float* sh = p.shs + (size_t)idx * p.M * 3;
-            float* dsh = p.dL_dsh + (size_t)idx * p.M * 3;
+            float* slab = sSH + threadIdx.x;                 // element (k, c) at slab[(3k + c) * SLAB_LD]
             const unsigned cl = p.clamped[idx];
             const float dRGB[3] = {(cl & 1u) ? 0.f : dcol[0], (cl & 2u) ? 0.f : dcol[1], (cl & 4u) ? 0.f : dcol[2]};
             float w[16], wx[16], wy[16], wz[16];   // basis and its derivatives w.r.t. x,y,z
@@ -215,15 +242,14 @@ __global__ void __launch_bounds__(256) projection_bwd_kernel(const ProjBwdParams
                 if (k < p.M) {
                     const bool act = k < ncoef;
                     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-                    if (act) { s0 = sh[3 * k]; s1 = sh[3 * k + 1]; s2 = sh[3 * k + 2]; }
+                    if (act) { s0 = slab[(3 * k) * SLAB_LD]; s1 = slab[(3 * k + 1) * SLAB_LD]; s2 = slab[(3 * k + 2) * SLAB_LD]; }
                     const float dotc = s0 * dRGB[0] + s1 * dRGB[1] + s2 * dRGB[2];
                     ddx += wx[k] * dotc; ddy += wy[k] * dotc; ddz += wz[k] * dotc;
-                    dsh[3 * k] = act ? w[k] * dRGB[0] : 0.f;
-                    dsh[3 * k + 1] = act ? w[k] * dRGB[1] : 0.f;
-                    dsh[3 * k + 2] = act ? w[k] * dRGB[2] : 0.f;
+                    slab[(3 * k) * SLAB_LD] = act ? w[k] * dRGB[0] : 0.f;        // in place: sh -> dL/dsh
+                    slab[(3 * k + 1) * SLAB_LD] = act ? w[k] * dRGB[1] : 0.f;
+                    slab[(3 * k + 2) * SLAB_LD] = act ? w[k] * dRGB[2] : 0.f;
                 }
             }
-            for (int k = 16; k < p.M; ++k) { dsh[3 * k] = 0.f; dsh[3 * k + 1] = 0.f; dsh[3 * k + 2] = 0.f; }
             // dnormvdv (auxiliary.h:105-116)
             const float sum2 = dox * dox + doy * doy + doz * doz;
             const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
@@ -267,9 +293,27 @@ __global__ void __launch_bounds__(256) projection_bwd_kernel(const ProjBwdParams
             drot[3] = 2 * r * (dMt[0][1] - dMt[1][0]) + 2 * x * (dMt[2][0] + dMt[0][2]) + 2 * y * (dMt[1][2] + dMt[2][1]) - 4 * z * (dMt[1][1] + dMt[0][0]);
         }
     } else if (p.shs) {
-        float* dsh = p.dL_dsh + (size_t)idx * p.M * 3;
-        for (int k = 0; k < 3 * p.M; ++k) dsh[k] = 0.f;
+        for (int k = 0; k < rowf; ++k) sSH[k * SLAB_LD + threadIdx.x] = 0.f;
     }
+    if (p.shs) {                                    // coalesced write-back of the dL/dsh slab
+        __syncthreads();
+        const int total = nvalid * rowf;
+        float* dst = p.dL_dsh + (size_t)block_base * rowf;
+        if ((rowf & 3) == 0) {
+            float4* dst4 = reinterpret_cast<float4*>(dst);
+            for (int i4 = threadIdx.x; i4 < total / 4; i4 += PROJ_THREADS) {
+                const int i = 4 * i4, t = i / rowf, k = i - t * rowf;
+                dst4[i4] = make_float4(sSH[(k + 0) * SLAB_LD + t], sSH[(k + 1) * SLAB_LD + t],
+                                       sSH[(k + 2) * SLAB_LD + t], sSH[(k + 3) * SLAB_LD + t]);
+            }
+        } else {
+            for (int i = threadIdx.x; i < total; i += PROJ_THREADS) {
+                const int t = i / rowf, k = i - t * rowf;
+                dst[i] = sSH[k * SLAB_LD + t];
+            }
+        }
+    }
+    if (!in_range) return;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         p.dL_dmeans2D[3 * (size_t)idx + k] = dmean2[k];
@@ -299,7 +343,8 @@ int launch_projection_backward(const r3dg_raster_bwd_args& a, const GeomLayout& 
     p.dL_dmeans2D = a.dL_dmeans2D; p.dL_dcolors = a.dL_dcolors; p.dL_dopacity = a.dL_dopacity;
     p.dL_dmeans3D = a.dL_dmeans3D; p.dL_dfeatures = a.dL_dfeatures; p.dL_dcov3D = a.dL_dcov3D;
     p.dL_dsh = a.dL_dsh; p.dL_dscales = a.dL_dscales; p.dL_drotations = a.dL_drotations;
-    projection_bwd_kernel<<<(a.P + 255) / 256, 256, 0, stream>>>(p);
+    const size_t sh_smem = a.shs ? (size_t)3 * a.M * SLAB_LD * sizeof(float) : 0;
+    projection_bwd_kernel<<<(a.P + PROJ_THREADS - 1) / PROJ_THREADS, PROJ_THREADS, sh_smem, stream>>>(p);
     R3DG_CUDA_TRY(cudaGetLastError());
     return 0;
 }

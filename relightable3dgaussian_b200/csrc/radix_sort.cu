@@ -75,13 +75,18 @@ struct SortSmem {
 };
 
 __global__ void __launch_bounds__(R3DG_SORT_THREADS) sort_onesweep_kernel(
-    GeomHeader* header, long long capacity, int pass, const uint64_t* __restrict__ keys_in,
+    GeomHeader* header, long long capacity, int slot, int passes, const uint64_t* __restrict__ keys_in,
     const uint32_t* __restrict__ vals_in, uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
     const uint32_t* __restrict__ digit_base, volatile uint32_t* lookback) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SortSmem& sm = *reinterpret_cast<SortSmem*>(smem_raw);
     const long long R = min((long long)header->num_rendered, capacity);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // slot = index among the EXECUTED passes; the digit it sorts on is decided on the device
+    const uint32_t depth_diff = header->depth_or & header->depth_nor;
+    const int pass = sort_digit_of_slot(depth_diff, passes, slot);
+    if (pass < 0) return;                              // fewer digits needed than slots launched
+    if (blockIdx.x == 0 && tid == 0 && slot == 0) header->sort_exec = (uint32_t)sort_num_exec(depth_diff, passes);
     const int shift = 8 * pass;
     const long long ntiles = (R + R3DG_SORT_TILE - 1) / R3DG_SORT_TILE;
     constexpr int NW = R3DG_SORT_THREADS / 32;
@@ -89,7 +94,7 @@ __global__ void __launch_bounds__(R3DG_SORT_THREADS) sort_onesweep_kernel(
 
     while (true) {
         __syncthreads();
-        if (tid == 0) sm.tile = atomicAdd(&header->sort_ticket[pass], 1u);
+        if (tid == 0) sm.tile = atomicAdd(&header->sort_ticket[slot], 1u);
         for (int i = tid; i < NW * 256; i += R3DG_SORT_THREADS) (&sm.warp_hist[0][0])[i] = 0;
         __syncthreads();
         const long long tile = sm.tile;
@@ -200,11 +205,11 @@ int launch_sort(void* geom_header, char* bin, const BinLayout& bl, int passes, i
     }
     uint64_t* ka = (uint64_t*)(bin + bl.keys_a); uint64_t* kb = (uint64_t*)(bin + bl.keys_b);
     uint32_t* va = (uint32_t*)(bin + bl.vals_a); uint32_t* vb = (uint32_t*)(bin + bl.vals_b);
-    for (int p = 0; p < passes; ++p) {
-        const bool even = (p & 1) == 0;
+    for (int k = 0; k < passes; ++k) {
+        const bool even = (k & 1) == 0;
         sort_onesweep_kernel<<<num_sms * 3, R3DG_SORT_THREADS, smem, stream>>>(
-            header, bl.capacity, p, even ? ka : kb, even ? va : vb, even ? kb : ka, even ? vb : va, hist,
-            (volatile uint32_t*)(lookback + (size_t)p * bl.max_tiles * 256));
+            header, bl.capacity, k, passes, even ? ka : kb, even ? va : vb, even ? kb : ka, even ? vb : va, hist,
+            (volatile uint32_t*)(lookback + (size_t)k * bl.max_tiles * 256));
     }
     R3DG_CUDA_TRY(cudaGetLastError());
     return 0;
