@@ -138,6 +138,40 @@ long long r3dg_raster_debug_copy(int id, int P, int S, int W, int H, const void*
                                  const void* img, const void* binning, size_t binning_bytes,
                                  void* dst, long long max_bytes, r3dg_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * BVH visibility: LBVH over the Gaussians' 3-sigma boxes + opacity ray trace.
+ * Replaces the reference's `bvh_tracing._C` (bvh/src/bindings.cpp:8-13, bvh/include/bvh.h).
+ * ------------------------------------------------------------------------------------------ */
+size_t r3dg_bvh_build_tmp_bytes(int P);
+size_t r3dg_bvh_trace_tmp_bytes(int P);
+
+/* Fused replacement of the PyTorch prologue of RayTracer.__init__ (bvh/__init__.py:29-57):
+ * fills nodes i32[2P-1,5] (all -1, count column 0 for internal / 1 for leaf nodes) and aabbs
+ * f32[2P-1,6] (internal: +1e5/-1e5, leaf i at row P-1+i: box of the 8 corners mu +- 3 s_a a +- ...),
+ * with the same op-by-op fp32 rounding as the PyTorch expression. */
+int r3dg_bvh_leaf_aabbs(int P, const float* means3D, const float* scales, const float* rotations,
+                        int32_t* nodes, float* aabbs, r3dg_stream_t stream);
+
+/* Replaces create_bvh / construct_bvh (bvh/src/bvh.cu:8-27, bvh/src/construct.cu:147-266):
+ * nodes / aabbs pre-filled as above are completed IN PLACE (leaf half reordered by Morton code,
+ * internal nodes, parent links, subtree leaf counts, refitted boxes); morton u64[P] out.
+ * tmp: r3dg_bvh_build_tmp_bytes(P) bytes of scratch. */
+int r3dg_bvh_build(int P, int32_t* nodes, float* aabbs, uint64_t* morton, void* tmp, size_t tmp_bytes,
+                   r3dg_stream_t stream);
+
+/* Replaces trace_bvh_opacity (bvh/src/bvh.cu:88-116, bvh/src/trace.cu:196-287).  Ray r has
+ * direction rays_d[r] and origin rays_o[r / rays_per_origin] + origin_offset * rays_d[r]
+ * (rays_per_origin = 1, origin_offset = 0 reproduces the reference call; the host mirror of
+ * RayTracer.trace_visibility passes the un-expanded origins and 0.05, bvh/__init__.py:63).
+ * covs3D holds the INVERSE covariances [P,6].  Outputs: num_contributes i32[num_rays],
+ * rendered_opacity f32[num_rays] in {0} U [0.9, 1]; every element is written.
+ * tmp: r3dg_bvh_trace_tmp_bytes(P) bytes of scratch (re-packed tree). */
+int r3dg_bvh_trace_opacity(int P, long long num_rays, const int32_t* nodes, const float* aabbs,
+                           const float* rays_o, int rays_per_origin, float origin_offset,
+                           const float* rays_d, const float* means3D, const float* covs3D,
+                           const float* opacities, const float* normals, int32_t* num_contributes,
+                           float* rendered_opacity, void* tmp, size_t tmp_bytes, r3dg_stream_t stream);
+
 /* Measurement hooks used by bench.py (never needed by the reference's callers).
  * r3dg_launch_count: number of this library's kernels launched so far in the process.
  * r3dg_prof_begin/end: while active, every forward/backward records CUDA events on the launching

@@ -4,5 +4,5 @@
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 gcc -O2 -fopenmp -ffp-contract=off -fno-fast-math -fPIC -shared -Wall -Wno-unknown-pragmas \
-    "$HERE/oracle_raster.c" -o "$HERE/liboracle_raster.so" -lm
+    "$HERE/oracle_raster.c" "$HERE/oracle_bvh.c" -o "$HERE/liboracle_raster.so" -lm
 echo "[oracle] built $HERE/liboracle_raster.so"

@@ -21,8 +21,8 @@ c_fp = ctypes.POINTER(ctypes.c_float)
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle_raster.so")
-    src = os.path.join(_HERE, "oracle_raster.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_raster.c", "oracle_bvh.c", "build.sh")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["bash", os.path.join(_HERE, "build.sh")], stdout=subprocess.DEVNULL)
     return so
 
@@ -236,3 +236,36 @@ def eval_sh(deg, sh, dirs):
                               _C4[7] * xz * (xx - 3 * yy) * sh[..., 23] +
                               _C4[8] * (xx * (xx - 3 * yy) - yy * (3 * xx - yy)) * sh[..., 24])
     return result.astype(np.float32)
+
+
+# ----------------------------------------------------------------------------------------------
+# BVH visibility (oracle_bvh.c): leaf boxes, LBVH build, opacity trace
+# ----------------------------------------------------------------------------------------------
+def bvh_build(means3D, scales, rotations):
+    """bvh/__init__.py:29-59 + construct.cu:147-266.  Returns nodes i32[2P-1,5], aabbs f32[2P-1,6],
+    morton u64[P]."""
+    P = means3D.shape[0]
+    nodes = np.full((2 * P - 1, 5), -1, np.int32)
+    nodes[:P - 1, 4] = 0
+    nodes[P - 1:, 4] = 1
+    aabbs = np.zeros((2 * P - 1, 6), np.float32)
+    aabbs[:, :3] = 100000
+    aabbs[:, 3:] = -100000
+    leaf = np.zeros((P, 6), np.float32)
+    lib().oracle_bvh_leaf_aabbs(ctypes.c_int(P), _p(_f32(means3D)), _p(_f32(scales)), _p(_f32(rotations)), _p(leaf))
+    aabbs[P - 1:] = leaf
+    morton = np.zeros(P, np.uint64)
+    lib().oracle_bvh_build(ctypes.c_int(P), _p(nodes), _p(aabbs), _p(morton))
+    return nodes, aabbs, morton
+
+
+def bvh_trace_opacity(nodes, aabbs, rays_o, rays_d, means3D, covs3D, opacities, normals):
+    """trace.cu:196-287.  rays_o / rays_d [..., 3] contiguous; returns (contribute i32[...], opacity f32[...])."""
+    shape = rays_d.shape[:-1]
+    n = int(np.prod(shape)) if len(shape) else 1
+    contrib = np.zeros(shape, np.int32)
+    opa = np.ones(shape, np.float32)
+    lib().oracle_bvh_trace_opacity(ctypes.c_int64(n), _p(np.ascontiguousarray(nodes, np.int32)), _p(_f32(aabbs)),
+                                   _p(_f32(rays_o)), _p(_f32(rays_d)), _p(_f32(means3D)), _p(_f32(covs3D)),
+                                   _p(_f32(opacities)), _p(_f32(normals)), _p(contrib), _p(opa))
+    return contrib, opa

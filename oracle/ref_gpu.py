@@ -136,3 +136,78 @@ class RefRasterizer:
         if rc != 0:
             raise RuntimeError("reference backward failed")
         return g
+
+
+# ----------------------------------------------------------------------------------------------
+# reference BVH (oracle/_ref/libref_bvh.so)
+# ----------------------------------------------------------------------------------------------
+BVH_LIB_PATH = os.path.join(_HERE, "_ref", "libref_bvh.so")
+_bvh = None
+
+
+def bvh_available():
+    return os.path.exists(BVH_LIB_PATH) and torch.cuda.is_available()
+
+
+def bvh_lib():
+    global _bvh
+    if _bvh is None:
+        _bvh = ctypes.CDLL(BVH_LIB_PATH)
+    return _bvh
+
+
+def ref_leaf_init(means3D, scales, rotations):
+    """bvh/__init__.py:29-57 in PyTorch (build_rotation: utils/general_utils.py:82-103), verbatim op order."""
+    P = means3D.shape[0]
+    r = rotations
+    norm = torch.sqrt(r[:, 0] * r[:, 0] + r[:, 1] * r[:, 1] + r[:, 2] * r[:, 2] + r[:, 3] * r[:, 3])
+    q = r / norm[:, None]
+    rot = torch.zeros((q.size(0), 3, 3), device=r.device)
+    rr, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    rot[:, 0, 0] = 1 - 2 * (y * y + z * z); rot[:, 0, 1] = 2 * (x * y - rr * z); rot[:, 0, 2] = 2 * (x * z + rr * y)
+    rot[:, 1, 0] = 2 * (x * y + rr * z); rot[:, 1, 1] = 1 - 2 * (x * x + z * z); rot[:, 1, 2] = 2 * (y * z - rr * x)
+    rot[:, 2, 0] = 2 * (x * z - rr * y); rot[:, 2, 1] = 2 * (y * z + rr * x); rot[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    nodes = torch.full((2 * P - 1, 5), -1, device=r.device).int()
+    nodes[:P - 1, 4] = 0
+    nodes[P - 1:, 4] = 1
+    aabbs = torch.zeros(2 * P - 1, 6, device=r.device).float()
+    aabbs[:, :3] = 100000
+    aabbs[:, 3:] = -100000
+    a, b, c = rot[:, :, 0], rot[:, :, 1], rot[:, :, 2]
+    m = 3
+    sa, sb, sc = m * scales[:, 0], m * scales[:, 1], m * scales[:, 2]
+    xs = [means3D + s0 * a * sa[:, None] + s1 * b * sb[:, None] + s2 * c * sc[:, None]
+          for s0 in (1, -1) for s1 in (1, -1) for s2 in (1, -1)]
+    # (means +- a*sa) +- b*sb +- c*sc : multiplying by +-1 is exact, so this is the reference's rounding
+    aabb_min = xs[0]
+    aabb_max = xs[0]
+    for t in xs[1:]:
+        aabb_min = torch.minimum(aabb_min, t)
+        aabb_max = torch.maximum(aabb_max, t)
+    aabbs[P - 1:] = torch.cat([aabb_min, aabb_max], dim=-1)
+    return nodes.contiguous(), aabbs.contiguous()
+
+
+def ref_bvh_create(means3D, scales, rotations):
+    nodes, aabbs = ref_leaf_init(means3D, scales, rotations)
+    P = means3D.shape[0]
+    morton = torch.zeros(P, dtype=torch.int64, device=means3D.device)
+    torch.cuda.synchronize()
+    rc = bvh_lib().ref_bvh_create(P, _p(means3D.contiguous()), _p(scales.contiguous()), _p(rotations.contiguous()),
+                                  _p(nodes), _p(aabbs), _p(morton))
+    if rc != 0:
+        raise RuntimeError("reference create_bvh failed")
+    return nodes, aabbs, morton
+
+
+def ref_bvh_trace_opacity(nodes, aabbs, rays_o, rays_d, means3D, covs3D, opacities, normals):
+    shape = rays_d.shape[:-1]
+    n = rays_d.numel() // 3
+    contrib = torch.zeros(shape, dtype=torch.int32, device=rays_d.device)
+    opa = torch.ones(shape, dtype=torch.float32, device=rays_d.device)
+    ts = [t.contiguous() for t in (rays_o, rays_d, means3D, covs3D, opacities, normals)]
+    torch.cuda.synchronize()
+    rc = bvh_lib().ref_bvh_trace_opacity(n, _p(nodes), _p(aabbs), *[_p(t) for t in ts], _p(contrib), _p(opa))
+    if rc != 0:
+        raise RuntimeError("reference trace_bvh_opacity failed")
+    return contrib, opa

@@ -55,6 +55,13 @@ SYMBOLS = [
     ("r3dg_raster_forward", c_int, [ctypes.POINTER(RasterFwdArgs), c_void_p]),
     ("r3dg_raster_backward", c_int, [ctypes.POINTER(RasterBwdArgs), c_void_p]),
     ("r3dg_mark_visible", c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    ("r3dg_bvh_build_tmp_bytes", c_size_t, [c_int]),
+    ("r3dg_bvh_trace_tmp_bytes", c_size_t, [c_int]),
+    ("r3dg_bvh_leaf_aabbs", c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    ("r3dg_bvh_build", c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    ("r3dg_bvh_trace_opacity", c_int, [c_int, c_ll, c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_size_t, c_void_p]),
     ("r3dg_launch_count", ctypes.c_ulonglong, []),
     ("r3dg_prof_begin", c_int, [c_int]),
     ("r3dg_prof_end", c_int, [ctypes.POINTER(c_float), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),

@@ -167,6 +167,35 @@ int r3dg_mark_visible(int P, const float* means3D, const float* viewmatrix, cons
     return launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
 }
 
+// ---- BVH visibility (bvh_tracing._C) -------------------------------------------------------
+size_t r3dg_bvh_build_tmp_bytes(int P) { return bvh_build_tmp_bytes(P); }
+size_t r3dg_bvh_trace_tmp_bytes(int P) { return bvh_packets_bytes(P); }
+
+int r3dg_bvh_leaf_aabbs(int P, const float* means3D, const float* scales, const float* rotations,
+                        int32_t* nodes, float* aabbs, r3dg_stream_t stream) {
+    g_launches += P > 0 ? 1 : 0;
+    return launch_bvh_leaf_aabbs(P, means3D, scales, rotations, nodes, aabbs, (cudaStream_t)stream);
+}
+
+int r3dg_bvh_build(int P, int32_t* nodes, float* aabbs, uint64_t* morton, void* tmp, size_t tmp_bytes,
+                   r3dg_stream_t stream) {
+    if (P < 0) return R3DG_ERR_BAD_ARG;
+    g_launches += P > 0 ? 6 + 2 + 4 : 0;
+    return launch_bvh_build(P, nodes, aabbs, morton, tmp, tmp_bytes, num_sms(), (cudaStream_t)stream);
+}
+
+int r3dg_bvh_trace_opacity(int P, long long num_rays, const int32_t* nodes, const float* aabbs,
+                           const float* rays_o, int rays_per_origin, float origin_offset, const float* rays_d,
+                           const float* means3D, const float* covs3D, const float* opacities,
+                           const float* normals, int32_t* num_contributes, float* rendered_opacity,
+                           void* tmp, size_t tmp_bytes, r3dg_stream_t stream) {
+    if (P < 0 || num_rays < 0) return R3DG_ERR_BAD_ARG;
+    g_launches += (P > 0 && num_rays > 0) ? 2 : 0;
+    return launch_bvh_trace(P, num_rays, nodes, aabbs, rays_o, rays_per_origin, origin_offset, rays_d, means3D, covs3D,
+                            opacities, normals, num_contributes, rendered_opacity, tmp, tmp_bytes, num_sms(),
+                            (cudaStream_t)stream);
+}
+
 namespace {
 __global__ void unpack_rec_kernel(int P, int recf, int what, const float* __restrict__ rec,
                                   const uint32_t* __restrict__ tiles, float* __restrict__ dst) {

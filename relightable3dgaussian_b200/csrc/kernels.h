@@ -25,4 +25,16 @@ int launch_composite_backward(const r3dg_raster_bwd_args& a, const GeomLayout& g
 int launch_projection_backward(const r3dg_raster_bwd_args& a, const GeomLayout& gl,
                                cudaStream_t stream);
 
+size_t bvh_build_tmp_bytes(int P);
+size_t bvh_packets_bytes(int P);
+int launch_bvh_leaf_aabbs(int P, const float* means3D, const float* scales, const float* rotations,
+                          int32_t* nodes, float* aabbs, cudaStream_t stream);
+int launch_bvh_build(int P, int32_t* nodes, float* aabbs, uint64_t* morton, void* tmp, size_t tmp_bytes,
+                     int num_sms, cudaStream_t stream);
+int launch_bvh_trace(int P, long long num_rays, const int32_t* nodes, const float* aabbs,
+                     const float* rays_o, int o_group, float o_offset, const float* rays_d,
+                     const float* means3D, const float* covs3D, const float* opacities,
+                     const float* normals, int32_t* num_contributes, float* rendered_opacity,
+                     void* packets, size_t packets_bytes, int num_sms, cudaStream_t stream);
+
 }  // namespace r3dg

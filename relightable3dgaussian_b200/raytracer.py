@@ -1,0 +1,107 @@
+"""Host-side mirror of the reference's BVH operator surface: `RayTracer` (bvh/__init__.py:28-71),
+`sample_incident_rays` / `fibonacci_sphere_sampling` / `rotation_between_z`
+(scene/gaussian_model.py:20-28, utils/graphics_utils.py:9-37, utils/sh_utils.py:36-68) and the
+visibility bake `update_visibility` (scene/gaussian_model.py:312-342), on the B200 kernels.
+
+Differences from the reference that are not observable in the results:
+  * the ~60 small PyTorch kernels of RayTracer.__init__ are one fused kernel (same fp32 rounding);
+  * trace_visibility does not materialise `rays_o + 0.05 * rays_d` nor the expanded origins: the
+    trace kernel forms them per ray (same fp32 ops), saving 24 B/ray of HBM traffic.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _C_bvh as _C
+from . import _lib
+
+
+def rotation_between_z(vec):
+    """utils/sh_utils.py:36-68 (device-agnostic restatement)."""
+    v1, v2 = -vec[..., 1], vec[..., 0]
+    v3 = torch.zeros_like(v1)
+    v11, v22, v33 = v1 * v1, v2 * v2, v3 * v3
+    v12, v13, v23 = v1 * v2, v1 * v3, v2 * v3
+    cos_p_1 = (vec[..., 2] + 1).clamp_min(1e-7)
+    R = torch.zeros(vec.shape[:-1] + (3, 3), dtype=torch.float32, device=vec.device)
+    R[..., 0, 0] = 1 + (-v33 - v22) / cos_p_1
+    R[..., 0, 1] = -v3 + v12 / cos_p_1
+    R[..., 0, 2] = v2 + v13 / cos_p_1
+    R[..., 1, 0] = v3 + v12 / cos_p_1
+    R[..., 1, 1] = 1 + (-v33 - v11) / cos_p_1
+    R[..., 1, 2] = -v1 + v23 / cos_p_1
+    R[..., 2, 0] = -v2 + v13 / cos_p_1
+    R[..., 2, 1] = v1 + v23 / cos_p_1
+    R[..., 2, 2] = 1 + (-v22 - v11) / cos_p_1
+    return torch.where((vec[..., 2] + 1 > 0)[..., None, None], R,
+                       -torch.eye(3, dtype=torch.float32, device=vec.device).expand_as(R))
+
+
+def fibonacci_sphere_sampling(normals, sample_num, random_rotate=True):
+    """utils/graphics_utils.py:9-37."""
+    pre_shape = normals.shape[:-1]
+    if len(pre_shape) > 1:
+        normals = normals.reshape(-1, 3)
+    delta = np.pi * (3.0 - np.sqrt(5.0))
+    idx = torch.arange(sample_num, dtype=torch.float, device=normals.device)[None]
+    z = (1 - 2 * idx / (2 * sample_num - 1)).clamp_min(np.sin(10 / 180 * np.pi))
+    rad = torch.sqrt(1 - z ** 2)
+    theta = delta * idx
+    if random_rotate:
+        theta = torch.rand(*pre_shape, 1, device=normals.device) * 2 * np.pi + theta
+    y = torch.cos(theta) * rad
+    x = torch.sin(theta) * rad
+    z_samples = torch.stack([x, y, z.expand_as(y)], dim=-2)
+    incident_dirs = rotation_between_z(normals) @ z_samples
+    incident_dirs = F.normalize(incident_dirs, dim=-2).transpose(-1, -2)
+    incident_areas = torch.ones_like(incident_dirs)[..., 0:1] * 2 * np.pi
+    if len(pre_shape) > 1:
+        incident_dirs = incident_dirs.reshape(*pre_shape, sample_num, 3)
+        incident_areas = incident_areas.reshape(*pre_shape, sample_num, 1)
+    return incident_dirs, incident_areas
+
+
+def sample_incident_rays(normals, is_training=False, sample_num=24):
+    """scene/gaussian_model.py:20-28."""
+    return fibonacci_sphere_sampling(normals, sample_num, random_rotate=bool(is_training))
+
+
+class RayTracer:
+    """bvh/__init__.py:28-71: builds the LBVH in __init__, `trace_visibility` bakes T in {0} U [0.9,1]."""
+
+    def __init__(self, means3D, scales, rotations):
+        lib = _lib.load()
+        P = means3D.shape[0]
+        dev = means3D.device
+        nodes = torch.empty((2 * P - 1, 5), dtype=torch.int32, device=dev)
+        aabbs = torch.empty((2 * P - 1, 6), dtype=torch.float32, device=dev)
+        m, s, r = (t.detach().float().contiguous() for t in (means3D, scales, rotations))
+        stream = torch.cuda.current_stream(dev)
+        _lib.check(lib.r3dg_bvh_leaf_aabbs(P, m.data_ptr(), s.data_ptr(), r.data_ptr(), nodes.data_ptr(),
+                                           aabbs.data_ptr(), stream.cuda_stream), "RayTracer leaf boxes")
+        self.tree, self.aabb, self.morton = _C.create_bvh(m, s, r, nodes, aabbs)
+
+    @torch.no_grad()
+    def trace_visibility(self, rays_o, rays_d, means3D, symm_inv, opacity, normals):
+        # origins that are an expand() over the sample dimension are passed un-expanded
+        group = 1
+        if rays_o.dim() >= 2 and rays_o.shape == rays_d.shape and rays_o.stride(-2) == 0 and rays_d.is_contiguous():
+            group = rays_o.shape[-2]
+            rays_o = rays_o[..., 0, :]
+        cotrib, opa = _C._trace(self.tree, self.aabb, rays_o, group, 0.05, rays_d, means3D, symm_inv, opacity, normals)
+        return {"visibility": opa.unsqueeze(-1), "contribute": cotrib.unsqueeze(-1)}
+
+
+@torch.no_grad()
+def update_visibility(xyz, scaling, rotation, inverse_covariance, opacity, normal, sample_num):
+    """scene/gaussian_model.py:312-342 as a free function of the activated Gaussian tensors.
+    Returns (visibility [P,N,1], incident_dirs [P,N,3], incident_areas [P,N,1])."""
+    raytracer = RayTracer(xyz, scaling, rotation)
+    vis, dirs, areas = [], [], []
+    chunk_size = max(1, xyz.shape[0] // ((sample_num - 1) // 24 + 1))
+    for offset in range(0, xyz.shape[0], chunk_size):
+        d, a = sample_incident_rays(normal[offset:offset + chunk_size], False, sample_num)
+        res = raytracer.trace_visibility(xyz[offset:offset + chunk_size, None].expand_as(d), d, xyz,
+                                         inverse_covariance, opacity, normal)
+        vis.append(res["visibility"]); dirs.append(d); areas.append(a)
+    return torch.cat(vis, dim=0), torch.cat(dirs, dim=0), torch.cat(areas, dim=0)

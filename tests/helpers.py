@@ -52,3 +52,36 @@ def max_rel_above_floor(a, b, floor=1e-6):
     if not m.any():
         return 0.0
     return float((np.abs(a - b)[m] / np.abs(b)[m]).max())
+
+
+def inverse_covariance(scales, rotations):
+    """scene/gaussian_model.py:257-260 + utils/general_utils.py:151-160 (strip_symmetric of
+    L L^T with L = R diag(1/s)); torch ops, device of the inputs."""
+    r = rotations
+    norm = torch.sqrt(r[:, 0] * r[:, 0] + r[:, 1] * r[:, 1] + r[:, 2] * r[:, 2] + r[:, 3] * r[:, 3])
+    q = r / norm[:, None]
+    R = torch.zeros((q.size(0), 3, 3), device=r.device)
+    rr, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R[:, 0, 0] = 1 - 2 * (y * y + z * z); R[:, 0, 1] = 2 * (x * y - rr * z); R[:, 0, 2] = 2 * (x * z + rr * y)
+    R[:, 1, 0] = 2 * (x * y + rr * z); R[:, 1, 1] = 1 - 2 * (x * x + z * z); R[:, 1, 2] = 2 * (y * z - rr * x)
+    R[:, 2, 0] = 2 * (x * z - rr * y); R[:, 2, 1] = 2 * (y * z + rr * x); R[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    L = torch.zeros((q.size(0), 3, 3), dtype=torch.float, device=r.device)
+    inv_s = 1 / scales
+    L[:, 0, 0] = inv_s[:, 0]; L[:, 1, 1] = inv_s[:, 1]; L[:, 2, 2] = inv_s[:, 2]
+    L = R @ L
+    cov = L @ L.transpose(1, 2)
+    return torch.stack([cov[:, 0, 0], cov[:, 0, 1], cov[:, 0, 2], cov[:, 1, 1], cov[:, 1, 2], cov[:, 2, 2]], dim=-1).contiguous()
+
+
+def bvh_case(recipe, P, n_src, N, boost, seed=3):
+    """Seeded BVH / visibility case: P Gaussians, rays from the first n_src of them along N
+    Fibonacci directions around the FLIPPED normal (so that they run through the scene),
+    origins pre-offset by 0.05 d like bvh/__init__.py:63."""
+    from relightable3dgaussian_b200.raytracer import fibonacci_sphere_sampling
+    sc = synth.make_scene(P, recipe, seed, 0)
+    scales = sc.scales * boost
+    normals = sc.normals
+    dirs, _ = fibonacci_sphere_sampling(-normals[:n_src], N, random_rotate=False)
+    rays_o = (sc.means3D[:n_src, None] + dirs * 0.05).contiguous()
+    return dict(means3D=sc.means3D, scales=scales.contiguous(), rotations=sc.rotations, opacity=sc.opacities[:, 0].contiguous(),
+                normals=normals, inv_cov=inverse_covariance(scales, sc.rotations), rays_o=rays_o, rays_d=dirs.contiguous())
