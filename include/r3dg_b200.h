@@ -172,6 +172,53 @@ int r3dg_bvh_trace_opacity(int P, long long num_rays, const int32_t* nodes, cons
                            const float* opacities, const float* normals, int32_t* num_contributes,
                            float* rendered_opacity, void* tmp, size_t tmp_bytes, r3dg_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * BRDF shading: fused `rendering_equation` (gaussian_renderer/neilf.py:339-371) + `GGX_specular`
+ * (:374-406) + lat-long environment lookup (scene/direct_light_map.py:70-83) + SH incident light.
+ * The reference has no extension boundary here (pure PyTorch; its render_equation.cu is dead,
+ * unbuilt code with a different BRDF — SURVEY.md fact 2); the host mirror
+ * relightable3dgaussian_b200/shading.py gives this entry the reference function's signature.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct r3dg_shade_args {
+    int P, N;                          /* Gaussians, incident samples per Gaussian */
+    int sh_coeffs;                     /* incidents.shape[1]; 16 (degree 3) is supported */
+    int env_h, env_w;                  /* environment texture size */
+    const float* base_color;           /* [P,3] */
+    const float* roughness;            /* [P]   */
+    const float* normals;              /* [P,3] (no gradient: detached at neilf.py:94) */
+    const float* viewdirs;             /* [P,3] */
+    const float* incidents;            /* [P,16,3] SH coefficients of the local incident light */
+    const float* env;                  /* [env_h,env_w,3] ACTIVATED environment map (softplus / HDR) */
+    const float* env_transform;        /* [3,3] row-major or NULL (EnvLight.transform, envmap.py:39-42) */
+    const float* visibility;           /* [P,N]   baked */
+    const float* incident_dirs;        /* [P,N,3] baked */
+    const float* incident_areas;       /* [P,N]   baked */
+    /* forward outputs; the three [P,3] means and mean_visibility are optional (all or none),
+     * the three per-sample [P,N,3] arrays are optional (all or none, eval only) */
+    float* pbr;                        /* [P,3] */
+    float* diffuse_light;              /* [P,3] */
+    float* specular;                   /* [P,3] */
+    float* mean_incident_lights;       /* [P,3] or NULL  (= incident_lights.mean(-2)) */
+    float* mean_local_lights;          /* [P,3] or NULL */
+    float* mean_global_lights;         /* [P,3] or NULL */
+    float* mean_visibility;            /* [P]   or NULL */
+    float* incident_lights;            /* [P,N,3] or NULL */
+    float* local_incident_lights;      /* [P,N,3] or NULL */
+    float* global_incident_lights;     /* [P,N,3] or NULL */
+    /* backward: cotangents (dL_dpbr required, the others may be NULL) and gradients out */
+    const float* dL_dpbr;              /* [P,3] */
+    const float* dL_ddiffuse_light;    /* [P,3] or NULL */
+    const float* dL_dspecular;         /* [P,3] or NULL */
+    float* dL_dbase_color;             /* [P,3] */
+    float* dL_droughness;              /* [P] */
+    float* dL_dviewdirs;               /* [P,3] */
+    float* dL_dincidents;              /* [P,16,3] */
+    float* dL_denv;                    /* [env_h,env_w,3] (zeroed, then accumulated) */
+} r3dg_shade_args;
+
+int r3dg_render_equation_forward(const r3dg_shade_args* args, r3dg_stream_t stream);
+int r3dg_render_equation_backward(const r3dg_shade_args* args, r3dg_stream_t stream);
+
 /* Measurement hooks used by bench.py (never needed by the reference's callers).
  * r3dg_launch_count: number of this library's kernels launched so far in the process.
  * r3dg_prof_begin/end: while active, every forward/backward records CUDA events on the launching

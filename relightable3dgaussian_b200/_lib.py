@@ -45,6 +45,18 @@ class RasterBwdArgs(ctypes.Structure):
          ("binning", c_void_p), ("binning_bytes", c_size_t)])
 
 
+class ShadeArgs(ctypes.Structure):
+    _fields_ = (
+        [(n, c_int) for n in ("P", "N", "sh_coeffs", "env_h", "env_w")] +
+        [(n, c_void_p) for n in ("base_color", "roughness", "normals", "viewdirs", "incidents", "env",
+                                 "env_transform", "visibility", "incident_dirs", "incident_areas",
+                                 "pbr", "diffuse_light", "specular", "mean_incident_lights",
+                                 "mean_local_lights", "mean_global_lights", "mean_visibility",
+                                 "incident_lights", "local_incident_lights", "global_incident_lights",
+                                 "dL_dpbr", "dL_ddiffuse_light", "dL_dspecular", "dL_dbase_color",
+                                 "dL_droughness", "dL_dviewdirs", "dL_dincidents", "dL_denv")])
+
+
 # every symbol include/r3dg_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("r3dg_version", ctypes.c_char_p, []),
@@ -62,6 +74,8 @@ SYMBOLS = [
     ("r3dg_bvh_trace_opacity", c_int, [c_int, c_ll, c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_size_t, c_void_p]),
+    ("r3dg_render_equation_forward", c_int, [ctypes.POINTER(ShadeArgs), c_void_p]),
+    ("r3dg_render_equation_backward", c_int, [ctypes.POINTER(ShadeArgs), c_void_p]),
     ("r3dg_launch_count", ctypes.c_ulonglong, []),
     ("r3dg_prof_begin", c_int, [c_int]),
     ("r3dg_prof_end", c_int, [ctypes.POINTER(c_float), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),

@@ -14,6 +14,12 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
          "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 
 
+# shading.cu mirrors a chain of separate PyTorch elementwise kernels (each op rounded on its own);
+# without FMA contraction the fused kernel reproduces that rounding instead of a differently
+# (if slightly better) rounded result of an ill-conditioned GGX denominator.
+PER_FILE_FLAGS = {"shading.cu": ["-fmad=false"]}
+
+
 def sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 
@@ -35,7 +41,8 @@ def build(force=False, verbose=False):
         obj = os.path.join(CSRC, s[:-3] + ".o")
         objs.append(obj)
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr):
-            jobs.append([NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
+            extra = PER_FILE_FLAGS.get(s, [])
+            jobs.append([NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
     if jobs:
         def run(cmd):
             r = subprocess.run(cmd, capture_output=True, text=True)

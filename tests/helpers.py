@@ -85,3 +85,22 @@ def bvh_case(recipe, P, n_src, N, boost, seed=3):
     rays_o = (sc.means3D[:n_src, None] + dirs * 0.05).contiguous()
     return dict(means3D=sc.means3D, scales=scales.contiguous(), rotations=sc.rotations, opacity=sc.opacities[:, 0].contiguous(),
                 normals=normals, inv_cov=inverse_covariance(scales, sc.rotations), rays_o=rays_o, rays_d=dirs.contiguous())
+
+
+def shading_case(P, N, He, seed):
+    """Seeded inputs of `rendering_equation` (neilf.py:339): activated material parameters, SH
+    incident light, raw env map (softplus applied by the light object), baked visibility / dirs."""
+    from relightable3dgaussian_b200.raytracer import fibonacci_sphere_sampling
+    g = torch.Generator().manual_seed(500 + seed)
+    n = torch.nn.functional.normalize(torch.randn(P, 3, generator=g), dim=-1)
+    dirs, areas = fibonacci_sphere_sampling(n, N, random_rotate=False)
+    vis = torch.where(torch.rand(P, N, 1, generator=g) < 0.4, torch.zeros(P, N, 1), 0.9 + 0.1 * torch.rand(P, N, 1, generator=g))
+    return dict(base_color=torch.sigmoid(torch.randn(P, 3, generator=g)) * 0.77 + 0.03,
+                roughness=torch.sigmoid(torch.randn(P, 1, generator=g)) * 0.9 + 0.09,
+                normals=(n + 0.05 * torch.randn(P, 3, generator=g)).contiguous(),       # deliberately not unit length
+                viewdirs=torch.nn.functional.normalize(torch.randn(P, 3, generator=g), dim=-1),
+                incidents=(torch.randn(P, 16, 3, generator=g) * 0.3).contiguous(),
+                env_raw=torch.randn(1, He, 2 * He, 3, generator=g),
+                visibility=vis.contiguous(), incident_dirs=dirs.contiguous(), incident_areas=areas.contiguous(),
+                cot_pbr=torch.randn(P, 3, generator=g), cot_diffuse=torch.randn(P, 3, generator=g),
+                cot_specular=torch.randn(P, 3, generator=g))

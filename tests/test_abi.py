@@ -30,7 +30,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_field_order_matches_header():
     hdr = open(os.path.join(ROOT, "include", "r3dg_b200.h")).read()
-    for cname, cls in (("r3dg_raster_fwd_args", _lib.RasterFwdArgs), ("r3dg_raster_bwd_args", _lib.RasterBwdArgs)):
+    for cname, cls in (("r3dg_raster_fwd_args", _lib.RasterFwdArgs), ("r3dg_raster_bwd_args", _lib.RasterBwdArgs),
+                       ("r3dg_shade_args", _lib.ShadeArgs)):
         body = re.search(r"typedef struct " + cname + r" \{(.*?)\} " + cname + ";", hdr, re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         fields = []

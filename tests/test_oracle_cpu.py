@@ -9,6 +9,7 @@ import os
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 from helpers import GOLDEN, case_inputs, max_rel_above_floor, npy, oracle_kwargs, rel_l2, sh_case
 from oracle import oracle
@@ -155,3 +156,25 @@ def test_bvh_oracle_matches_reference_cuda_golden(path):
     assert flips <= 5e-3, flips
     assert np.abs(vis - g["visibility"])[same].max() <= 1e-4
     assert (cont != g["contribute"])[same].mean() <= 5e-3
+
+
+SHADING_CASES = sorted(glob.glob(os.path.join(GOLDEN, "shading_*.npz")))
+
+
+@pytest.mark.parametrize("path", SHADING_CASES, ids=[os.path.basename(p)[8:-4] for p in SHADING_CASES])
+def test_shading_oracle_matches_reference_function_golden(path):
+    """PyTorch restatement of rendering_equation / GGX_specular / direct_light vs outputs and autograd
+    gradients of the reference's own function bodies (make_golden_shading.py)."""
+    from oracle import oracle_shading as osh
+    g = np.load(path)
+    t = lambda k: torch.from_numpy(g["in_" + k])
+    leaves = {k: t(k).clone().requires_grad_(True) for k in ("base_color", "roughness", "viewdirs", "incidents", "env_raw")}
+    env_tex = F.softplus(leaves["env_raw"])[0]
+    pbr, ex = osh.rendering_equation(leaves["base_color"], leaves["roughness"], t("normals"), leaves["viewdirs"],
+                                     leaves["incidents"], env_tex, t("visibility"), t("incident_dirs"), t("incident_areas"))
+    np.testing.assert_allclose(pbr.detach().numpy(), g["pbr"], rtol=1e-5, atol=1e-6)
+    for k in ("incident_lights", "local_incident_lights", "global_incident_lights", "diffuse_light", "specular"):
+        np.testing.assert_allclose(ex[k].detach().numpy(), g["x_" + k], rtol=1e-5, atol=1e-6)
+    ((pbr * t("cot_pbr")).sum() + (ex["diffuse_light"] * t("cot_diffuse")).sum() + (ex["specular"] * t("cot_specular")).sum()).backward()
+    for k, v in leaves.items():
+        assert rel_l2(v.grad.numpy(), g["grad_" + k]) < 1e-5, k
