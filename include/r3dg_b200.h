@@ -219,6 +219,13 @@ typedef struct r3dg_shade_args {
 int r3dg_render_equation_forward(const r3dg_shade_args* args, r3dg_stream_t stream);
 int r3dg_render_equation_backward(const r3dg_shade_args* args, r3dg_stream_t stream);
 
+/* Replaces `simple_knn._C.distCUDA2` (submodules/simple-knn/spatial.cu:15-26, simple_knn.cu:185-221):
+ * mean_dist2[i] = mean of the 3 smallest squared distances from point i to the other points.
+ * Init-time only in the reference (scene/gaussian_model.py:427), but imported at module import. */
+size_t r3dg_knn_tmp_bytes(int P);
+int r3dg_knn_dist2(int P, const float* points /* [P,3] */, float* mean_dist2 /* [P] */, void* tmp,
+                   size_t tmp_bytes, r3dg_stream_t stream);
+
 /* Measurement hooks used by bench.py (never needed by the reference's callers).
  * r3dg_launch_count: number of this library's kernels launched so far in the process.
  * r3dg_prof_begin/end: while active, every forward/backward records CUDA events on the launching

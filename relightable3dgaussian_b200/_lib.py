@@ -76,6 +76,8 @@ SYMBOLS = [
                                        c_size_t, c_void_p]),
     ("r3dg_render_equation_forward", c_int, [ctypes.POINTER(ShadeArgs), c_void_p]),
     ("r3dg_render_equation_backward", c_int, [ctypes.POINTER(ShadeArgs), c_void_p]),
+    ("r3dg_knn_tmp_bytes", c_size_t, [c_int]),
+    ("r3dg_knn_dist2", c_int, [c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     ("r3dg_launch_count", ctypes.c_ulonglong, []),
     ("r3dg_prof_begin", c_int, [c_int]),
     ("r3dg_prof_end", c_int, [ctypes.POINTER(c_float), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),

@@ -196,6 +196,14 @@ int r3dg_bvh_trace_opacity(int P, long long num_rays, const int32_t* nodes, cons
                             (cudaStream_t)stream);
 }
 
+// ---- simple_knn._C.distCUDA2 ----------------------------------------------------------------
+size_t r3dg_knn_tmp_bytes(int P) { return knn_tmp_bytes(P); }
+int r3dg_knn_dist2(int P, const float* points, float* mean_dist2, void* tmp, size_t tmp_bytes, r3dg_stream_t stream) {
+    if (P < 0) return R3DG_ERR_BAD_ARG;
+    g_launches += P > 0 ? 6 + 2 + 4 : 0;
+    return launch_knn(P, points, mean_dist2, tmp, tmp_bytes, num_sms(), (cudaStream_t)stream);
+}
+
 namespace {
 __global__ void unpack_rec_kernel(int P, int recf, int what, const float* __restrict__ rec,
                                   const uint32_t* __restrict__ tiles, float* __restrict__ dst) {

@@ -37,4 +37,7 @@ int launch_bvh_trace(int P, long long num_rays, const int32_t* nodes, const floa
                      const float* normals, int32_t* num_contributes, float* rendered_opacity,
                      void* packets, size_t packets_bytes, int num_sms, cudaStream_t stream);
 
+size_t knn_tmp_bytes(int P);
+int launch_knn(int P, const float* points, float* out, void* tmp, size_t tmp_bytes, int num_sms, cudaStream_t stream);
+
 }  // namespace r3dg
