@@ -18,16 +18,44 @@ import torch
 
 from . import _lib
 
-_state = {}          # per-device speculative capacity + pinned readback slot
+_state = {}          # per-device speculative capacity + pinned readback slots
+_SLOTS = 64
 
 
 def _dev_state(device):
     key = device.index if device.index is not None else torch.cuda.current_device()
     st = _state.get(key)
     if st is None:
-        st = {"capacity": 0, "pinned": torch.zeros(1, dtype=torch.int32).pin_memory()}
+        st = {"capacity": 0, "pinned": torch.zeros(_SLOTS, dtype=torch.int32).pin_memory(), "next": 0}
         _state[key] = st
     return st
+
+
+class DeferredCount:
+    """`num_rendered` of a forward whose read-back has not been waited for yet (opt-in, see
+    rasterizer.set_deferred_count).  int() / resolve() waits for the forward's event; an
+    overflow of the speculative binning buffer is reported then (nothing out of bounds was
+    written, but that forward's outputs are invalid)."""
+
+    def __init__(self, event, slot_view, capacity, state, P):
+        self._event, self._slot, self._capacity, self._state, self._P = event, slot_view, capacity, state, P
+        self._value = None
+
+    def resolve(self):
+        if self._value is None:
+            self._event.synchronize()
+            self._value = int(self._slot.item())
+            self._state["capacity"] = max(int(self._value * 1.5) + 4096, 4 * self._P + 4096)
+            if self._value > self._capacity:
+                raise RuntimeError(
+                    f"deferred rasterization overflowed its speculative binning buffer ({self._value} instances > "
+                    f"capacity {self._capacity}); the outputs of that forward are invalid — call it again")
+        return self._value
+
+    __int__ = __index__ = resolve
+
+    def __repr__(self):
+        return f"DeferredCount({self._value if self._value is not None else 'pending'})"
 
 
 def _ptr(t):
@@ -51,7 +79,7 @@ def _prep(t, name):
 def rasterize_gaussians(background, means3D, features, colors, opacity, scales, rotations,
                         scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
                         cx, cy, image_height, image_width, sh, degree, campos, prefiltered,
-                        computer_pseudo_normal, debug):
+                        computer_pseudo_normal, debug, _defer=False):
     """== RasterizeGaussiansCUDA (rasterize_points.cu:36-141).  Returns the 13-tuple
     (rendered, n_contrib, out_color, out_opacity, out_depth, out_feature, out_normal,
      out_surface_xyz, out_weights, radii, geomBuffer, binningBuffer, imgBuffer)."""
@@ -86,6 +114,9 @@ def rasterize_gaussians(background, means3D, features, colors, opacity, scales, 
     st = _dev_state(dev)
     capacity = max(st["capacity"], 4 * P + 4096)
     stream = torch.cuda.current_stream(dev)
+    slot = st["next"]
+    st["next"] = (slot + 1) % _SLOTS
+    pinned = st["pinned"][slot:slot + 1]
     while True:
         binningBuffer = torch.empty((lib.r3dg_raster_binning_bytes(capacity),), dtype=torch.uint8,
                                     device=dev)
@@ -106,14 +137,20 @@ def rasterize_gaussians(background, means3D, features, colors, opacity, scales, 
         a.geom = geomBuffer.data_ptr(); a.geom_bytes = geomBuffer.numel()
         a.img = imgBuffer.data_ptr(); a.img_bytes = imgBuffer.numel()
         a.binning = binningBuffer.data_ptr(); a.binning_bytes = binningBuffer.numel()
-        a.num_rendered_host = st["pinned"].data_ptr()
+        a.num_rendered_host = pinned.data_ptr()
         _lib.check(lib.r3dg_raster_forward(ctypes.byref(a), stream.cuda_stream), "rasterize_gaussians")
+        if _defer:                    # opt-in: let the host run ahead; the count is resolved later
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            rendered = DeferredCount(ev, pinned, capacity, st, P)
+            break
         stream.synchronize()          # the one readback: num_rendered is part of the return tuple
-        rendered = int(st["pinned"].item())
+        rendered = int(pinned.item())
         if rendered <= capacity:
             break
         capacity = int(rendered * 1.25) + 4096      # speculation missed: rerun with room to spare
-    st["capacity"] = max(int(rendered * 1.25) + 4096, 4 * P + 4096)
+    if not _defer:
+        st["capacity"] = max(int(rendered * 1.25) + 4096, 4 * P + 4096)
     off = lib.r3dg_raster_img_n_contrib_offset(W, H)
     n_contrib = imgBuffer[off:off + 4 * H * W].view(torch.int32).view(H, W)   # view, like the reference
     return (rendered, n_contrib, out_color, out_opacity, out_depth, out_feature, out_normal,

@@ -85,11 +85,11 @@ int r3dg_raster_forward(const r3dg_raster_fwd_args* a, r3dg_stream_t stream_) {
     const uint32_t* vals_a = (const uint32_t*)(bin + bl.vals_a);
     const uint32_t* vals_b = (const uint32_t*)(bin + bl.vals_b);
     if ((rc = launch_tile_ranges(geom + gl.header, capacity, (const uint64_t*)(bin + bl.keys_a), (const uint64_t*)(bin + bl.keys_b),
-                                 img + il.ranges, tiles, num_sms(), stream)) != 0) return rc;
+                                 img + il.ranges, (uint32_t*)(img + il.tile_order), tiles, num_sms(), stream)) != 0) return rc;
     prof_mark(true, 5, stream);
     if ((rc = launch_composite_forward(*a, gl, il, vals_a, vals_b, stream, [](int i, cudaStream_t s) { prof_mark(true, i, s); })) != 0) return rc;
     prof_mark(true, 7, stream);
-    g_launches += 2 + (a->computer_pseudo_normal ? 1 : 0);
+    g_launches += 3 + (a->computer_pseudo_normal ? 1 : 0);
     if (g_prof.on) g_prof.fwd_calls++;
     if (a->num_rendered_host)
         R3DG_CUDA_TRY(cudaMemcpyAsync(a->num_rendered_host, geom + gl.header, sizeof(int), cudaMemcpyDeviceToHost, stream));

@@ -60,7 +60,7 @@ struct GeomLayout {
 };
 
 struct ImgLayout {
-    size_t final_T, n_contrib, ranges, total;
+    size_t final_T, n_contrib, ranges, tile_order, total;
     __host__ __device__ ImgLayout(int W, int H) {
         size_t HW = (size_t)W * H;
         size_t T = (size_t)((W + R3DG_TILE - 1) / R3DG_TILE) * ((H + R3DG_TILE - 1) / R3DG_TILE);
@@ -68,6 +68,7 @@ struct ImgLayout {
         final_T = off;   off = align_up(off + HW * 4, 256);
         n_contrib = off; off = align_up(off + HW * 4, 256);
         ranges = off;    off = align_up(off + T * 8, 256);
+        tile_order = off; off = align_up(off + T * 4, 256);      // tiles by descending list length
         total = off;
     }
 };
@@ -131,6 +132,17 @@ inline __host__ uint32_t higher_msb(uint32_t n) {
     }
     if (n >> msb) msb++;
     return msb;
+}
+
+// Relaxed GPU-scope accesses for the look-back descriptors (flag and value share one word, so no
+// further ordering is needed); `volatile` asm so that polling loops really re-load.
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // --- exact-association arithmetic (see tools/sass_trace.py / DESIGN.md "bit-exact binning") ----

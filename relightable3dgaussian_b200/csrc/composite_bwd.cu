@@ -24,6 +24,7 @@ struct CompositeBwdParams {
     const uint32_t* vals_a;      // the sorted Gaussian ids live in vals_a or vals_b depending on
     const uint32_t* vals_b;      // the (device-side) number of executed radix passes
     const GeomHeader* header;
+    const uint32_t* tile_order;  // CTA -> tile, heaviest tiles first
     const float* rec;
     const float* bg;
     const float* final_T;
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(32 * NW) composite_bwd_kernel(const CompositeB
     __shared__ int sId[NW][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int PARTS = 8 / NW;
-    const int tile = blockIdx.x / PARTS;
+    const int tile = (int)p.tile_order[blockIdx.x / PARTS];
     const int wb = (blockIdx.x % PARTS) * NW + warp;
     const int tx = tile % p.gx, ty = tile / p.gx;
     const int bx0 = tx * R3DG_TILE + (wb & 1) * 8, by0 = ty * R3DG_TILE + (wb >> 1) * 4;
@@ -223,6 +224,7 @@ int launch_composite_backward(const r3dg_raster_bwd_args& a, const GeomLayout& g
     const int gy = (a.H + R3DG_TILE - 1) / R3DG_TILE;
     p.ranges = (const uint2*)(img + il.ranges);
     p.vals_a = vals_a; p.vals_b = vals_b; p.header = (const GeomHeader*)(geom + gl.header);
+    p.tile_order = (const uint32_t*)(img + il.tile_order);
     p.rec = (const float*)(geom + gl.rec);
     p.bg = a.background;
     p.final_T = (const float*)(img + il.final_T);

@@ -10,8 +10,8 @@ typedef void (*stage_mark_fn)(int, cudaStream_t);
 int launch_projection(const r3dg_raster_fwd_args& a, const GeomLayout& gl, const BinLayout& bl,
                       cudaStream_t stream, stage_mark_fn mark);
 int launch_tile_ranges(const void* geom_header, long long capacity, const uint64_t* keys_a,
-                       const uint64_t* keys_b, void* ranges, int num_tiles, int num_sms,
-                       cudaStream_t stream);
+                       const uint64_t* keys_b, void* ranges, uint32_t* tile_order, int num_tiles,
+                       int num_sms, cudaStream_t stream);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,
                         cudaStream_t stream);
 int launch_sort(void* geom_header, char* bin, const BinLayout& bl, int passes, int num_sms,

@@ -276,8 +276,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(int P, const uint32_
     const uint32_t b = s_block;
     const int base = b * R3DG_SCAN_ITEMS + threadIdx.x * SCAN_PER_THREAD;
     uint32_t v[SCAN_PER_THREAD], sum = 0;
+    if (base + SCAN_PER_THREAD <= P) {           // 2 x 16 B vector loads (base is a multiple of 8 elements)
+        const uint4* in4 = reinterpret_cast<const uint4*>(in + base);
 #pragma unroll
-    for (int i = 0; i < SCAN_PER_THREAD; ++i) { v[i] = base + i < P ? in[base + i] : 0u; sum += v[i]; }
+        for (int q = 0; q < SCAN_PER_THREAD / 4; ++q) { const uint4 t = in4[q]; v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_PER_THREAD; ++i) v[i] = base + i < P ? in[base + i] : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < SCAN_PER_THREAD; ++i) sum += v[i];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t inc = sum;
 #pragma unroll
@@ -290,23 +298,31 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(int P, const uint32_
         for (int d = 1; d < 8; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += t; }
         if (lane < SCAN_THREADS / 32) s_warp[lane] = wi - w;            // exclusive warp offsets
         const uint32_t total = __shfl_sync(0xffffffffu, wi, SCAN_THREADS / 32 - 1);
-        if (lane == 0) {
-            uint32_t prefix = 0;
-            if (b == 0) {
-                state[0] = total | 0x80000000u;
-            } else {
-                state[b] = total | 0x40000000u;
-                __threadfence();
-                int t = (int)b - 1;
-                while (true) {
-                    uint32_t s;
-                    do { s = state[t]; } while ((s >> 30) == 0u);
-                    prefix += s & 0x3fffffffu;
-                    if ((s >> 30) == 2u) break;
-                    --t;
-                }
-                state[b] = (prefix + total) | 0x80000000u;
+        // warp-parallel decoupled look-back: lane i inspects block b-1-i, 32 predecessors per round
+        uint32_t prefix = 0;
+        if (b == 0) {
+            if (lane == 0) st_relaxed_gpu(const_cast<uint32_t*>(state), total | 0x80000000u);
+        } else {
+            if (lane == 0) st_relaxed_gpu(const_cast<uint32_t*>(state) + b, total | 0x40000000u);
+            int t = (int)b - 1;
+            while (true) {
+                const uint32_t sv = (t - lane >= 0) ? ld_relaxed_gpu(const_cast<const uint32_t*>(state) + (t - lane)) : 0x80000000u;
+                const unsigned ready = __ballot_sync(0xffffffffu, (sv >> 30) != 0u);
+                const unsigned incl = __ballot_sync(0xffffffffu, (sv >> 30) == 2u);
+                // usable run: consecutive ready lanes from lane 0, cut at the first inclusive one
+                const int n_ready = __ffs(~ready) - 1 < 0 ? 32 : __ffs(~ready) - 1;
+                const int first_inc = incl ? __ffs(incl) - 1 : 32;
+                const int take = first_inc < n_ready ? first_inc + 1 : n_ready;
+                uint32_t v = lane < take ? (sv & 0x3fffffffu) : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                prefix += v;
+                if (first_inc < n_ready) break;
+                t -= take;
             }
+            if (lane == 0) st_relaxed_gpu(const_cast<uint32_t*>(state) + b, (prefix + total) | 0x80000000u);
+        }
+        if (lane == 0) {
             s_prefix = prefix;
             if ((int)b == (P + R3DG_SCAN_ITEMS - 1) / R3DG_SCAN_ITEMS - 1) header->num_rendered = prefix + total;
         }
@@ -314,35 +330,69 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(int P, const uint32_
     __syncthreads();
     uint32_t run = s_prefix + s_warp[warp] + (inc - sum);
 #pragma unroll
-    for (int i = 0; i < SCAN_PER_THREAD; ++i) { run += v[i]; if (base + i < P) out[base + i] = run; }
+    for (int i = 0; i < SCAN_PER_THREAD; ++i) { run += v[i]; v[i] = run; }
+    if (base + SCAN_PER_THREAD <= P) {
+        uint4* out4 = reinterpret_cast<uint4*>(out + base);
+#pragma unroll
+        for (int q = 0; q < SCAN_PER_THREAD / 4; ++q) out4[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_PER_THREAD; ++i) if (base + i < P) out[base + i] = v[i];
+    }
 }
 
 // ---- duplicateWithKeys (rasterizer_impl.cu:70-111): emission order = Gaussian index, then tile
-// row, then tile column — the stable sort preserves it for equal (tile, depth) keys. -------------
+// row, then tile column — the stable sort preserves it for equal (tile, depth) keys.
+// The reference lets one thread loop over its Gaussian's rectangle (long-tail divergence,
+// scattered 8 B stores).  Here a warp owns 32 consecutive Gaussians, whose output slots form ONE
+// contiguous range [offset of the first, offset after the last): lanes stride that range, find the
+// owning Gaussian of each slot by a 5-step search over the warp's prefix sums, and store fully
+// coalesced 256 B rows with every lane busy regardless of how the tile counts are distributed.
 __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int recf, int gx, int gy,
                                                         const float* __restrict__ rec,
                                                         const int* __restrict__ radii,
                                                         const uint32_t* __restrict__ offsets,
                                                         uint64_t* __restrict__ keys,
                                                         uint32_t* __restrict__ vals, long long capacity) {
+    __shared__ uint32_t sIncl[8][32], sDepth[8][32];
+    __shared__ int sX0[8][32], sY0[8][32], sW[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
-    const int radius = radii[idx];
-    if (radius <= 0) return;
-    uint32_t off = idx == 0 ? 0u : offsets[idx - 1];
-    const float4 a = *reinterpret_cast<const float4*>(rec + (size_t)idx * recf);
-    const float4 b = *reinterpret_cast<const float4*>(rec + (size_t)idx * recf + 4);
-    int x0, y0, x1, y1;
-    get_rect(a.x, a.y, radius, gx, gy, x0, y0, x1, y1);
-    const uint64_t dbits = (uint64_t)__float_as_uint(b.z);
-    for (int y = y0; y < y1; ++y)
-        for (int x = x0; x < x1; ++x) {
-            if ((long long)off < capacity) {
-                keys[off] = ((uint64_t)(uint32_t)(y * gx + x) << 32) | dbits;
-                vals[off] = (uint32_t)idx;
-            }
-            ++off;
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    uint32_t dbits = 0, cnt = 0;
+    if (idx < P) {
+        const int radius = radii[idx];
+        if (radius > 0) {
+            const float4 a = *reinterpret_cast<const float4*>(rec + (size_t)idx * recf);
+            const float4 b = *reinterpret_cast<const float4*>(rec + (size_t)idx * recf + 4);
+            get_rect(a.x, a.y, radius, gx, gy, x0, y0, x1, y1);
+            dbits = __float_as_uint(b.z);
+            cnt = (uint32_t)((x1 - x0) * (y1 - y0));
         }
+    }
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
+    const int first = blockIdx.x * blockDim.x + warp * 32;                     // first Gaussian of this warp
+    const uint32_t base = first == 0 ? 0u : offsets[first - 1];               // == global offset of the warp's slot 0
+    sIncl[warp][lane] = incl; sDepth[warp][lane] = dbits; sX0[warp][lane] = x0; sY0[warp][lane] = y0; sW[warp][lane] = x1 - x0;
+    __syncwarp();
+    for (uint32_t s = lane; s < total; s += 32) {
+        int lo = 0, hi = 31;                                                  // smallest g with incl[g] > s
+#pragma unroll
+        for (int it = 0; it < 5; ++it) { const int mid = (lo + hi) >> 1; if (sIncl[warp][mid] > s) hi = mid; else lo = mid + 1; }
+        const int g = lo;
+        const uint32_t excl = g == 0 ? 0u : sIncl[warp][g - 1];
+        const int t = (int)(s - excl), w = sW[warp][g];
+        const int ty = sY0[warp][g] + t / w, tx = sX0[warp][g] + t % w;
+        const long long off = (long long)base + s;
+        if (off < capacity) {
+            keys[off] = ((uint64_t)(uint32_t)(ty * gx + tx) << 32) | (uint64_t)sDepth[warp][g];
+            vals[off] = (uint32_t)(first + g);
+        }
+    }
 }
 
 // ---- identifyTileRanges (rasterizer_impl.cu:116-138) ----------------------------------------
@@ -362,6 +412,34 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(const GeomHeader* __re
             if (cur != prev) { ranges[prev].y = (uint32_t)i; ranges[cur].x = (uint32_t)i; }
         }
         if (i == R - 1) ranges[cur].y = (uint32_t)R;
+    }
+}
+
+// Longest-processing-time-first order of the tiles for the compositors: the CTAs of the heavy
+// tiles (longest sorted lists) are launched first so that the grid's tail consists of light tiles
+// (with row-major order the last heavy CTAs left 20% of the SM-cycles idle).  Coarse counting sort
+// by list length (64 buckets), one CTA.
+__global__ void __launch_bounds__(1024) tile_order_kernel(int T, const uint2* __restrict__ ranges, uint32_t* __restrict__ order) {
+    __shared__ uint32_t s_max, s_cnt[64], s_cur[64];
+    const int tid = threadIdx.x;
+    if (tid == 0) s_max = 0;
+    if (tid < 64) s_cnt[tid] = 0;
+    __syncthreads();
+    uint32_t m = 0;
+    for (int t = tid; t < T; t += 1024) { const uint2 r = ranges[t]; m = max(m, r.y - r.x); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0) atomicMax(&s_max, m);
+    __syncthreads();
+    const uint32_t mx = s_max;
+    const int shift = mx < 64 ? 0 : (32 - __clz(mx)) - 6;            // bucket = len >> shift in [0, 63]
+    for (int t = tid; t < T; t += 1024) { const uint2 r = ranges[t]; atomicAdd(&s_cnt[min(63u, (r.y - r.x) >> shift)], 1u); }
+    __syncthreads();
+    if (tid == 0) { uint32_t acc = 0; for (int b = 63; b >= 0; --b) { s_cur[b] = acc; acc += s_cnt[b]; } }   // descending
+    __syncthreads();
+    for (int t = tid; t < T; t += 1024) {
+        const uint2 r = ranges[t];
+        order[atomicAdd(&s_cur[min(63u, (r.y - r.x) >> shift)], 1u)] = (uint32_t)t;
     }
 }
 
@@ -409,9 +487,11 @@ int launch_projection(const r3dg_raster_fwd_args& a, const GeomLayout& gl, const
 }
 
 int launch_tile_ranges(const void* geom_header, long long capacity, const uint64_t* keys_a,
-                       const uint64_t* keys_b, void* ranges, int num_tiles, int num_sms, cudaStream_t stream) {
+                       const uint64_t* keys_b, void* ranges, uint32_t* tile_order, int num_tiles, int num_sms,
+                       cudaStream_t stream) {
     R3DG_CUDA_TRY(cudaMemsetAsync(ranges, 0, (size_t)num_tiles * 8, stream));
     tile_ranges_kernel<<<num_sms * 8, 256, 0, stream>>>((const GeomHeader*)geom_header, capacity, keys_a, keys_b, (uint2*)ranges);
+    tile_order_kernel<<<1, 1024, 0, stream>>>(num_tiles, (const uint2*)ranges, tile_order);
     R3DG_CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -136,21 +136,41 @@ __global__ void __launch_bounds__(R3DG_SORT_THREADS) sort_onesweep_kernel(
             // padding keys (~0) inflate digit 255 of the last tile: remove them from the count
             uint32_t cnt = acc;
             if (d == 255) cnt -= (uint32_t)(R3DG_SORT_TILE - count);
-            volatile uint32_t* lb = lookback + (size_t)tile * 256;
+            uint32_t* lb = const_cast<uint32_t*>(lookback) + (size_t)tile * 256;
             uint32_t prefix = 0;
             if (tile == 0) {
-                lb[d] = cnt | FLAG_INC;
+                st_relaxed_gpu(lb + d, cnt | FLAG_INC);
             } else {
-                lb[d] = cnt | FLAG_AGG;
+                st_relaxed_gpu(lb + d, cnt | FLAG_AGG);
+                // Decoupled look-back.  The nearest predecessor is usually still ranking: spin on it
+                // with single loads; everything further back was published long ago, so those
+                // descriptors are fetched LB_BATCH at a time instead of as a chain of dependent
+                // L2 round trips.
+                constexpr int LB_BATCH = 8;
+                const uint32_t* col = const_cast<const uint32_t*>(lookback) + d;
                 long long t = tile - 1;
-                while (true) {
-                    uint32_t s;
-                    do { s = lookback[(size_t)t * 256 + d]; } while ((s & (FLAG_AGG | FLAG_INC)) == 0u);
-                    prefix += s & VAL_MASK;
-                    if (s & FLAG_INC) break;
+                bool done = false;
+                while (!done) {
+                    uint32_t s0;
+                    do { s0 = ld_relaxed_gpu(col + (size_t)t * 256); } while ((s0 & (FLAG_AGG | FLAG_INC)) == 0u);
+                    prefix += s0 & VAL_MASK;
+                    if (s0 & FLAG_INC) break;
                     --t;
+                    uint32_t sv[LB_BATCH];
+#pragma unroll
+                    for (int i = 0; i < LB_BATCH; ++i) sv[i] = (t - i >= 0) ? ld_relaxed_gpu(col + (size_t)(t - i) * 256) : FLAG_INC;
+                    int used = 0;
+#pragma unroll
+                    for (int i = 0; i < LB_BATCH; ++i) {
+                        if (!done && used == i && (sv[i] & (FLAG_AGG | FLAG_INC)) != 0u) {
+                            prefix += sv[i] & VAL_MASK;
+                            ++used;
+                            if (sv[i] & FLAG_INC) done = true;
+                        }
+                    }
+                    t -= used;
                 }
-                lb[d] = (prefix + cnt) | FLAG_INC;
+                st_relaxed_gpu(lb + d, (prefix + cnt) | FLAG_INC);
             }
             sm.global_off[d] = digit_base[pass * 256 + d] + prefix;
             // block-wide exclusive scan of acc over the 256 digits -> local_off

@@ -32,6 +32,21 @@ class GaussianRasterizationSettings(NamedTuple):
     debug: bool
 
 
+_DEFER_COUNT = False
+
+
+def set_deferred_count(enabled: bool):
+    """Opt-in host run-ahead (not part of the reference surface).  The reference forward blocks on
+    a D2H copy of `num_rendered` (rasterizer_impl.cu:291); by default so do we, once, after the
+    whole forward is enqueued.  With deferral on, `num_rendered` is returned as a
+    `_C_raster.DeferredCount` (int()-able) that is resolved in backward, after the backward kernels
+    have been enqueued, so the loss and the backward follow the forward on the GPU without a host
+    round trip in between.  The binning buffer is then sized 1.5x the last count; an overflow
+    raises at resolve time instead of being retried transparently."""
+    global _DEFER_COUNT
+    _DEFER_COUNT = bool(enabled)
+
+
 def _snapshot(args):
     return tuple(a.cpu().clone() if isinstance(a, torch.Tensor) else a for a in args)
 
@@ -58,7 +73,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
                 raise
         else:
-            out = _C.rasterize_gaussians(*args)
+            out = _C.rasterize_gaussians(*args, _defer=_DEFER_COUNT)
         (num_rendered, num_contrib, color, opacity, depth, feature, normal, surface_xyz, weights,
          radii, geomBuffer, binningBuffer, imgBuffer) = out
         ctx.raster_settings = rs
@@ -89,6 +104,8 @@ class _RasterizeGaussians(torch.autograd.Function):
                 raise
         else:
             grads = _C.rasterize_gaussians_backward(*args)
+        if isinstance(ctx.num_rendered, _C.DeferredCount):
+            ctx.num_rendered.resolve()          # after the backward kernels are in flight
         (g_means2D, g_colors_precomp, g_opacities, g_means3D, g_features, g_cov3Ds, g_sh, g_scales,
          g_rotations) = grads
         return (g_means3D, g_means2D, g_features, g_sh, g_colors_precomp, g_opacities, g_scales,

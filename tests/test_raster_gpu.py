@@ -305,3 +305,36 @@ def test_dropin_module_names():
     for n in ("rasterize_gaussians", "rasterize_gaussians_backward", "mark_visible"):
         assert callable(getattr(mod._C, n))
     assert hasattr(mod, "GaussianRasterizer") and hasattr(mod, "GaussianRasterizationSettings")
+
+
+def test_deferred_count_option(C):
+    """Opt-in host run-ahead: same results, `num_rendered` resolves lazily, overflow is reported."""
+    from relightable3dgaussian_b200 import rasterizer, _C_raster
+    from relightable3dgaussian_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+    sc, cam = case_inputs(4000, 160, 96, 5, view=2, scale_boost=3.0)
+    rs = GaussianRasterizationSettings(96, 160, cam.tanfovx, cam.tanfovy, cam.cx, cam.cy, torch.zeros(3).cuda(), 1.0,
+                                       cam.viewmatrix.cuda(), cam.projmatrix.cuda(), 3, cam.campos.cuda(), False, True, True, False)
+    def run():
+        leaf = lambda t: t.cuda().requires_grad_(True)
+        m3, op, sh, s, r, ft = map(leaf, (sc.means3D, sc.opacities, sc.shs, sc.scales, sc.rotations, sc.features))
+        out = GaussianRasterizer(rs)(means3D=m3, means2D=torch.zeros_like(m3, requires_grad=True), opacities=op, shs=sh,
+                                     scales=s, rotations=r, features=ft)
+        (out[2].sum() + out[5].sum()).backward()
+        return out, sh.grad
+    ref_out, ref_g = run()
+    rasterizer.set_deferred_count(True)
+    try:
+        out, g = run()
+        assert isinstance(out[0], _C_raster.DeferredCount) and int(out[0]) == ref_out[0]
+        assert torch.equal(out[2], ref_out[2]) and torch.equal(out[1], ref_out[1])
+        assert rel_l2(npy(g), npy(ref_g)) < 1e-5
+        for st in _C_raster._state.values():
+            st["capacity"] = 0                                  # force a too-small speculative buffer
+        sc2, _ = case_inputs(300, 160, 96, 5, view=2, scale_boost=40.0)
+        leaf = lambda t: t.cuda()
+        out = GaussianRasterizer(rs)(means3D=leaf(sc2.means3D), means2D=torch.zeros(300, 3).cuda(), opacities=leaf(sc2.opacities),
+                                     shs=leaf(sc2.shs), scales=leaf(sc2.scales), rotations=leaf(sc2.rotations), features=leaf(sc2.features))
+        with pytest.raises(RuntimeError):
+            int(out[0])
+    finally:
+        rasterizer.set_deferred_count(False)
