@@ -1,0 +1,94 @@
+#!/usr/bin/env python3
+"""Stage-3 measurements on one B200 (development / evidence, not the headline bench):
+  * BVH build + visibility bake (update_visibility) vs the unmodified reference kernels
+    (oracle/_ref/libref_bvh.so driven like bvh/__init__.py + scene/gaussian_model.py:312-342);
+  * fused rendering_equation fwd+bwd vs the reference's PyTorch formulation (oracle_shading on GPU).
+Prints one JSON line per measurement."""
+import json
+import os
+import sys
+import time
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from helpers import inverse_covariance, shading_case  # noqa: E402
+from relightable3dgaussian_b200 import raytracer, shading, synth  # noqa: E402
+from oracle import oracle_shading as osh, ref_gpu  # noqa: E402
+
+
+def timeit(fn, n=3, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def bvh(P, N):
+    sc = synth.make_scene(P, "shell-v1", 0, 0)
+    d = lambda t: t.cuda()
+    xyz, s, r, op, nrm = d(sc.means3D), d(sc.scales), d(sc.rotations), d(sc.opacities[:, 0].contiguous()), d(sc.normals)
+    icov = inverse_covariance(s, r)
+    t_build = timeit(lambda: raytracer.RayTracer(xyz, s, r))
+    t_bake = timeit(lambda: raytracer.update_visibility(xyz, s, r, icov, op, nrm, N), n=2)
+    out = dict(what="bvh", P=P, N=N, rays=P * N, ours_build_ms=t_build, ours_bake_ms=t_bake,
+               ours_Mrays_per_s=P * N / t_bake / 1e3)
+    if ref_gpu.bvh_available():
+        t_rbuild = timeit(lambda: ref_gpu.ref_bvh_create(xyz, s, r))
+        nodes, aabbs, _ = ref_gpu.ref_bvh_create(xyz, s, r)
+
+        def ref_bake():
+            chunk = max(1, P // ((N - 1) // 24 + 1))
+            for off in range(0, P, chunk):
+                dirs, _ = raytracer.sample_incident_rays(nrm[off:off + chunk], False, N)
+                ro = xyz[off:off + chunk, None].expand_as(dirs) + dirs * 0.05          # bvh/__init__.py:63
+                ref_gpu.ref_bvh_trace_opacity(nodes, aabbs, ro.contiguous(), dirs, xyz, icov, op, nrm)
+        t_rbake = timeit(ref_bake, n=2)
+        vis_o, _, _ = raytracer.update_visibility(xyz, s, r, icov, op, nrm, N)
+        out.update(ref_build_ms=t_rbuild, ref_bake_ms=t_rbake, bake_speedup=t_rbake / t_bake, build_speedup=t_rbuild / t_build,
+                   blocked_fraction=float((vis_o == 0).float().mean()))
+    print(json.dumps(out), flush=True)
+
+
+class Light:
+    def __init__(self, env_raw):
+        self.env = env_raw
+
+    @property
+    def get_env(self):
+        return F.softplus(self.env)
+
+
+def shade(P, N):
+    c = {k: v.cuda() for k, v in shading_case(P, N, 16, seed=2).items()}
+
+    def run(ours):
+        leaves = {k: c[k].clone().requires_grad_(True) for k in ("base_color", "roughness", "viewdirs", "incidents")}
+        env_raw = c["env_raw"].clone().requires_grad_(True)
+        if ours:
+            pbr, ex = shading.rendering_equation(leaves["base_color"], leaves["roughness"], c["normals"], leaves["viewdirs"],
+                                                 leaves["incidents"], Light(env_raw), c["visibility"], c["incident_dirs"], c["incident_areas"])
+        else:
+            pbr, ex = osh.rendering_equation(leaves["base_color"], leaves["roughness"], c["normals"], leaves["viewdirs"],
+                                             leaves["incidents"], F.softplus(env_raw)[0], c["visibility"], c["incident_dirs"], c["incident_areas"])
+        ((pbr * c["cot_pbr"]).sum() + (ex["diffuse_light"] * c["cot_diffuse"]).sum()).backward()
+    t_o = timeit(lambda: run(True), n=5)
+    torch.cuda.reset_peak_memory_stats(); run(True); mem_o = torch.cuda.max_memory_allocated()
+    t_r = timeit(lambda: run(False), n=3)
+    torch.cuda.reset_peak_memory_stats(); run(False); mem_r = torch.cuda.max_memory_allocated()
+    print(json.dumps(dict(what="shading fwd+bwd", P=P, N=N, ours_ms=t_o, pytorch_ms=t_r, speedup=t_r / t_o,
+                          ours_peak_GB=mem_o / 1e9, pytorch_peak_GB=mem_r / 1e9,
+                          ours_GBps_of_baked_tensors=2 * P * N * 20 / t_o / 1e6)), flush=True)
+
+
+if __name__ == "__main__":
+    bvh(300_000, 64)
+    shade(300_000, 64)
+    shade(1_000_000, 32)
