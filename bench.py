@@ -37,7 +37,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 HEADLINE = dict(P=1_000_000, W=800, H=800, S=5, views=8, recipe="shell-v1", seed=0)
-STAGES = ["project", "scan", "emit_keys", "radix_sort", "tile_ranges", "composite_fwd",
+STAGES = ["project", "depth_sort", "bin_count", "bin_offsets", "bin_scatter", "composite_fwd",
           "surface_normal", "composite_bwd", "project_bwd"]
 
 
@@ -93,8 +93,11 @@ def alg_bytes(P, Pv, R, HW, T, S):
     """Algorithmic bytes per stage and view (R, Pv measured in this run)."""
     return {
         "project": 236 * P + 48 * Pv,
-        "scan": 8 * P, "emit_keys": 12 * R,
-        "radix_sort": 24 * R, "tile_ranges": 8 * R + 8 * T,
+        # depth-ordered binning (DESIGN.md): 3 x (read + write) of P (key, id) pairs + histogram read;
+        # two walks over (id, rect) of the sorted Gaussians; the chunk x tile matrix (~P/512 rows)
+        "depth_sort": 52 * P, "bin_count": 12 * P + 4 * T * (P // 512 + 1),
+        "bin_offsets": 16 * T * (P // 512 + 1) + 12 * T,
+        "bin_scatter": 12 * P + 4 * T * (P // 512 + 1) + 4 * R + 12 * T,
         "composite_fwd": R * (4 + 40 + 4 * S) + HW * 4 * (3 + 1 + 1 + S) + 8 * HW + 4 * P,
         "surface_normal": 44 * HW,
         "composite_bwd": R * (44 + 4 * S) + HW * 4 * (5 + S) + 8 * HW + Pv * 4 * (11 + S),

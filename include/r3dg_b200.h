@@ -229,7 +229,7 @@ int r3dg_knn_dist2(int P, const float* points /* [P,3] */, float* mean_dist2 /* 
 /* Measurement hooks used by bench.py (never needed by the reference's callers).
  * r3dg_launch_count: number of this library's kernels launched so far in the process.
  * r3dg_prof_begin/end: while active, every forward/backward records CUDA events on the launching
- * stream between its stages (0 project, 1 scan, 2 emit keys, 3 radix sort, 4 tile ranges,
+ * stream between its stages (0 project, 1 depth sort, 2 bin count, 3 bin offsets, 4 bin scatter,
  * 5 composite fwd, 6 surface/normal, 7 composite bwd, 8 projection bwd); r3dg_prof_end sums the
  * per-stage milliseconds over the recorded calls (caller synchronises first). */
 unsigned long long r3dg_launch_count(void);

@@ -23,7 +23,7 @@ int num_sms() {
     return g_num_sms;
 }
 // ---- optional stage profiler: CUDA events recorded on the launching stream between stages ----
-enum { ST_PROJECT = 0, ST_SCAN, ST_EMIT, ST_SORT, ST_RANGES, ST_COMPOSITE, ST_NORMAL, ST_COMPOSITE_BWD,
+enum { ST_PROJECT = 0, ST_DEPTH_SORT, ST_BIN_COUNT, ST_BIN_OFFSETS, ST_BIN_SCATTER, ST_COMPOSITE, ST_NORMAL, ST_COMPOSITE_BWD,
        ST_PROJECT_BWD, ST_COUNT };
 struct Prof {
     bool on = false;
@@ -37,11 +37,6 @@ inline void prof_mark(bool fwd, int i, cudaStream_t s) {
     const int call = fwd ? g_prof.fwd_calls : g_prof.bwd_calls;
     if (call >= g_prof.max_calls) return;
     cudaEventRecord(g_prof.at(call, i), s);
-}
-int sort_passes(int W, int H) {
-    const int tiles = ((W + R3DG_TILE - 1) / R3DG_TILE) * ((H + R3DG_TILE - 1) / R3DG_TILE);
-    const int bits = 32 + (int)higher_msb((uint32_t)tiles);     // rasterizer_impl.cu:310,318
-    return (bits + 7) / 8;
 }
 }  // namespace
 
@@ -73,23 +68,22 @@ int r3dg_raster_forward(const r3dg_raster_fwd_args* a, r3dg_stream_t stream_) {
     const int tiles = ((a->W + R3DG_TILE - 1) / R3DG_TILE) * ((a->H + R3DG_TILE - 1) / R3DG_TILE);
     R3DG_CUDA_TRY(cudaMemsetAsync(geom + gl.header, 0, sizeof(GeomHeader), stream));
     int rc = 0;
-    const int passes = sort_passes(a->W, a->H);
+    auto mark = [](int i, cudaStream_t s) { prof_mark(true, i, s); };
     prof_mark(true, 0, stream);
     if (a->P > 0) {
-        if ((rc = launch_projection(*a, gl, bl, stream, [](int i, cudaStream_t s) { prof_mark(true, i, s); })) != 0) return rc;
-        prof_mark(true, 3, stream);
-        if ((rc = launch_sort(geom + gl.header, bin, bl, passes, num_sms(), stream)) != 0) return rc;
-        g_launches += 3 + 2 + passes;
+        if ((rc = launch_projection(*a, gl, stream)) != 0) return rc;
+        prof_mark(true, 1, stream);
+        if ((rc = launch_binning(a->P, a->W, a->H, geom, gl, img, il, bin, bl, num_sms(), stream, mark)) != 0) return rc;
+        g_launches += 1 + (2 + R3DG_SORT_MAX_PASSES) + 4;
+    } else {
+        R3DG_CUDA_TRY(cudaMemsetAsync(img + il.ranges, 0, (size_t)tiles * 8, stream));
+        for (int i = 1; i <= 4; ++i) prof_mark(true, i, stream);
     }
-    prof_mark(true, 4, stream);
-    const uint32_t* vals_a = (const uint32_t*)(bin + bl.vals_a);
-    const uint32_t* vals_b = (const uint32_t*)(bin + bl.vals_b);
-    if ((rc = launch_tile_ranges(geom + gl.header, capacity, (const uint64_t*)(bin + bl.keys_a), (const uint64_t*)(bin + bl.keys_b),
-                                 img + il.ranges, (uint32_t*)(img + il.tile_order), tiles, num_sms(), stream)) != 0) return rc;
+    if ((rc = launch_tile_order(img + il.ranges, (uint32_t*)(img + il.tile_order), tiles, stream)) != 0) return rc;
     prof_mark(true, 5, stream);
-    if ((rc = launch_composite_forward(*a, gl, il, vals_a, vals_b, stream, [](int i, cudaStream_t s) { prof_mark(true, i, s); })) != 0) return rc;
+    if ((rc = launch_composite_forward(*a, gl, il, (const uint32_t*)(bin + bl.point_list), stream, mark)) != 0) return rc;
     prof_mark(true, 7, stream);
-    g_launches += 3 + (a->computer_pseudo_normal ? 1 : 0);
+    g_launches += 2 + (a->computer_pseudo_normal ? 1 : 0);
     if (g_prof.on) g_prof.fwd_calls++;
     if (a->num_rendered_host)
         R3DG_CUDA_TRY(cudaMemcpyAsync(a->num_rendered_host, geom + gl.header, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -114,7 +108,7 @@ int r3dg_raster_backward(const r3dg_raster_bwd_args* a, r3dg_stream_t stream_) {
     char* bin = (char*)a->binning;
     int rc = 0;
     prof_mark(false, 8, stream);
-    if ((rc = launch_composite_backward(*a, gl, il, (const uint32_t*)(bin + bl.vals_a), (const uint32_t*)(bin + bl.vals_b), stream)) != 0) return rc;
+    if ((rc = launch_composite_backward(*a, gl, il, (const uint32_t*)(bin + bl.point_list), stream)) != 0) return rc;
     prof_mark(false, 9, stream);
     if ((rc = launch_projection_backward(*a, gl, stream)) != 0) return rc;
     prof_mark(false, 10, stream);
@@ -254,7 +248,17 @@ long long r3dg_raster_debug_copy(int id, int P, int S, int W, int H, const void*
         case 5: if (max_bytes < 16LL * P) return -1; if (P) unpack_rec_kernel<<<nb, 256, 0, stream>>>(P, gl.recf, 5, rec, tt, (float*)dst); return 16LL * P;
         case 6: if (max_bytes < 12LL * P) return -1; if (P) unpack_rec_kernel<<<nb, 256, 0, stream>>>(P, gl.recf, 6, rec, tt, (float*)dst); return 12LL * P;
         case 7: return copy(geom + gl.tiles_touched, 4 * (size_t)P);
-        case 8: return copy(geom + gl.point_offsets, 4 * (size_t)P);
+        case 8: {   // reference geomState.point_offsets: rebuilt on demand (not needed by the hot path)
+            if (max_bytes < 4LL * P) return -1;
+            if (P == 0) return 0;
+            char* tmp = nullptr;
+            const size_t state_bytes = ((size_t)P / R3DG_SCAN_ITEMS + 2) * 4;
+            if (cudaMalloc(&tmp, 256 + state_bytes) != cudaSuccess) return -2;
+            int rc = launch_point_offsets(P, tt, (uint32_t*)dst, (uint32_t*)(tmp + 256), (GeomHeader*)tmp, stream);
+            cudaStreamSynchronize(stream);
+            cudaFree(tmp);
+            return rc == 0 ? 4LL * P : -2;
+        }
         case 13: return copy(img + il.final_T, 4 * HW);
         case 14: return copy(img + il.n_contrib, 4 * HW);
         case 15: return copy(img + il.ranges, 8 * (size_t)tiles);
@@ -262,13 +266,13 @@ long long r3dg_raster_debug_copy(int id, int P, int S, int W, int H, const void*
             const long long capacity = bin_capacity_for_bytes(binning_bytes);
             if (capacity < 1) return -1;
             const BinLayout bl(capacity);
-            GeomHeader h;     // debug path: one blocking read of the header to learn the result buffer
-            if (cudaStreamSynchronize(stream) != cudaSuccess ||
-                cudaMemcpy(&h, geom + gl.header, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
-            const bool in_b = (h.sort_exec & 1u) != 0;
             // caller limits the copy to R entries through max_bytes
-            if (id == 9) return copy(bin + (in_b ? bl.vals_b : bl.vals_a), (size_t)max_bytes);
-            return copy(bin + (in_b ? bl.keys_b : bl.keys_a), (size_t)max_bytes);
+            if (id == 9) return copy(bin + bl.point_list, std::min((size_t)max_bytes, (size_t)capacity * 4));
+            // reference binningState.point_list_keys (sorted): rebuilt from the lists
+            const long long limit = std::min(max_bytes / 8, capacity);
+            if (launch_rebuild_keys(tiles, img + il.ranges, (const uint32_t*)(bin + bl.point_list), rec, gl.recf, limit,
+                                    (uint64_t*)dst, stream) != 0) return -2;
+            return limit * 8;
         }
     }
     return -1;

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) bvh_leaf_aabb_kernel(int P, const float* 
 // ---- build -----------------------------------------------------------------------------------
 struct BvhTmp {                 // layout of the caller-provided build workspace
     size_t header, bounds, leafcopy, flags, bin, total;
-    BinLayout bl;
+    SortLayout bl;
     __host__ BvhTmp(int P) : bl(P < 1 ? 1 : P) {
         size_t off = 0;
         header = off;   off = align_up(off + sizeof(GeomHeader), 256);
@@ -84,7 +84,7 @@ __device__ __forceinline__ float ord2f(int o) { return __int_as_float(o >= 0 ? o
 
 __global__ void bvh_init_kernel(GeomHeader* h, int* bounds, int P) {
     if (threadIdx.x == 0) {
-        h->num_rendered = (uint32_t)P; h->depth_or = 0xffffffffu; h->depth_nor = 0xffffffffu;   // sort every digit
+        h->num_rendered = (uint32_t)P; h->depth_or = 0x3fffffffu; h->depth_nor = 0x3fffffffu;   // sort all 30 Morton bits
         for (int k = 0; k < 3; ++k) { bounds[k] = f2ord(100000.f); bounds[3 + k] = f2ord(-100000.f); }   // construct.cu:159-162
     }
 }
@@ -120,7 +120,7 @@ __device__ __forceinline__ uint32_t expand_bits(uint32_t v) {
 
 // construct.cu:23-51: 30-bit Morton code of the leaf-box centroid normalised to the scene box
 __global__ void __launch_bounds__(256) bvh_morton_kernel(int P, const float* __restrict__ leaf, const int* __restrict__ bounds,
-                                                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                                                         uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     uint32_t code[3];
@@ -133,19 +133,19 @@ __global__ void __launch_bounds__(256) bvh_morton_kernel(int P, const float* __r
         c = fminf(fmaxf(mul_(c, 1024.0f), 0.0f), 1023.0f);
         code[k] = expand_bits((uint32_t)c);
     }
-    keys[i] = (uint64_t)(code[0] * 4 + code[1] * 2 + code[2]);
+    keys[i] = code[0] * 4 + code[1] * 2 + code[2];
     vals[i] = (uint32_t)i;
 }
 
 __global__ void __launch_bounds__(256) bvh_leaves_kernel(int P, const GeomHeader* __restrict__ h,
-                                                         const uint64_t* __restrict__ ka, const uint64_t* __restrict__ kb,
+                                                         const uint32_t* __restrict__ ka, const uint32_t* __restrict__ kb,
                                                          const uint32_t* __restrict__ va, const uint32_t* __restrict__ vb,
                                                          const float* __restrict__ leafcopy, int32_t* __restrict__ nodes,
                                                          float* __restrict__ aabbs, uint64_t* __restrict__ morton) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     const bool in_b = (h->sort_exec & 1u) != 0;
-    const uint64_t m = in_b ? kb[i] : ka[i];
+    const uint64_t m = in_b ? kb[i] : ka[i];   // 30-bit code, widened
     const uint32_t idx = in_b ? vb[i] : va[i];
     morton[i] = (m << 31) | idx;                                    // construct.cu:184-192 (31, not 32)
     nodes[(size_t)(P - 1 + i) * 5 + 3] = (int32_t)idx;               // construct.cu:196-201
@@ -407,10 +407,10 @@ int launch_bvh_build(int P, int32_t* nodes, float* aabbs, uint64_t* morton, void
     R3DG_CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)P * 4, stream));
     bvh_init_kernel<<<1, 32, 0, stream>>>(h, bounds, P);
     bvh_bounds_kernel<<<num_sms * 4, 256, 0, stream>>>(P, leaf, bounds, leafcopy);
-    bvh_morton_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, leafcopy, bounds, (uint64_t*)(bin + t.bl.keys_a), (uint32_t*)(bin + t.bl.vals_a));
-    int rc = launch_sort(h, bin, t.bl, 4, num_sms, stream);          // 30-bit keys: 4 byte digits
+    bvh_morton_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, leafcopy, bounds, (uint32_t*)(bin + t.bl.keys_a), (uint32_t*)(bin + t.bl.vals_a));
+    int rc = launch_sort(h, bin, t.bl, P, num_sms, stream);          // 30-bit keys: 4 passes of 8 bits
     if (rc != 0) return rc;
-    bvh_leaves_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, h, (const uint64_t*)(bin + t.bl.keys_a), (const uint64_t*)(bin + t.bl.keys_b),
+    bvh_leaves_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, h, (const uint32_t*)(bin + t.bl.keys_a), (const uint32_t*)(bin + t.bl.keys_b),
                                                            (const uint32_t*)(bin + t.bl.vals_a), (const uint32_t*)(bin + t.bl.vals_b),
                                                            leafcopy, nodes, aabbs, morton);
     if (P > 1) bvh_internal_kernel<<<(P - 1 + 255) / 256, 256, 0, stream>>>(P, morton, nodes);

@@ -29,9 +29,9 @@ __host__ __device__ inline int rec_floats(int S) { return 8 + 4 * num_groups(S);
 
 struct GeomHeader {               // first 256 bytes of the geometry buffer
     uint32_t num_rendered;        // R = total (tile, Gaussian) instances (may exceed capacity)
-    uint32_t scan_ticket;         // dynamic block id for the chained scan
+    uint32_t scan_ticket;         // dynamic block id for the chained scan (debug point_offsets only)
     uint32_t sort_ticket[8];      // dynamic tile id per radix pass
-    uint32_t depth_or;            // OR of visible depth bit patterns
+    uint32_t depth_or;            // OR of the sort keys (visible depth bit patterns)
     uint32_t depth_nor;           // OR of their complements: bit varies across keys iff set in both
     uint32_t sort_exec;           // number of radix passes actually executed (parity = result buffer)
     uint32_t pad[51];
@@ -42,8 +42,41 @@ inline __host__ __device__ size_t align_up(size_t x, size_t a) { return (x + a -
 
 #define R3DG_SCAN_ITEMS 2048       // items per chained-scan block
 
+// ---- radix sort of (u32 key, u32 value) pairs (radix_sort.cu) ---------------------------------
+#define R3DG_SORT_THREADS 256
+#define R3DG_SORT_ITEMS 8
+#define R3DG_SORT_TILE (R3DG_SORT_THREADS * R3DG_SORT_ITEMS)   // 2048 pairs per onesweep tile
+#define R3DG_SORT_MAX_PASSES 4
+
+struct SortLayout {
+    size_t keys_a, keys_b, vals_a, vals_b, hist, lookback, total;
+    long long n, tiles;
+    __host__ __device__ SortLayout(long long n_) : n(n_) {
+        tiles = (n_ + R3DG_SORT_TILE - 1) / R3DG_SORT_TILE + 1;
+        size_t off = 0;
+        keys_a = off; off = align_up(off + (size_t)n_ * 4, 256);
+        keys_b = off; off = align_up(off + (size_t)n_ * 4, 256);
+        vals_a = off; off = align_up(off + (size_t)n_ * 4, 256);
+        vals_b = off; off = align_up(off + (size_t)n_ * 4, 256);
+        hist = off;   off = align_up(off + (size_t)R3DG_SORT_MAX_PASSES * 256 * 4, 256);
+        lookback = off;                                   // two descriptor planes, used alternately
+        off = align_up(off + (size_t)2 * tiles * 256 * 4, 256);
+        total = off;
+    }
+};
+
+// The key bits above the highest VARYING bit are identical in every key and need no pass; the
+// remaining nb bits are split evenly over ceil(nb/8) passes of w <= 8 bits.  All of it is decided
+// on the device from (key_or & key_nor); the k-th pass reads buffer (k & 1), so the result lives
+// in buffer (sort_exec & 1).
+__device__ __forceinline__ void sort_plan(uint32_t diff, int& passes, int& w) {
+    const int nb = 32 - __clz(diff);                      // __clz(0) == 32
+    passes = (nb + 7) >> 3;
+    w = passes ? (nb + passes - 1) / passes : 0;
+}
+
 struct GeomLayout {
-    size_t header, rec, tiles_touched, point_offsets, clamped, scan_state, grad, total;
+    size_t header, rec, tiles_touched, rects, clamped, scan_state, sort, grad, total;
     int P, S, recf;
     __host__ __device__ GeomLayout(int P_, int S_) : P(P_), S(S_) {
         recf = rec_floats(S_);
@@ -51,16 +84,33 @@ struct GeomLayout {
         header = off;        off = align_up(off + sizeof(GeomHeader), 256);
         rec = off;           off = align_up(off + (size_t)P_ * recf * 4, 256);
         tiles_touched = off; off = align_up(off + (size_t)P_ * 4, 256);
-        point_offsets = off; off = align_up(off + (size_t)P_ * 4, 256);
+        rects = off;         off = align_up(off + (size_t)P_ * 8, 256);         // packed tile rectangles
         clamped = off;       off = align_up(off + (size_t)P_, 256);
         scan_state = off;    off = align_up(off + ((size_t)P_ / R3DG_SCAN_ITEMS + 2) * 4, 256);
+        sort = off;          off = align_up(off + SortLayout(P_).total, 256);   // depth sort of the Gaussians
         grad = off;          off = align_up(off + (size_t)P_ * recf * 4, 256);   // backward scratch
         total = off;
     }
 };
 
+// ---- depth-ordered tile binning (binning.cu) -------------------------------------------------
+// The depth-sorted Gaussians are cut into `chunks` runs of CH; M[chunk][tile] first counts the
+// instances a chunk adds to a tile, then (scanned down the columns) is the chunk's first slot
+// inside the tile's list.
+#define R3DG_BIN_MAX_CHUNKS 2048
+__host__ __device__ inline int bin_max_chunks(size_t T) {
+    size_t c = ((size_t)1 << 26) / (T ? T : 1);
+    return (int)(c < 296 ? 296 : (c > R3DG_BIN_MAX_CHUNKS ? R3DG_BIN_MAX_CHUNKS : c));
+}
+__host__ __device__ inline int bin_chunk_len(int P, size_t T) {     // Gaussians per chunk, multiple of 32
+    const int mc = bin_max_chunks(T);
+    int ch = (P + mc - 1) / mc;
+    ch = (ch + 31) / 32 * 32;
+    return ch < 32 ? 32 : ch;
+}
+
 struct ImgLayout {
-    size_t final_T, n_contrib, ranges, tile_order, total;
+    size_t final_T, n_contrib, ranges, tile_order, tile_total, bin_matrix, total;
     __host__ __device__ ImgLayout(int W, int H) {
         size_t HW = (size_t)W * H;
         size_t T = (size_t)((W + R3DG_TILE - 1) / R3DG_TILE) * ((H + R3DG_TILE - 1) / R3DG_TILE);
@@ -69,59 +119,22 @@ struct ImgLayout {
         n_contrib = off; off = align_up(off + HW * 4, 256);
         ranges = off;    off = align_up(off + T * 8, 256);
         tile_order = off; off = align_up(off + T * 4, 256);      // tiles by descending list length
+        tile_total = off; off = align_up(off + T * 4, 256);
+        bin_matrix = off; off = align_up(off + (size_t)bin_max_chunks(T) * T * 4, 256);
         total = off;
     }
 };
 
-#define R3DG_SORT_THREADS 256
-#define R3DG_SORT_ITEMS 12
-#define R3DG_SORT_TILE (R3DG_SORT_THREADS * R3DG_SORT_ITEMS)   // 3072 keys per onesweep tile
-#define R3DG_SORT_MAX_PASSES 8
-
+// Binning buffer: the per-tile depth-sorted Gaussian lists (reference binningState.point_list).
 struct BinLayout {
-    size_t keys_a, keys_b, vals_a, vals_b, hist, lookback, total;
-    long long capacity, max_tiles;
+    size_t point_list, total;
+    long long capacity;
     __host__ __device__ BinLayout(long long cap) : capacity(cap) {
-        max_tiles = (cap + R3DG_SORT_TILE - 1) / R3DG_SORT_TILE + 1;
-        size_t off = 0;
-        keys_a = off; off = align_up(off + (size_t)cap * 8, 256);
-        keys_b = off; off = align_up(off + (size_t)cap * 8, 256);
-        vals_a = off; off = align_up(off + (size_t)cap * 4, 256);
-        vals_b = off; off = align_up(off + (size_t)cap * 4, 256);
-        hist = off;   off = align_up(off + (size_t)R3DG_SORT_MAX_PASSES * 256 * 4, 256);
-        lookback = off;
-        off = align_up(off + (size_t)R3DG_SORT_MAX_PASSES * max_tiles * 256 * 4, 256);
-        total = off;
+        point_list = 0;
+        total = align_up((size_t)cap * 4, 256);
     }
 };
-
-// capacity such that BinLayout(capacity).total <= bytes (monotone; solved by a short search)
-inline __host__ long long bin_capacity_for_bytes(size_t bytes) {
-    long long lo = 0, hi = (long long)(bytes / 24) + 1;
-    while (lo < hi) {
-        long long mid = (lo + hi + 1) / 2;
-        if (BinLayout(mid).total <= bytes) lo = mid; else hi = mid - 1;
-    }
-    return lo;
-}
-
-// Radix passes over the 64-bit key (tile << 32 | depth bits).  A depth digit whose bits are
-// identical in every key is a no-op for a stable sort and is skipped on the device; the k-th
-// EXECUTED pass reads buffer (k & 1) and writes buffer (~k & 1), so the result lives in buffer
-// (sort_exec & 1) where sort_exec is only known on the device.
-__device__ __forceinline__ int sort_digit_of_slot(uint32_t depth_diff, int passes, int slot) {
-    int k = 0;
-    for (int p = 0; p < passes; ++p) {
-        const bool needed = p >= 4 || ((depth_diff >> (8 * p)) & 0xffu) != 0u;
-        if (needed) { if (k == slot) return p; ++k; }
-    }
-    return -1;
-}
-__device__ __forceinline__ int sort_num_exec(uint32_t depth_diff, int passes) {
-    int k = 0;
-    for (int p = 0; p < passes; ++p) k += (p >= 4 || ((depth_diff >> (8 * p)) & 0xffu) != 0u) ? 1 : 0;
-    return k;
-}
+inline __host__ long long bin_capacity_for_bytes(size_t bytes) { return (long long)(bytes / 256 * 256 / 4); }
 
 // getHigherMsb (reference rasterizer_impl.cu:35-50): bits needed for tile ids.
 inline __host__ uint32_t higher_msb(uint32_t n) {

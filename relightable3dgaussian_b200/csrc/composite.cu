@@ -26,8 +26,7 @@ namespace r3dg {
 struct CompositeFwdParams {
     int W, H, gx, S, recf;
     const uint2* ranges;
-    const uint32_t* vals_a;      // the sorted Gaussian ids live in vals_a or vals_b depending on
-    const uint32_t* vals_b;      // the (device-side) number of executed radix passes
+    const uint32_t* point_list;  // per-tile depth-sorted Gaussian ids (binning.cu)
     const GeomHeader* header;
     const uint32_t* tile_order;  // CTA -> tile, heaviest tiles first
     const float* rec;
@@ -57,7 +56,7 @@ __global__ void __launch_bounds__(32 * NW) composite_fwd_kernel(const CompositeF
     const int toDo = (int)(range.y - range.x);
     const float4* __restrict__ rec4 = reinterpret_cast<const float4*>(p.rec);
     const int rec4n = p.recf >> 2;
-    const uint32_t* __restrict__ plist = ((p.header->sort_exec & 1u) ? p.vals_b : p.vals_a) + range.x;
+    const uint32_t* __restrict__ plist = p.point_list + range.x;
 
     float T = 1.0f, Dp = 0.0f, Op = 0.0f;
     float C[4 * NG];
@@ -206,14 +205,14 @@ int composite_nw() {
 }
 
 int launch_composite_forward(const r3dg_raster_fwd_args& a, const GeomLayout& gl, const ImgLayout& il,
-                             const uint32_t* vals_a, const uint32_t* vals_b, cudaStream_t stream, stage_mark_fn mark) {
+                             const uint32_t* point_list, cudaStream_t stream, stage_mark_fn mark) {
     char* geom = (char*)a.geom;
     char* img = (char*)a.img;
     CompositeFwdParams p;
     p.W = a.W; p.H = a.H; p.gx = (a.W + R3DG_TILE - 1) / R3DG_TILE; p.S = a.S; p.recf = gl.recf;
     const int gy = (a.H + R3DG_TILE - 1) / R3DG_TILE;
     p.ranges = (const uint2*)(img + il.ranges);
-    p.vals_a = vals_a; p.vals_b = vals_b; p.header = (const GeomHeader*)(geom + gl.header);
+    p.point_list = point_list; p.header = (const GeomHeader*)(geom + gl.header);
     p.tile_order = (const uint32_t*)(img + il.tile_order);
     p.rec = (const float*)(geom + gl.rec);
     p.bg = a.background;

@@ -21,8 +21,7 @@ namespace r3dg {
 struct CompositeBwdParams {
     int W, H, gx, S, recf, backward_geometry;
     const uint2* ranges;
-    const uint32_t* vals_a;      // the sorted Gaussian ids live in vals_a or vals_b depending on
-    const uint32_t* vals_b;      // the (device-side) number of executed radix passes
+    const uint32_t* point_list;  // per-tile depth-sorted Gaussian ids (binning.cu)
     const GeomHeader* header;
     const uint32_t* tile_order;  // CTA -> tile, heaviest tiles first
     const float* rec;
@@ -77,7 +76,7 @@ __global__ void __launch_bounds__(32 * NW) composite_bwd_kernel(const CompositeB
     const size_t HW = (size_t)p.H * p.W, pix = (size_t)p.W * py + px;
     const float4* __restrict__ rec4 = reinterpret_cast<const float4*>(p.rec);
     const int rec4n = p.recf >> 2;
-    const uint32_t* __restrict__ plist = ((p.header->sort_exec & 1u) ? p.vals_b : p.vals_a) + range.x;
+    const uint32_t* __restrict__ plist = p.point_list + range.x;
 
     const float T_final = inside ? p.final_T[pix] : 0.0f;
     float T = T_final;
@@ -215,7 +214,7 @@ static void launch_bwd_ng(const CompositeBwdParams& p, int tiles, cudaStream_t s
 }
 
 int launch_composite_backward(const r3dg_raster_bwd_args& a, const GeomLayout& gl, const ImgLayout& il,
-                              const uint32_t* vals_a, const uint32_t* vals_b, cudaStream_t stream) {
+                              const uint32_t* point_list, cudaStream_t stream) {
     char* geom = (char*)a.geom;
     char* img = (char*)a.img;
     CompositeBwdParams p;
@@ -223,7 +222,7 @@ int launch_composite_backward(const r3dg_raster_bwd_args& a, const GeomLayout& g
     p.backward_geometry = a.backward_geometry;
     const int gy = (a.H + R3DG_TILE - 1) / R3DG_TILE;
     p.ranges = (const uint2*)(img + il.ranges);
-    p.vals_a = vals_a; p.vals_b = vals_b; p.header = (const GeomHeader*)(geom + gl.header);
+    p.point_list = point_list; p.header = (const GeomHeader*)(geom + gl.header);
     p.tile_order = (const uint32_t*)(img + il.tile_order);
     p.rec = (const float*)(geom + gl.rec);
     p.bg = a.background;

@@ -7,20 +7,25 @@
 namespace r3dg {
 
 typedef void (*stage_mark_fn)(int, cudaStream_t);
-int launch_projection(const r3dg_raster_fwd_args& a, const GeomLayout& gl, const BinLayout& bl,
-                      cudaStream_t stream, stage_mark_fn mark);
-int launch_tile_ranges(const void* geom_header, long long capacity, const uint64_t* keys_a,
-                       const uint64_t* keys_b, void* ranges, uint32_t* tile_order, int num_tiles,
-                       int num_sms, cudaStream_t stream);
+int launch_projection(const r3dg_raster_fwd_args& a, const GeomLayout& gl, cudaStream_t stream);
+int launch_point_offsets(int P, const uint32_t* tiles_touched, uint32_t* out, uint32_t* state,
+                         GeomHeader* ticket_header, cudaStream_t stream);
+int launch_tile_order(const void* ranges, uint32_t* tile_order, int num_tiles, cudaStream_t stream);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,
                         cudaStream_t stream);
-int launch_sort(void* geom_header, char* bin, const BinLayout& bl, int passes, int num_sms,
+// radix_sort.cu: stable sort of n (u32 key, u32 value) pairs laid out by SortLayout in `buf`
+int launch_sort(void* geom_header, char* buf, const SortLayout& sl, long long n, int num_sms,
                 cudaStream_t stream);
+// binning.cu: depth sort + order-preserving tile binning -> point_list, ranges, num_rendered
+int launch_binning(int P, int W, int H, char* geom, const GeomLayout& gl, char* img, const ImgLayout& il,
+                   char* bin, const BinLayout& bl, int num_sms, cudaStream_t stream, stage_mark_fn mark);
+int launch_rebuild_keys(int T, const void* ranges, const uint32_t* point_list, const float* rec, int recf,
+                        long long limit, uint64_t* keys, cudaStream_t stream);
 int launch_composite_forward(const r3dg_raster_fwd_args& a, const GeomLayout& gl,
-                             const ImgLayout& il, const uint32_t* vals_a, const uint32_t* vals_b,
+                             const ImgLayout& il, const uint32_t* point_list,
                              cudaStream_t stream, stage_mark_fn mark);
 int launch_composite_backward(const r3dg_raster_bwd_args& a, const GeomLayout& gl,
-                              const ImgLayout& il, const uint32_t* vals_a, const uint32_t* vals_b,
+                              const ImgLayout& il, const uint32_t* point_list,
                               cudaStream_t stream);
 int launch_projection_backward(const r3dg_raster_bwd_args& a, const GeomLayout& gl,
                                cudaStream_t stream);

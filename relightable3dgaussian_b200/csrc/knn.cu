@@ -16,7 +16,7 @@ namespace r3dg {
 
 struct KnnTmp {
     size_t header, bounds, sorted_pts, boxes, bin, total;
-    BinLayout bl;
+    SortLayout bl;
     __host__ KnnTmp(int P) : bl(P < 1 ? 1 : P) {
         size_t off = 0;
         header = off;     off = align_up(off + sizeof(GeomHeader), 256);
@@ -33,7 +33,7 @@ __device__ __forceinline__ float ord2f_k(int o) { return __int_as_float(o >= 0 ?
 
 __global__ void knn_init_kernel(GeomHeader* h, int* bounds, int P) {
     if (threadIdx.x == 0) {
-        h->num_rendered = (uint32_t)P; h->depth_or = 0xffffffffu; h->depth_nor = 0xffffffffu;
+        h->num_rendered = (uint32_t)P; h->depth_or = 0x3fffffffu; h->depth_nor = 0x3fffffffu;   // sort all 30 Morton bits
         for (int k = 0; k < 3; ++k) { bounds[k] = f2ord_k(0.f); bounds[3 + k] = f2ord_k(0.f); }   // reduction init {0,0,0}, simple_knn.cu:191
     }
 }
@@ -60,7 +60,7 @@ __device__ __forceinline__ uint32_t spread10(uint32_t x) {      // prepMorton, s
 }
 
 __global__ void __launch_bounds__(256) knn_morton_kernel(int P, const float* __restrict__ pts, const int* __restrict__ bounds,
-                                                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                                                         uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     uint32_t c[3];
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) knn_morton_kernel(int P, const float* __r
         const float t = ((pts[3 * (size_t)i + k] - lo) / (hi - lo)) * 1023.0f;
         c[k] = spread10((uint32_t)fminf(fmaxf(t, 0.f), 1023.f));
     }
-    keys[i] = (uint64_t)(c[0] | (c[1] << 1) | (c[2] << 2));
+    keys[i] = c[0] | (c[1] << 1) | (c[2] << 2);
     vals[i] = (uint32_t)i;
 }
 
@@ -156,8 +156,8 @@ int launch_knn(int P, const float* points, float* out, void* tmp_, size_t tmp_by
     R3DG_CUDA_TRY(cudaMemsetAsync(h, 0, sizeof(GeomHeader), stream));
     knn_init_kernel<<<1, 32, 0, stream>>>(h, bounds, P);
     knn_bounds_kernel<<<num_sms * 4, 256, 0, stream>>>(P, points, bounds);
-    knn_morton_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, points, bounds, (uint64_t*)(bin + t.bl.keys_a), (uint32_t*)(bin + t.bl.vals_a));
-    int rc = launch_sort(h, bin, t.bl, 4, num_sms, stream);
+    knn_morton_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, points, bounds, (uint32_t*)(bin + t.bl.keys_a), (uint32_t*)(bin + t.bl.vals_a));
+    int rc = launch_sort(h, bin, t.bl, P, num_sms, stream);
     if (rc != 0) return rc;
     knn_gather_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, h, (const uint32_t*)(bin + t.bl.vals_a), (const uint32_t*)(bin + t.bl.vals_b), points, sorted);
     knn_boxes_kernel<<<(P + KNN_BOX - 1) / KNN_BOX, KNN_BOX, 0, stream>>>(P, sorted, boxes);

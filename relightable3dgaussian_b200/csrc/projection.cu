@@ -119,6 +119,8 @@ struct ProjParams {
     int* radii;
     float* out_weights;
     GeomHeader* header;
+    uint32_t *sort_keys, *sort_vals;      // depth-sort input (radix_sort.cu)
+    uint2* rects;                         // packed tile rectangles (binning.cu)
 };
 
 #define PROJ_THREADS 128
@@ -155,6 +157,7 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjParams 
         p.radii[idx] = 0;
         p.tiles_touched[idx] = 0;
         p.out_weights[idx] = 0.0f;
+        p.sort_vals[idx] = (uint32_t)idx;
         px = p.means3D[3 * (size_t)idx]; py = p.means3D[3 * (size_t)idx + 1]; pz = p.means3D[3 * (size_t)idx + 2];
         tz = xform_row_(sV, 2, px, py, pz);
         if (tz <= 0.2f) {                              // auxiliary.h:154 (x/y frustum test is disabled there)
@@ -242,6 +245,11 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjParams 
         const uint32_t o = __reduce_or_sync(0xffffffffu, alive ? bits : 0u);
         const uint32_t no = __reduce_or_sync(0xffffffffu, alive ? ~bits : 0u);
         if ((threadIdx.x & 31) == 0 && (o | no)) { atomicOr(&p.header->depth_or, o); atomicOr(&p.header->depth_nor, no); }
+    }
+    if (idx < p.P) {   // depth-sort key + packed tile rectangle {x0 | y0 << 16, w | h << 16}; culled: empty rectangle
+        p.sort_keys[idx] = alive ? __float_as_uint(tz) : 0u;
+        p.rects[idx] = alive ? make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)(x1 - x0) | ((uint32_t)(y1 - y0) << 16))
+                             : make_uint2(0u, 0u);
     }
     if (!alive) return;
     float4* rec = reinterpret_cast<float4*>(p.rec + (size_t)idx * p.recf);
@@ -341,80 +349,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(int P, const uint32_
     }
 }
 
-// ---- duplicateWithKeys (rasterizer_impl.cu:70-111): emission order = Gaussian index, then tile
-// row, then tile column — the stable sort preserves it for equal (tile, depth) keys.
-// The reference lets one thread loop over its Gaussian's rectangle (long-tail divergence,
-// scattered 8 B stores).  Here a warp owns 32 consecutive Gaussians, whose output slots form ONE
-// contiguous range [offset of the first, offset after the last): lanes stride that range, find the
-// owning Gaussian of each slot by a 5-step search over the warp's prefix sums, and store fully
-// coalesced 256 B rows with every lane busy regardless of how the tile counts are distributed.
-__global__ void __launch_bounds__(256) emit_keys_kernel(int P, int recf, int gx, int gy,
-                                                        const float* __restrict__ rec,
-                                                        const int* __restrict__ radii,
-                                                        const uint32_t* __restrict__ offsets,
-                                                        uint64_t* __restrict__ keys,
-                                                        uint32_t* __restrict__ vals, long long capacity) {
-    __shared__ uint32_t sIncl[8][32], sDepth[8][32];
-    __shared__ int sX0[8][32], sY0[8][32], sW[8][32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-    uint32_t dbits = 0, cnt = 0;
-    if (idx < P) {
-        const int radius = radii[idx];
-        if (radius > 0) {
-            const float4 a = *reinterpret_cast<const float4*>(rec + (size_t)idx * recf);
-            const float4 b = *reinterpret_cast<const float4*>(rec + (size_t)idx * recf + 4);
-            get_rect(a.x, a.y, radius, gx, gy, x0, y0, x1, y1);
-            dbits = __float_as_uint(b.z);
-            cnt = (uint32_t)((x1 - x0) * (y1 - y0));
-        }
-    }
-    uint32_t incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
-    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total == 0) return;
-    const int first = blockIdx.x * blockDim.x + warp * 32;                     // first Gaussian of this warp
-    const uint32_t base = first == 0 ? 0u : offsets[first - 1];               // == global offset of the warp's slot 0
-    sIncl[warp][lane] = incl; sDepth[warp][lane] = dbits; sX0[warp][lane] = x0; sY0[warp][lane] = y0; sW[warp][lane] = x1 - x0;
-    __syncwarp();
-    for (uint32_t s = lane; s < total; s += 32) {
-        int lo = 0, hi = 31;                                                  // smallest g with incl[g] > s
-#pragma unroll
-        for (int it = 0; it < 5; ++it) { const int mid = (lo + hi) >> 1; if (sIncl[warp][mid] > s) hi = mid; else lo = mid + 1; }
-        const int g = lo;
-        const uint32_t excl = g == 0 ? 0u : sIncl[warp][g - 1];
-        const int t = (int)(s - excl), w = sW[warp][g];
-        const int ty = sY0[warp][g] + t / w, tx = sX0[warp][g] + t % w;
-        const long long off = (long long)base + s;
-        if (off < capacity) {
-            keys[off] = ((uint64_t)(uint32_t)(ty * gx + tx) << 32) | (uint64_t)sDepth[warp][g];
-            vals[off] = (uint32_t)(first + g);
-        }
-    }
-}
-
-// ---- identifyTileRanges (rasterizer_impl.cu:116-138) ----------------------------------------
-__global__ void __launch_bounds__(256) tile_ranges_kernel(const GeomHeader* __restrict__ header,
-                                                          long long capacity,
-                                                          const uint64_t* __restrict__ keys_a,
-                                                          const uint64_t* __restrict__ keys_b,
-                                                          uint2* __restrict__ ranges) {
-    const long long R = min((long long)header->num_rendered, capacity);
-    const uint64_t* __restrict__ keys = (header->sort_exec & 1u) ? keys_b : keys_a;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < R;
-         i += (long long)gridDim.x * blockDim.x) {
-        const uint32_t cur = (uint32_t)(keys[i] >> 32);
-        if (i == 0) ranges[cur].x = 0;
-        else {
-            const uint32_t prev = (uint32_t)(keys[i - 1] >> 32);
-            if (cur != prev) { ranges[prev].y = (uint32_t)i; ranges[cur].x = (uint32_t)i; }
-        }
-        if (i == R - 1) ranges[cur].y = (uint32_t)R;
-    }
-}
-
 // Longest-processing-time-first order of the tiles for the compositors: the CTAs of the heavy
 // tiles (longest sorted lists) are launched first so that the grid's tail consists of light tiles
 // (with row-major order the last heavy CTAs left 20% of the SM-cycles idle).  Coarse counting sort
@@ -452,10 +386,8 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D,
 }
 
 // ---- host launchers -----------------------------------------------------------------------
-int launch_projection(const r3dg_raster_fwd_args& a, const GeomLayout& gl, const BinLayout& bl,
-                      cudaStream_t stream, stage_mark_fn mark) {
+int launch_projection(const r3dg_raster_fwd_args& a, const GeomLayout& gl, cudaStream_t stream) {
     char* geom = (char*)a.geom;
-    char* bin = (char*)a.binning;
     ProjParams p;
     p.P = a.P; p.S = a.S; p.D = a.D; p.M = a.M; p.W = a.W; p.H = a.H;
     p.gx = (a.W + R3DG_TILE - 1) / R3DG_TILE; p.gy = (a.H + R3DG_TILE - 1) / R3DG_TILE;
@@ -470,27 +402,30 @@ int launch_projection(const r3dg_raster_fwd_args& a, const GeomLayout& gl, const
     p.rec = (float*)(geom + gl.rec); p.tiles_touched = (uint32_t*)(geom + gl.tiles_touched);
     p.clamped = (uint8_t*)(geom + gl.clamped); p.radii = a.radii; p.out_weights = a.out_weights;
     p.header = (GeomHeader*)(geom + gl.header);
-    const int nb = (a.P + 255) / 256;
+    const SortLayout sl(a.P);
+    p.sort_keys = (uint32_t*)(geom + gl.sort + sl.keys_a);
+    p.sort_vals = (uint32_t*)(geom + gl.sort + sl.vals_a);
+    p.rects = (uint2*)(geom + gl.rects);
     const size_t sh_smem = a.shs ? (size_t)3 * a.M * (PROJ_THREADS + 1) * sizeof(float) : 0;
     project_kernel<<<(a.P + PROJ_THREADS - 1) / PROJ_THREADS, PROJ_THREADS, sh_smem, stream>>>(p);
-    mark(1, stream);
-    const int nscan = (a.P + R3DG_SCAN_ITEMS - 1) / R3DG_SCAN_ITEMS;
-    R3DG_CUDA_TRY(cudaMemsetAsync(geom + gl.scan_state, 0, (size_t)(nscan + 1) * 4, stream));
-    scan_kernel<<<nscan, SCAN_THREADS, 0, stream>>>(a.P, p.tiles_touched, (uint32_t*)(geom + gl.point_offsets),
-                                                    (volatile uint32_t*)(geom + gl.scan_state), p.header);
-    mark(2, stream);
-    emit_keys_kernel<<<nb, 256, 0, stream>>>(a.P, gl.recf, p.gx, p.gy, p.rec, a.radii,
-                                             (const uint32_t*)(geom + gl.point_offsets),
-                                             (uint64_t*)(bin + bl.keys_a), (uint32_t*)(bin + bl.vals_a), bl.capacity);
     R3DG_CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
-int launch_tile_ranges(const void* geom_header, long long capacity, const uint64_t* keys_a,
-                       const uint64_t* keys_b, void* ranges, uint32_t* tile_order, int num_tiles, int num_sms,
-                       cudaStream_t stream) {
-    R3DG_CUDA_TRY(cudaMemsetAsync(ranges, 0, (size_t)num_tiles * 8, stream));
-    tile_ranges_kernel<<<num_sms * 8, 256, 0, stream>>>((const GeomHeader*)geom_header, capacity, keys_a, keys_b, (uint2*)ranges);
+// Debug only (r3dg_raster_debug_copy id 8): the reference's geomState.point_offsets, the inclusive
+// scan of tiles_touched in Gaussian-index order (rasterizer_impl.cu:288).  The hot path no longer
+// needs it.  `state` holds P / R3DG_SCAN_ITEMS + 2 words, `ticket_header` a zeroed GeomHeader.
+int launch_point_offsets(int P, const uint32_t* tiles_touched, uint32_t* out, uint32_t* state,
+                         GeomHeader* ticket_header, cudaStream_t stream) {
+    const int nscan = (P + R3DG_SCAN_ITEMS - 1) / R3DG_SCAN_ITEMS;
+    R3DG_CUDA_TRY(cudaMemsetAsync(state, 0, (size_t)(nscan + 1) * 4, stream));
+    R3DG_CUDA_TRY(cudaMemsetAsync(ticket_header, 0, sizeof(GeomHeader), stream));
+    scan_kernel<<<nscan, SCAN_THREADS, 0, stream>>>(P, tiles_touched, out, (volatile uint32_t*)state, ticket_header);
+    R3DG_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int launch_tile_order(const void* ranges, uint32_t* tile_order, int num_tiles, cudaStream_t stream) {
     tile_order_kernel<<<1, 1024, 0, stream>>>(num_tiles, (const uint2*)ranges, tile_order);
     R3DG_CUDA_TRY(cudaGetLastError());
     return 0;

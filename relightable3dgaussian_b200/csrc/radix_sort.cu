@@ -1,17 +1,19 @@
-// Stable LSD radix sort of (u64 key, u32 value) pairs — replaces cub::DeviceRadixSort::SortPairs
-// at reference rasterizer_impl.cu:313-318 (K5).  Hand-written one-sweep design for sm_100a:
+// Stable LSD radix sort of (u32 key, u32 value) pairs.  In the rasterizer it orders the Gaussians
+// by view depth once (P pairs) instead of the reference's cub::DeviceRadixSort::SortPairs over
+// all R ~ 8 P (tile, depth) instances (rasterizer_impl.cu:313-318); the per-tile lists are then
+// produced by the order-preserving binning in binning.cu.  The BVH and kNN builders sort their
+// 30-bit Morton codes with it (bvh.cu, knn.cu).  Hand-written one-sweep design for sm_100a:
 //
-//   1. sort_histogram_kernel : one read of the keys builds the digit histograms of ALL passes
-//      (and clears the look-back descriptors this frame will use);
-//   2. sort_scan_kernel      : exclusive scan of each 256-bin histogram -> global digit bases;
+//   1. sort_histogram_kernel : one read of the keys builds the digit histograms of ALL passes;
+//   2. sort_scan_kernel      : exclusive scan of each histogram -> global digit bases;
 //   3. sort_onesweep_kernel  : per pass ONE read + ONE write of the pairs.  A persistent grid
-//      pulls 3072-key tiles from an atomic ticket; per tile: warp-synchronous match-any ranking
-//      (stable), chained decoupled look-back per digit for the tile's global offset, reorder
-//      through shared memory so that global writes are digit-contiguous runs.
+//      pulls 2048-pair tiles from an atomic ticket.  Per tile: a shared-memory histogram gives the
+//      tile's digit counts, which are published for the successors BEFORE the expensive ranking
+//      (so nobody waits on it); warp-synchronous match-any ranking (stable); decoupled look-back
+//      per digit with escalating batches of independent loads; reorder through shared memory so
+//      that the global writes are digit-contiguous runs.
 //
-// The number of keys R is read from the geometry header on the device: no host sync, grids are
-// sized from the SM count.  Stability + emission order (Gaussian index ascending) reproduces
-// the reference's tie order for equal (tile, depth) keys bit-exactly.
+// Which key bits need sorting is decided on the device (sort_plan in common.cuh): no host sync.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -21,36 +23,34 @@ namespace r3dg {
 #define FLAG_INC 0x80000000u
 #define VAL_MASK 0x3fffffffu
 
-__global__ void __launch_bounds__(256) sort_histogram_kernel(const GeomHeader* __restrict__ header,
-                                                             long long capacity, int passes,
-                                                             const uint64_t* __restrict__ keys,
+__global__ void __launch_bounds__(256) sort_histogram_kernel(GeomHeader* __restrict__ header, long long n,
+                                                             const uint32_t* __restrict__ keys,
                                                              uint32_t* __restrict__ hist,
-                                                             uint32_t* __restrict__ lookback,
-                                                             long long max_tiles) {
+                                                             uint32_t* __restrict__ lookback0) {
     __shared__ uint32_t sh[R3DG_SORT_MAX_PASSES * 256];
-    const long long R = min((long long)header->num_rendered, capacity);
-    for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) sh[i] = 0;
+    int passes, w;
+    sort_plan(header->depth_or & header->depth_nor, passes, w);
+    if (blockIdx.x == 0 && threadIdx.x == 0) header->sort_exec = (uint32_t)passes;
+    const uint32_t mask = (1u << w) - 1u;
+    for (int i = threadIdx.x; i < R3DG_SORT_MAX_PASSES * 256; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < R; i += stride) {
-        const uint64_t k = keys[i];
-        for (int p = 0; p < passes; ++p) atomicAdd(&sh[p * 256 + (uint32_t)((k >> (8 * p)) & 0xff)], 1u);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t k = keys[i];
+        for (int p = 0; p < passes; ++p) atomicAdd(&sh[p * 256 + ((k >> (p * w)) & mask)], 1u);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < passes * 256; i += blockDim.x)
         if (sh[i]) atomicAdd(&hist[i], sh[i]);
-    // clear the look-back descriptors of the tiles this frame uses
-    const long long ntiles = (R + R3DG_SORT_TILE - 1) / R3DG_SORT_TILE;
-    for (int p = 0; p < passes; ++p) {
-        uint32_t* lb = lookback + (size_t)p * max_tiles * 256;
-        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < ntiles * 256; i += stride) lb[i] = 0;
-    }
+    // clear descriptor plane 0 (pass 0); every pass clears the other plane for its successor
+    const long long ntiles = (n + R3DG_SORT_TILE - 1) / R3DG_SORT_TILE;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < ntiles * 256; i += stride) lookback0[i] = 0;
 }
 
-__global__ void __launch_bounds__(256) sort_scan_kernel(int passes, uint32_t* __restrict__ hist) {
+__global__ void __launch_bounds__(256) sort_scan_kernel(uint32_t* __restrict__ hist) {
     // one block; thread d owns bin d of every pass; exclusive scan through shared memory
     __shared__ uint32_t s[256];
-    for (int p = 0; p < passes; ++p) {
+    for (int p = 0; p < R3DG_SORT_MAX_PASSES; ++p) {
         const uint32_t v = hist[p * 256 + threadIdx.x];
         s[threadIdx.x] = v;
         __syncthreads();
@@ -65,171 +65,180 @@ __global__ void __launch_bounds__(256) sort_scan_kernel(int passes, uint32_t* __
     }
 }
 
+// One look-back step: B descriptors of consecutive predecessors are fetched with independent
+// loads and consumed in order while they are ready.  Returns true when an inclusive prefix ended
+// the walk.
+template <int B>
+__device__ __forceinline__ bool lookback_step(const uint32_t* col, long long& t, uint32_t& prefix) {
+    uint32_t sv[B];
+#pragma unroll
+    for (int i = 0; i < B; ++i) sv[i] = (t - i >= 0) ? ld_relaxed_gpu(col + (size_t)(t - i) * 256) : FLAG_INC;
+    int used = 0;
+    bool done = false;
+#pragma unroll
+    for (int i = 0; i < B; ++i) {
+        if (!done && used == i && (sv[i] & (FLAG_AGG | FLAG_INC)) != 0u) {
+            prefix += sv[i] & VAL_MASK;
+            ++used;
+            if (sv[i] & FLAG_INC) done = true;
+        }
+    }
+    t -= used;
+    return done;
+}
+
 struct SortSmem {
-    uint64_t keys[R3DG_SORT_TILE];
+    uint32_t keys[R3DG_SORT_TILE];
     uint32_t vals[R3DG_SORT_TILE];
     uint32_t warp_hist[R3DG_SORT_THREADS / 32][256];
-    uint32_t local_off[256];     // exclusive prefix of digit counts inside the tile
+    uint32_t block_hist[256];    // digit counts of the tile (valid keys only)
+    uint32_t local_off[256];     // exclusive prefix of the digit counts inside the tile
     uint32_t global_off[256];    // global start of this tile's run of digit d
+    uint32_t s_w[R3DG_SORT_THREADS / 32];
     uint32_t tile;
 };
 
 __global__ void __launch_bounds__(R3DG_SORT_THREADS) sort_onesweep_kernel(
-    GeomHeader* header, long long capacity, int slot, int passes, const uint64_t* __restrict__ keys_in,
-    const uint32_t* __restrict__ vals_in, uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-    const uint32_t* __restrict__ digit_base, volatile uint32_t* lookback) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SortSmem& sm = *reinterpret_cast<SortSmem*>(smem_raw);
-    const long long R = min((long long)header->num_rendered, capacity);
+    GeomHeader* header, long long n, int slot, const uint32_t* __restrict__ keys_in,
+    const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+    const uint32_t* __restrict__ digit_base, uint32_t* lb_cur, uint32_t* lb_next) {
+    __shared__ SortSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // slot = index among the EXECUTED passes; the digit it sorts on is decided on the device
-    const uint32_t depth_diff = header->depth_or & header->depth_nor;
-    const int pass = sort_digit_of_slot(depth_diff, passes, slot);
-    if (pass < 0) return;                              // fewer digits needed than slots launched
-    if (blockIdx.x == 0 && tid == 0 && slot == 0) header->sort_exec = (uint32_t)sort_num_exec(depth_diff, passes);
-    const int shift = 8 * pass;
-    const long long ntiles = (R + R3DG_SORT_TILE - 1) / R3DG_SORT_TILE;
+    int passes, w;
+    sort_plan(header->depth_or & header->depth_nor, passes, w);
+    if (slot >= passes) return;                          // fewer digits needed than slots launched
+    const int shift = slot * w;
+    const uint32_t mask = (1u << w) - 1u;
+    const int bins = 1 << w;
+    const long long ntiles = (n + R3DG_SORT_TILE - 1) / R3DG_SORT_TILE;
     constexpr int NW = R3DG_SORT_THREADS / 32;
-    constexpr int PER_WARP = R3DG_SORT_TILE / NW;        // 384 consecutive keys per warp
+    constexpr int PER_WARP = R3DG_SORT_TILE / NW;        // 256 consecutive pairs per warp
 
     while (true) {
         __syncthreads();
         if (tid == 0) sm.tile = atomicAdd(&header->sort_ticket[slot], 1u);
         for (int i = tid; i < NW * 256; i += R3DG_SORT_THREADS) (&sm.warp_hist[0][0])[i] = 0;
+        sm.block_hist[tid] = 0;
         __syncthreads();
         const long long tile = sm.tile;
         if (tile >= ntiles) break;
         const long long tile_base = tile * R3DG_SORT_TILE;
-        const int count = (int)min((long long)R3DG_SORT_TILE, R - tile_base);
+        const int count = (int)min((long long)R3DG_SORT_TILE, n - tile_base);
 
-        // ---- load + stable ranking within the warp's 384-key slice ---------------------------
-        uint64_t k[R3DG_SORT_ITEMS];
-        uint32_t v[R3DG_SORT_ITEMS];
-        uint32_t rank[R3DG_SORT_ITEMS];
+        // ---- load; tile digit counts through shared atomics ----------------------------------
+        uint32_t k[R3DG_SORT_ITEMS], v[R3DG_SORT_ITEMS], dg[R3DG_SORT_ITEMS], rank[R3DG_SORT_ITEMS];
 #pragma unroll
         for (int i = 0; i < R3DG_SORT_ITEMS; ++i) {
             const int local = warp * PER_WARP + i * 32 + lane;
             const bool valid = local < count;
-            k[i] = valid ? keys_in[tile_base + local] : ~0ull;
+            k[i] = valid ? keys_in[tile_base + local] : 0u;
             v[i] = valid ? vals_in[tile_base + local] : 0u;
         }
 #pragma unroll
         for (int i = 0; i < R3DG_SORT_ITEMS; ++i) {
-            const uint32_t d = (uint32_t)(k[i] >> shift) & 0xffu;
-            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            const bool valid = warp * PER_WARP + i * 32 + lane < count;
+            // padding slots take the last digit: they trail every valid key of that digit (they are
+            // the tail of the tile), so valid ranks are unaffected, and they are never stored
+            dg[i] = valid ? ((k[i] >> shift) & mask) : mask;
+            if (valid) atomicAdd(&sm.block_hist[dg[i]], 1u);
+        }
+        __syncthreads();
+
+        // ---- publish the aggregate at once; tile-local exclusive offsets ----------------------
+        const int d = tid;                                // R3DG_SORT_THREADS == 256 >= bins
+        const uint32_t cnt = sm.block_hist[d];
+        uint32_t* lb = lb_cur + (size_t)tile * 256;
+        if (d < bins) st_relaxed_gpu(lb + d, cnt | (tile == 0 ? FLAG_INC : FLAG_AGG));
+        {
+            uint32_t inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t t2 = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t2; }
+            if (lane == 31) sm.s_w[warp] = inc;
+            __syncthreads();
+            uint32_t woff = 0;
+#pragma unroll
+            for (int ww = 0; ww < NW; ++ww) if (ww < warp) woff += sm.s_w[ww];
+            sm.local_off[d] = woff + inc - cnt;
+        }
+
+        // ---- stable ranking within the warp's 256-pair slice ----------------------------------
+#pragma unroll
+        for (int i = 0; i < R3DG_SORT_ITEMS; ++i) {
+            const uint32_t peers = __match_any_sync(0xffffffffu, dg[i]);
             const int leader = __ffs(peers) - 1;
             const uint32_t below = __popc(peers & ((1u << lane) - 1u));
             uint32_t old = 0;
-            if (lane == leader) { old = sm.warp_hist[warp][d]; sm.warp_hist[warp][d] = old + __popc(peers); }
+            if (lane == leader) { old = sm.warp_hist[warp][dg[i]]; sm.warp_hist[warp][dg[i]] = old + __popc(peers); }
             old = __shfl_sync(0xffffffffu, old, leader);
             rank[i] = old + below;
             __syncwarp();
         }
         __syncthreads();
 
-        // ---- per digit: warp prefixes, tile count, decoupled look-back ------------------------
+        // ---- per digit: warp prefixes; decoupled look-back ------------------------------------
         {
-            const int d = tid;                            // R3DG_SORT_THREADS == 256 digits
             uint32_t acc = 0;
 #pragma unroll
-            for (int w = 0; w < NW; ++w) { const uint32_t t = sm.warp_hist[w][d]; sm.warp_hist[w][d] = acc; acc += t; }
-            // padding keys (~0) inflate digit 255 of the last tile: remove them from the count
-            uint32_t cnt = acc;
-            if (d == 255) cnt -= (uint32_t)(R3DG_SORT_TILE - count);
-            uint32_t* lb = const_cast<uint32_t*>(lookback) + (size_t)tile * 256;
+            for (int ww = 0; ww < NW; ++ww) { const uint32_t t = sm.warp_hist[ww][d]; sm.warp_hist[ww][d] = acc; acc += t; }
             uint32_t prefix = 0;
-            if (tile == 0) {
-                st_relaxed_gpu(lb + d, cnt | FLAG_INC);
-            } else {
-                st_relaxed_gpu(lb + d, cnt | FLAG_AGG);
-                // Decoupled look-back.  The nearest predecessor is usually still ranking: spin on it
-                // with single loads; everything further back was published long ago, so those
-                // descriptors are fetched LB_BATCH at a time instead of as a chain of dependent
-                // L2 round trips.
-                constexpr int LB_BATCH = 8;
-                const uint32_t* col = const_cast<const uint32_t*>(lookback) + d;
+            if (tile > 0 && d < bins) {
+                const uint32_t* col = lb_cur + d;
                 long long t = tile - 1;
-                bool done = false;
-                while (!done) {
-                    uint32_t s0;
-                    do { s0 = ld_relaxed_gpu(col + (size_t)t * 256); } while ((s0 & (FLAG_AGG | FLAG_INC)) == 0u);
-                    prefix += s0 & VAL_MASK;
-                    if (s0 & FLAG_INC) break;
-                    --t;
-                    uint32_t sv[LB_BATCH];
-#pragma unroll
-                    for (int i = 0; i < LB_BATCH; ++i) sv[i] = (t - i >= 0) ? ld_relaxed_gpu(col + (size_t)(t - i) * 256) : FLAG_INC;
-                    int used = 0;
-#pragma unroll
-                    for (int i = 0; i < LB_BATCH; ++i) {
-                        if (!done && used == i && (sv[i] & (FLAG_AGG | FLAG_INC)) != 0u) {
-                            prefix += sv[i] & VAL_MASK;
-                            ++used;
-                            if (sv[i] & FLAG_INC) done = true;
-                        }
-                    }
-                    t -= used;
-                }
+                // predecessors published their aggregates before ranking, so the walk rarely waits:
+                // 1 load, then 8, then 32 independent loads per step
+                if (!lookback_step<1>(col, t, prefix))
+                    if (!lookback_step<8>(col, t, prefix))
+                        while (!lookback_step<32>(col, t, prefix)) {}
                 st_relaxed_gpu(lb + d, (prefix + cnt) | FLAG_INC);
             }
-            sm.global_off[d] = digit_base[pass * 256 + d] + prefix;
-            // block-wide exclusive scan of acc over the 256 digits -> local_off
-            uint32_t inc = acc;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { uint32_t t2 = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t2; }
-            __shared__ uint32_t s_w[NW];
-            if (lane == 31) s_w[warp] = inc;
-            __syncthreads();
-            uint32_t woff = 0;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) if (w < warp) woff += s_w[w];
-            sm.local_off[d] = woff + inc - acc;
+            sm.global_off[d] = digit_base[slot * 256 + d] + prefix;
+            lb_next[(size_t)tile * 256 + d] = 0;          // descriptor plane of the next pass
         }
         __syncthreads();
 
         // ---- reorder through shared memory, then digit-contiguous global writes ----------------
 #pragma unroll
         for (int i = 0; i < R3DG_SORT_ITEMS; ++i) {
-            const uint32_t d = (uint32_t)(k[i] >> shift) & 0xffu;
-            const uint32_t pos = sm.local_off[d] + sm.warp_hist[warp][d] + rank[i];
-            sm.keys[pos] = k[i];
-            sm.vals[pos] = v[i];
+            const bool valid = warp * PER_WARP + i * 32 + lane < count;
+            if (valid) {
+                const uint32_t pos = sm.local_off[dg[i]] + sm.warp_hist[warp][dg[i]] + rank[i];
+                sm.keys[pos] = k[i];
+                sm.vals[pos] = v[i];
+            }
         }
         __syncthreads();
         for (int i = tid; i < count; i += R3DG_SORT_THREADS) {
-            const uint64_t kk = sm.keys[i];
-            const uint32_t d = (uint32_t)(kk >> shift) & 0xffu;
-            const uint32_t dst = sm.global_off[d] + ((uint32_t)i - sm.local_off[d]);
+            const uint32_t kk = sm.keys[i];
+            const uint32_t dd = (kk >> shift) & mask;
+            const uint32_t dst = sm.global_off[dd] + ((uint32_t)i - sm.local_off[dd]);
             keys_out[dst] = kk;
             vals_out[dst] = sm.vals[i];
         }
     }
 }
 
-int launch_sort(void* geom_header, char* bin, const BinLayout& bl, int passes, int num_sms,
+// header: depth_or / depth_nor hold the OR of the keys and of their complements, sort_ticket[]
+// is zero.  On return (stream order) the sorted pairs are in buffer (header->sort_exec & 1).
+int launch_sort(void* geom_header, char* buf, const SortLayout& sl, long long n, int num_sms,
                 cudaStream_t stream) {
-    if (passes > R3DG_SORT_MAX_PASSES) return R3DG_ERR_UNSUPPORTED;
+    if (n > sl.n || n >= (1ll << 30)) return R3DG_ERR_BAD_ARG;
     GeomHeader* header = (GeomHeader*)geom_header;
-    uint32_t* hist = (uint32_t*)(bin + bl.hist);
-    uint32_t* lookback = (uint32_t*)(bin + bl.lookback);
+    uint32_t* hist = (uint32_t*)(buf + sl.hist);
+    uint32_t* lb0 = (uint32_t*)(buf + sl.lookback);
+    uint32_t* lb1 = lb0 + (size_t)sl.tiles * 256;
     R3DG_CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)R3DG_SORT_MAX_PASSES * 256 * 4, stream));
-    sort_histogram_kernel<<<num_sms * 4, 256, 0, stream>>>(header, bl.capacity, passes,
-                                                           (const uint64_t*)(bin + bl.keys_a), hist,
-                                                           lookback, bl.max_tiles);
-    sort_scan_kernel<<<1, 256, 0, stream>>>(passes, hist);
-    static bool attr_set = false;
-    const size_t smem = sizeof(SortSmem);
-    if (!attr_set) {
-        R3DG_CUDA_TRY(cudaFuncSetAttribute(sort_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    uint64_t* ka = (uint64_t*)(bin + bl.keys_a); uint64_t* kb = (uint64_t*)(bin + bl.keys_b);
-    uint32_t* va = (uint32_t*)(bin + bl.vals_a); uint32_t* vb = (uint32_t*)(bin + bl.vals_b);
-    for (int k = 0; k < passes; ++k) {
+    const long long ntiles = (n + R3DG_SORT_TILE - 1) / R3DG_SORT_TILE;
+    const int hb = (int)std::min<long long>((long long)num_sms * 4, std::max<long long>(1, (n + 2047) / 2048));
+    sort_histogram_kernel<<<hb, 256, 0, stream>>>(header, n, (const uint32_t*)(buf + sl.keys_a), hist, lb0);
+    sort_scan_kernel<<<1, 256, 0, stream>>>(hist);
+    uint32_t* ka = (uint32_t*)(buf + sl.keys_a); uint32_t* kb = (uint32_t*)(buf + sl.keys_b);
+    uint32_t* va = (uint32_t*)(buf + sl.vals_a); uint32_t* vb = (uint32_t*)(buf + sl.vals_b);
+    const int grid = (int)std::min<long long>((long long)num_sms * 4, std::max<long long>(1, ntiles));
+    for (int k = 0; k < R3DG_SORT_MAX_PASSES; ++k) {
         const bool even = (k & 1) == 0;
-        sort_onesweep_kernel<<<num_sms * 3, R3DG_SORT_THREADS, smem, stream>>>(
-            header, bl.capacity, k, passes, even ? ka : kb, even ? va : vb, even ? kb : ka, even ? vb : va, hist,
-            (volatile uint32_t*)(lookback + (size_t)k * bl.max_tiles * 256));
+        sort_onesweep_kernel<<<grid, R3DG_SORT_THREADS, 0, stream>>>(
+            header, n, k, even ? ka : kb, even ? va : vb, even ? kb : ka, even ? vb : va, hist,
+            even ? lb0 : lb1, even ? lb1 : lb0);
     }
     R3DG_CUDA_TRY(cudaGetLastError());
     return 0;

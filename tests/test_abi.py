@@ -55,7 +55,7 @@ def test_sizing_functions_monotone_and_aligned():
     off = lib.r3dg_raster_img_n_contrib_offset(800, 800)
     assert 0 < off < i1 and off % 256 == 0
     b1, b2 = lib.r3dg_raster_binning_bytes(10_000), lib.r3dg_raster_binning_bytes(20_000)
-    assert 24 * 10_000 <= b1 < b2
+    assert 4 * 10_000 <= b1 < b2          # one u32 list entry per (tile, Gaussian) instance
 
 
 def test_bad_arguments_are_rejected_without_touching_the_gpu():
