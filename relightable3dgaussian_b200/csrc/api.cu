@@ -74,7 +74,7 @@ int r3dg_raster_forward(const r3dg_raster_fwd_args* a, r3dg_stream_t stream_) {
         if ((rc = launch_projection(*a, gl, stream)) != 0) return rc;
         prof_mark(true, 1, stream);
         if ((rc = launch_binning(a->P, a->W, a->H, geom, gl, img, il, bin, bl, num_sms(), stream, mark)) != 0) return rc;
-        g_launches += 1 + (2 + R3DG_SORT_MAX_PASSES) + 4;
+        g_launches += 1 + (1 + R3DG_SORT_MAX_PASSES) + 5;   // project; histogram + radix passes; count, colsum, starts, apply, scatter
     } else {
         R3DG_CUDA_TRY(cudaMemsetAsync(img + il.ranges, 0, (size_t)tiles * 8, stream));
         for (int i = 1; i <= 4; ++i) prof_mark(true, i, stream);
@@ -174,7 +174,7 @@ int r3dg_bvh_leaf_aabbs(int P, const float* means3D, const float* scales, const 
 int r3dg_bvh_build(int P, int32_t* nodes, float* aabbs, uint64_t* morton, void* tmp, size_t tmp_bytes,
                    r3dg_stream_t stream) {
     if (P < 0) return R3DG_ERR_BAD_ARG;
-    g_launches += P > 0 ? 6 + 2 + 4 : 0;
+    g_launches += P > 0 ? 6 + 1 + R3DG_SORT_MAX_PASSES : 0;
     return launch_bvh_build(P, nodes, aabbs, morton, tmp, tmp_bytes, num_sms(), (cudaStream_t)stream);
 }
 
@@ -194,7 +194,7 @@ int r3dg_bvh_trace_opacity(int P, long long num_rays, const int32_t* nodes, cons
 size_t r3dg_knn_tmp_bytes(int P) { return knn_tmp_bytes(P); }
 int r3dg_knn_dist2(int P, const float* points, float* mean_dist2, void* tmp, size_t tmp_bytes, r3dg_stream_t stream) {
     if (P < 0) return R3DG_ERR_BAD_ARG;
-    g_launches += P > 0 ? 6 + 2 + 4 : 0;
+    g_launches += P > 0 ? 6 + 1 + R3DG_SORT_MAX_PASSES : 0;
     return launch_knn(P, points, mean_dist2, tmp, tmp_bytes, num_sms(), (cudaStream_t)stream);
 }
 

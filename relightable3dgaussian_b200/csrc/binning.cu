@@ -8,138 +8,256 @@
 //   1. stable-sort the P Gaussians by their depth bits (radix_sort.cu; ties keep index order);
 //   2. append them, in that order, to the lists of the tiles their rectangle covers.
 // Step 2 is a counting sort by tile id that must preserve the sequence order, done with two
-// passes over the depth-sorted sequence cut into chunks (one warp per chunk, a private per-tile
-// table in shared memory):
-//   bin_pass<false> : M[chunk][tile] = number of instances the chunk adds to the tile;
-//   bin_scan        : exclusive scan of every column of M (per tile over the chunks) + totals;
-//   bin_tile_start  : exclusive scan of the totals -> ranges[tile], R;
-//   bin_pass<true>  : every chunk re-walks its Gaussians and writes each instance to
-//                     start[tile] + M[chunk][tile] + (rank inside the chunk, in sequence order).
+// passes over the depth-sorted sequence cut into chunks (one CTA per chunk, per-tile tables in
+// shared memory):
+//   bin_count                  : M[chunk][tile] = number of instances the chunk adds to the tile;
+//   bin_colsum/starts/apply    : exclusive scan of every column of M (per tile over the chunks),
+//                                exclusive scan of the tile totals -> ranges[tile], R; M becomes the
+//                                absolute first slot of (chunk, tile);
+//   bin_scatter                : every chunk re-walks its Gaussians and writes each instance to
+//                                M[chunk][tile] + (rank inside the chunk, in sequence order).
 // Equal (tile, depth) keys end up in Gaussian-index order, exactly as the reference's stable sort
 // leaves them, so point_list and ranges are bit-identical.
+#include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
 namespace r3dg {
 
-// slot -> (Gaussian of the batch, tile) for a batch of 32 Gaussians whose inclusive instance
-// counts are staged in shared memory (same scheme as the cooperative key emission it replaces).
-struct BatchStage { uint32_t incl[32], xy[32], w[32], g[32]; };
-
-template <bool SCATTER>
-__global__ void __launch_bounds__(256) bin_pass_kernel(int P, int T, int gx, int CH, int chunks,
-                                                       const GeomHeader* __restrict__ header,
-                                                       const uint32_t* __restrict__ vals_a,
-                                                       const uint32_t* __restrict__ vals_b,
-                                                       const uint2* __restrict__ rects,
-                                                       uint32_t* __restrict__ M,
-                                                       const uint2* __restrict__ ranges,
-                                                       uint32_t* __restrict__ point_list, long long capacity) {
+// bin_count: one CTA per chunk, one thread per Gaussian walking its own rectangle; counting
+// needs no order, so the lanes work on different Gaussians in parallel with fire-and-forget
+// shared atomics on the CTA's table.
+__global__ void __launch_bounds__(256) bin_count_kernel(int P, int T, int gx, int CH,
+                                                        const GeomHeader* __restrict__ header,
+                                                        const uint32_t* __restrict__ vals_a,
+                                                        const uint32_t* __restrict__ vals_b,
+                                                        const uint2* __restrict__ rects, uint32_t* __restrict__ M) {
     extern __shared__ __align__(16) uint32_t bin_smem[];
-    const int nwb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c = blockIdx.x * nwb + warp;
-    if (c >= chunks) return;                              // no CTA-wide barriers below
-    uint32_t* tbl = bin_smem + (size_t)warp * T;
-    BatchStage& st = reinterpret_cast<BatchStage*>(bin_smem + (size_t)nwb * T)[warp];
+    uint32_t* tbl = bin_smem;
     const uint32_t* __restrict__ order = (header->sort_exec & 1u) ? vals_b : vals_a;
-    uint32_t* row = M + (size_t)c * T;
-    for (int t = lane; t < T; t += 32) tbl[t] = SCATTER ? ranges[t].x + row[t] : 0u;
-    __syncwarp();
+    const int c = blockIdx.x;
     const int j0 = c * CH, j1 = min(P, j0 + CH);
-    // two-deep software pipeline over the dependent gathers order[j] -> rects[g]
-    uint32_t g_cur = 0, g_nxt = 0;
-    uint2 r_cur = make_uint2(0u, 0u);
-    if (j0 + lane < j1) { g_cur = order[j0 + lane]; r_cur = rects[g_cur]; }
-    if (j0 + 32 + lane < j1) g_nxt = order[j0 + 32 + lane];
-    for (int jb = j0; jb < j1; jb += 32) {
-        const uint32_t g = g_cur;
-        const uint2 r = (jb + lane < j1) ? r_cur : make_uint2(0u, 0u);
-        // prefetch: rect of the next batch, index of the one after
-        g_cur = g_nxt;
-        if (jb + 32 + lane < j1) r_cur = rects[g_cur];
-        if (jb + 64 + lane < j1) g_nxt = order[jb + 64 + lane];
+    for (int t = threadIdx.x; t < T; t += blockDim.x) tbl[t] = 0u;
+    __syncthreads();
+    for (int j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
+        const uint2 r = rects[order[j]];
         const uint32_t w = r.y & 0xffffu, h = r.y >> 16;
-        const uint32_t cnt = w * h;
-        uint32_t incl = cnt;
+        uint32_t tile_row = (r.x >> 16) * (uint32_t)gx + (r.x & 0xffffu);
+        for (uint32_t y = 0; y < h; ++y, tile_row += (uint32_t)gx)
+            for (uint32_t x = 0; x < w; ++x) atomicAdd(&tbl[tile_row + x], 1u);
+    }
+    __syncthreads();
+    uint32_t* row = M + (size_t)c * T;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) row[t] = tbl[t];
+}
+
+// bin_scatter: one CTA per chunk.  Writing every instance straight to its slot costs one 4-byte
+// L2 write transaction per instance (~8M scattered sector writes = 130 us, whatever the ranking
+// logic).  Instead the chunk's instances are first gathered in shared memory grouped by tile:
+//   1. recount the chunk per tile (as bin_count), exclusive scan -> local CSR offsets;
+//   2. unordered append: one thread per Gaussian, slot = shared atomicAdd on the tile's cursor,
+//      entry = {Gaussian id, tile << 16 | position in the chunk};
+//   3. one thread per staged entry: rank = number of entries of its run (same tile) that come
+//      earlier in the sequence; global slot = M[chunk][tile] + rank.  A warp's lanes hold
+//      consecutive staged entries, i.e. whole runs, whose global slots are contiguous: the
+//      stores coalesce into a few sectors per run instead of one transaction per entry.
+// A chunk whose instances exceed the staging area is handled in several windows of tiles.
+#define BIN_SCATTER_THREADS 1024
+#define BIN_LONG_RUN 24            // runs longer than this are ranked through the bitmap
+#define BIN_MAX_LONG 2048          // >= staging capacity / BIN_LONG_RUN
+
+__global__ void __launch_bounds__(BIN_SCATTER_THREADS) bin_scatter_kernel(
+    int P, int T, int gx, int CH, int cap, const GeomHeader* __restrict__ header, const uint32_t* __restrict__ vals_a,
+    const uint32_t* __restrict__ vals_b, const uint2* __restrict__ rects, const uint32_t* __restrict__ M,
+    uint32_t* __restrict__ point_list, long long capacity) {
+    extern __shared__ __align__(16) uint32_t bin_smem[];
+    uint32_t* a = bin_smem;                               // [T] counts -> exclusive offsets -> cursors
+    const int words = (CH + 31) >> 5;                     // bitmap over the chunk positions, per warp
+    uint32_t* bitmaps = bin_smem + (((size_t)T + 3) & ~(size_t)3);
+    uint2* stage = reinterpret_cast<uint2*>(bitmaps + (size_t)(BIN_SCATTER_THREADS / 32) * 2 * words);
+    __shared__ uint32_t s_warp[BIN_SCATTER_THREADS / 32];
+    __shared__ int s_hi;
+    __shared__ uint32_t s_total, s_nlong;
+    __shared__ uint16_t s_long[BIN_MAX_LONG];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t* __restrict__ order = (header->sort_exec & 1u) ? vals_b : vals_a;
+    const int c = blockIdx.x;
+    const int j0 = c * CH, j1 = min(P, j0 + CH);
+    const uint32_t* __restrict__ row = M + (size_t)c * T;
+    for (int t = tid; t < T; t += BIN_SCATTER_THREADS) a[t] = 0u;
+    __syncthreads();
+    // ---- 1. per-tile counts of the chunk, exclusive scan over the tiles --------------------------
+    for (int j = j0 + tid; j < j1; j += BIN_SCATTER_THREADS) {
+        const uint2 r = rects[order[j]];
+        const uint32_t w = r.y & 0xffffu, h = r.y >> 16;
+        uint32_t tile_row = (r.x >> 16) * (uint32_t)gx + (r.x & 0xffffu);
+        for (uint32_t y = 0; y < h; ++y, tile_row += (uint32_t)gx)
+            for (uint32_t x = 0; x < w; ++x) atomicAdd(&a[tile_row + x], 1u);
+    }
+    __syncthreads();
+    const int per = (T + BIN_SCATTER_THREADS - 1) / BIN_SCATTER_THREADS;
+    const int t0 = min(T, tid * per), t1 = min(T, t0 + per);
+    uint32_t sum = 0;
+    for (int t = t0; t < t1; ++t) sum += a[t];
+    uint32_t inc = sum;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total == 0) continue;
-        st.incl[lane] = incl; st.xy[lane] = r.x; st.w[lane] = w ? w : 1u; st.g[lane] = g;
-        __syncwarp();
-        for (uint32_t base = 0; base < total; base += 32) {
-            const uint32_t s = base + lane;
-            const bool active = s < total;
-            int lo = 0, hi = 31;                          // smallest q with incl[q] > s
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t wv = lane < BIN_SCATTER_THREADS / 32 ? s_warp[lane] : 0u;
+        uint32_t wi = wv;
 #pragma unroll
-            for (int it = 0; it < 5; ++it) { const int mid = (lo + hi) >> 1; if (st.incl[mid] > s) hi = mid; else lo = mid + 1; }
-            const int q = lo;
-            const uint32_t excl = q == 0 ? 0u : st.incl[q - 1];
-            const uint32_t tt = active ? s - excl : 0u, ww = st.w[q], xy = st.xy[q];
-            const uint32_t ty = (xy >> 16) + tt / ww, tx = (xy & 0xffffu) + tt % ww;
-            const uint32_t tile = ty * (uint32_t)gx + tx;
-            if (!SCATTER) {
-                if (active) atomicAdd(&tbl[tile], 1u);
-            } else {
-                // lanes are in sequence order: equal tiles are ranked by lane
-                const uint32_t key = active ? tile : 0xffffffffu - (uint32_t)lane;
-                const uint32_t peers = __match_any_sync(0xffffffffu, key);
-                const int leader = __ffs(peers) - 1;
-                const uint32_t below = __popc(peers & ((1u << lane) - 1u));
-                uint32_t old = 0;
-                if (active && lane == leader) { old = tbl[tile]; tbl[tile] = old + __popc(peers); }
-                old = __shfl_sync(0xffffffffu, old, leader);
-                if (active) {
-                    const long long pos = (long long)old + below;
-                    if (pos < capacity) point_list[pos] = st.g[q];
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
+        if (lane < BIN_SCATTER_THREADS / 32) s_warp[lane] = wi - wv;
+        if (lane == 31) s_total = wi;
+    }
+    __syncthreads();
+    {
+        uint32_t run = s_warp[warp] + inc - sum;
+        for (int t = t0; t < t1; ++t) { const uint32_t n = a[t]; a[t] = run; run += n; }     // a[t] = first local slot of tile t
+    }
+    __syncthreads();
+    // ---- windows of tiles whose instances fit the staging area (normally a single one) ------------
+    int lo = 0;
+    while (lo < T) {
+        if (tid == 0) {
+            // E(t) = first local slot of tile t (a[] is still pristine for tiles >= lo), E(T) = total.
+            // Largest hi in (lo, T] with E(hi) - E(lo) <= cap; one tile never exceeds CH <= cap entries.
+            const uint32_t limit = a[lo] + (uint32_t)cap;
+            int l = T;
+            if (s_total > limit) {
+                l = lo + 1;
+                int h = T - 1;
+                while (l < h) { const int mid = (l + h + 1) >> 1; if (a[mid] <= limit) l = mid; else h = mid - 1; }
+            }
+            s_hi = l;
+        }
+        __syncthreads();
+        const int hi = s_hi;
+        const uint32_t first = a[lo];                      // read before any cursor of this window moves
+        if (tid == 0) s_nlong = 0u;
+        __syncthreads();
+        // ---- 2. unordered append of the window's instances --------------------------------------
+        for (int j = j0 + tid; j < j1; j += BIN_SCATTER_THREADS) {
+            const uint32_t g = order[j];
+            const uint2 r = rects[g];
+            const uint32_t w = r.y & 0xffffu, h = r.y >> 16;
+            uint32_t tile_row = (r.x >> 16) * (uint32_t)gx + (r.x & 0xffffu);
+            const uint32_t seq = (uint32_t)(j - j0);
+            for (uint32_t y = 0; y < h; ++y, tile_row += (uint32_t)gx)
+                for (uint32_t x = 0; x < w; ++x) {
+                    const uint32_t tile = tile_row + x;
+                    if ((int)tile >= lo && (int)tile < hi) {
+                        const uint32_t slot = atomicAdd(&a[tile], 1u) - first;
+                        stage[slot] = make_uint2(g, (tile << 16) | seq);
+                    }
+                }
+        }
+        __syncthreads();
+        // now a[t] = first slot of tile t+1 for t in [lo, hi)
+        const uint32_t n_stage = a[hi - 1] - first;
+        // the tiles with a long run (at most n_stage / BIN_LONG_RUN of them)
+        for (int t = lo + tid; t < hi; t += BIN_SCATTER_THREADS) {
+            const uint32_t rb = (t > lo ? a[t - 1] : first), re = a[t];
+            if (re - rb > BIN_LONG_RUN) s_long[atomicAdd(&s_nlong, 1u)] = (uint16_t)t;
+        }
+        __syncthreads();
+        // ---- 3. rank inside the run, coalesced copy-out -------------------------------------------
+        // 3a. short runs: one thread per staged entry, all-pairs rank
+        for (uint32_t i = tid; i < n_stage; i += BIN_SCATTER_THREADS) {
+            const uint2 e = stage[i];
+            const int t = (int)(e.y >> 16);
+            const uint32_t seq = e.y & 0xffffu;
+            const uint32_t rb = (t > lo ? a[t - 1] : first) - first, re = a[t] - first;
+            if (re - rb > BIN_LONG_RUN) continue;
+            uint32_t rank = 0;
+            for (uint32_t k = rb; k < re; ++k) rank += ((stage[k].y & 0xffffu) < seq) ? 1u : 0u;
+            const long long pos = (long long)row[t] + rank;
+            if (pos < capacity) point_list[pos] = e.x;
+        }
+        // 3b. long runs (depth slices that pile up on few tiles): one warp per run; a bitmap over the
+        //     chunk positions turns the rank into a prefix population count
+        {
+            uint32_t* bm = bitmaps + (size_t)warp * 2 * words;     // bits, then the exclusive prefix per word
+            uint32_t* bp = bm + words;
+            for (uint32_t li = warp; li < s_nlong; li += BIN_SCATTER_THREADS / 32) {
+                const int t = (int)s_long[li];
+                const uint32_t rb = (t > lo ? a[t - 1] : first) - first, re = a[t] - first;
+                for (int k = lane; k < words; k += 32) bm[k] = 0u;
+                __syncwarp();
+                for (uint32_t k = rb + lane; k < re; k += 32) { const uint32_t sq = stage[k].y & 0xffffu; atomicOr(&bm[sq >> 5], 1u << (sq & 31u)); }
+                __syncwarp();
+                uint32_t carry = 0;
+                for (int k0 = 0; k0 < words; k0 += 32) {
+                    const uint32_t c = (k0 + lane < words) ? (uint32_t)__popc(bm[k0 + lane]) : 0u;
+                    uint32_t inc = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+                    if (k0 + lane < words) bp[k0 + lane] = carry + inc - c;
+                    carry += __shfl_sync(0xffffffffu, inc, 31);
+                }
+                __syncwarp();
+                const uint32_t base = row[t];
+                for (uint32_t k = rb + lane; k < re; k += 32) {
+                    const uint2 e = stage[k];
+                    const uint32_t sq = e.y & 0xffffu;
+                    const uint32_t rank = bp[sq >> 5] + (uint32_t)__popc(bm[sq >> 5] & ((1u << (sq & 31u)) - 1u));
+                    const long long pos = (long long)base + rank;
+                    if (pos < capacity) point_list[pos] = e.x;
                 }
                 __syncwarp();
             }
         }
-        __syncwarp();
-    }
-    if (!SCATTER) {
-        __syncwarp();
-        for (int t = lane; t < T; t += 32) row[t] = tbl[t];
+        __syncthreads();
+        lo = hi;
     }
 }
 
-// Column scan of M: block = 32 tiles x 32 chunk groups.
-__global__ void __launch_bounds__(1024) bin_scan_kernel(int T, int chunks, uint32_t* __restrict__ M,
-                                                        uint32_t* __restrict__ tile_total) {
+// ---- column scan of M ------------------------------------------------------------------------
+// CTA = 32 tiles x 32 groups of BIN_G consecutive chunks (a "slab" of 32*BIN_G chunks);
+// grid = (tiles / 32, slabs).
+//   bin_colsum  : slab_sum[slab][tile] = sum of the slab's rows;
+//   bin_starts  : one CTA; exclusive scan of the tile totals -> ranges, R; per slab and tile the
+//                 absolute first slot (tile start + earlier slabs) -> slab_sum in place;
+//   bin_apply   : every thread keeps its BIN_G counts in registers, the CTA scans the 32 group sums
+//                 through shared memory and M is rewritten as ABSOLUTE first slots.
+#define BIN_G 16
+#define BIN_SLAB (32 * BIN_G)
+
+__global__ void __launch_bounds__(1024) bin_colsum_kernel(int T, int chunks, const uint32_t* __restrict__ M,
+                                                          uint32_t* __restrict__ slab_sum) {
     __shared__ uint32_t s[32][33];
     const int tx = threadIdx.x, gy = threadIdx.y;
     const int t = blockIdx.x * 32 + tx;
-    const int G = (chunks + 31) / 32;
-    const int c0 = min(chunks, gy * G), c1 = min(chunks, c0 + G);
+    const int c0 = blockIdx.y * BIN_SLAB + gy * BIN_G;
     uint32_t sum = 0;
-    if (t < T)
-        for (int c = c0; c < c1; ++c) sum += M[(size_t)c * T + t];
+    if (t < T) {
+#pragma unroll
+        for (int i = 0; i < BIN_G; ++i) if (c0 + i < chunks) sum += M[(size_t)(c0 + i) * T + t];
+    }
     s[gy][tx] = sum;
     __syncthreads();
     if (gy == 0) {
         uint32_t acc = 0;
 #pragma unroll
-        for (int g = 0; g < 32; ++g) { const uint32_t v = s[g][tx]; s[g][tx] = acc; acc += v; }
-        if (t < T) tile_total[t] = acc;
+        for (int g = 0; g < 32; ++g) acc += s[g][tx];
+        if (t < T) slab_sum[(size_t)blockIdx.y * T + t] = acc;
     }
-    __syncthreads();
-    uint32_t run = s[gy][tx];
-    if (t < T)
-        for (int c = c0; c < c1; ++c) { const uint32_t v = M[(size_t)c * T + t]; M[(size_t)c * T + t] = run; run += v; }
 }
 
-// Exclusive scan of the tile totals -> ranges (empty tiles stay (0,0) like the reference's
-// zero-initialised imgState.ranges), R -> header.  One CTA.
-__global__ void __launch_bounds__(1024) bin_tile_start_kernel(int T, const uint32_t* __restrict__ tile_total,
-                                                              uint2* __restrict__ ranges, GeomHeader* header,
-                                                              long long capacity) {
+// Empty tiles stay (0,0) like the reference's zero-initialised imgState.ranges.
+__global__ void __launch_bounds__(1024) bin_starts_kernel(int T, int slabs, uint32_t* __restrict__ slab_sum,
+                                                          uint2* __restrict__ ranges, GeomHeader* header,
+                                                          long long capacity) {
     __shared__ uint32_t s_warp[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int per = (T + 1023) / 1024;
     const int t0 = min(T, tid * per), t1 = min(T, t0 + per);
     uint32_t sum = 0;
-    for (int t = t0; t < t1; ++t) sum += tile_total[t];
+    for (int t = t0; t < t1; ++t)
+        for (int k = 0; k < slabs; ++k) sum += slab_sum[(size_t)k * T + t];
     uint32_t inc = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
@@ -156,11 +274,42 @@ __global__ void __launch_bounds__(1024) bin_tile_start_kernel(int T, const uint3
     __syncthreads();
     uint32_t run = s_warp[warp] + inc - sum;
     for (int t = t0; t < t1; ++t) {
-        const uint32_t n = tile_total[t];
+        uint32_t n = 0;
+        for (int k = 0; k < slabs; ++k) { const uint32_t v = slab_sum[(size_t)k * T + t]; slab_sum[(size_t)k * T + t] = run + n; n += v; }
         // on overflow (R > capacity: the host grows the buffer and re-runs) keep every range inside the buffer
         ranges[t] = n ? make_uint2((uint32_t)min((long long)run, capacity), (uint32_t)min((long long)run + n, capacity))
                       : make_uint2(0u, 0u);
         run += n;
+    }
+}
+
+__global__ void __launch_bounds__(1024) bin_apply_kernel(int T, int chunks, uint32_t* __restrict__ M,
+                                                         const uint32_t* __restrict__ slab_start) {
+    __shared__ uint32_t s[32][33];
+    const int tx = threadIdx.x, gy = threadIdx.y;
+    const int t = blockIdx.x * 32 + tx;
+    const int c0 = blockIdx.y * BIN_SLAB + gy * BIN_G;
+    uint32_t v[BIN_G], sum = 0;
+#pragma unroll
+    for (int i = 0; i < BIN_G; ++i) {
+        v[i] = (t < T && c0 + i < chunks) ? M[(size_t)(c0 + i) * T + t] : 0u;
+        sum += v[i];
+    }
+    s[gy][tx] = sum;
+    __syncthreads();
+    if (gy == 0) {
+        uint32_t acc = t < T ? slab_start[(size_t)blockIdx.y * T + t] : 0u;
+#pragma unroll
+        for (int g = 0; g < 32; ++g) { const uint32_t x = s[g][tx]; s[g][tx] = acc; acc += x; }
+    }
+    __syncthreads();
+    uint32_t run = s[gy][tx];
+    if (t < T) {
+#pragma unroll
+        for (int i = 0; i < BIN_G; ++i) {
+            if (c0 + i < chunks) M[(size_t)(c0 + i) * T + t] = run;
+            run += v[i];
+        }
     }
 }
 
@@ -182,52 +331,54 @@ int launch_rebuild_keys(int T, const void* ranges, const uint32_t* point_list, c
     return 0;
 }
 
-// Warps per CTA for the binning passes: as many private per-tile tables as fit.
-static int bin_warps_per_block(int T) {
-    const size_t per_warp = (size_t)T * 4 + sizeof(BatchStage);
-    const size_t budget = 100 * 1024;                     // two CTAs per SM when it fits
-    int nwb = (int)(budget / per_warp);
-    if (nwb >= 8) return 8;
-    if (nwb >= 1) return nwb;
-    return per_warp <= 227 * 1024 - 1024 ? 1 : 0;
-}
-
 int launch_binning(int P, int W, int H, char* geom, const GeomLayout& gl, char* img, const ImgLayout& il,
                    char* bin, const BinLayout& bl, int num_sms, cudaStream_t stream, stage_mark_fn mark) {
     const int gx = (W + R3DG_TILE - 1) / R3DG_TILE, gy = (H + R3DG_TILE - 1) / R3DG_TILE;
     const int T = gx * gy;
-    if (gx > 65535 || gy > 65535) return R3DG_ERR_UNSUPPORTED;
-    const int nwb = bin_warps_per_block(T);
-    if (nwb == 0) return R3DG_ERR_UNSUPPORTED;             // > ~58k tiles: per-warp table exceeds shared memory
+    const int CH = bin_chunk_len(P, (size_t)T);
+    const int chunks = (P + CH - 1) / CH;
+    // shared memory of bin_scatter: the per-tile array + as large a staging area as fits (>= CH entries,
+    // since one tile can receive every Gaussian of the chunk)
+    const size_t smem_max = 220 * 1024;                   // + ~5 KB static
+    const size_t tbl_bytes = (((size_t)T + 3) & ~(size_t)3) * 4 +
+                             (size_t)(BIN_SCATTER_THREADS / 32) * 2 * ((CH + 31) / 32) * 4;      // per-tile array + per-warp bitmaps
+    if (gx > 65535 || gy > 65535 || T > 65535 || tbl_bytes + (size_t)CH * 8 > smem_max) return R3DG_ERR_UNSUPPORTED;
+    int cap = (int)std::min<size_t>(std::min<size_t>((smem_max - tbl_bytes) / 8, (size_t)CH * 12), (size_t)BIN_MAX_LONG * BIN_LONG_RUN);
+    if (const char* e = getenv("R3DG_BIN_STAGE_CAP")) cap = std::max(CH, std::min(cap, atoi(e)));   // tests: force the multi-window path
     GeomHeader* header = (GeomHeader*)(geom + gl.header);
     const SortLayout sl(P);
     char* sbuf = geom + gl.sort;
     int rc = launch_sort(header, sbuf, sl, P, num_sms, stream);
     if (rc != 0) return rc;
     mark(2, stream);
-    const int CH = bin_chunk_len(P, (size_t)T);
-    const int chunks = (P + CH - 1) / CH;
-    const size_t smem = (size_t)nwb * ((size_t)T * 4 + sizeof(BatchStage));
+    const size_t smem_count = (size_t)T * 4;
+    const size_t smem_scatter = tbl_bytes + (size_t)cap * 8;
     static size_t attr_smem[2] = {0, 0};
-    if (smem > attr_smem[0]) {
-        R3DG_CUDA_TRY(cudaFuncSetAttribute(bin_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        R3DG_CUDA_TRY(cudaFuncSetAttribute(bin_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem[0] = smem;
+    if (smem_count > attr_smem[0]) {
+        R3DG_CUDA_TRY(cudaFuncSetAttribute(bin_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
+        attr_smem[0] = smem_count;
+    }
+    if (smem_scatter > attr_smem[1]) {
+        R3DG_CUDA_TRY(cudaFuncSetAttribute(bin_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
+        attr_smem[1] = smem_scatter;
     }
     const uint32_t* va = (const uint32_t*)(sbuf + sl.vals_a);
     const uint32_t* vb = (const uint32_t*)(sbuf + sl.vals_b);
     const uint2* rects = (const uint2*)(geom + gl.rects);
     uint32_t* M = (uint32_t*)(img + il.bin_matrix);
     uint2* ranges = (uint2*)(img + il.ranges);
-    uint32_t* tile_total = (uint32_t*)(img + il.tile_total);
+    uint32_t* slab_sum = (uint32_t*)(img + il.slab_sum);
     uint32_t* point_list = (uint32_t*)(bin + bl.point_list);
-    const int grid = (chunks + nwb - 1) / nwb;
-    bin_pass_kernel<false><<<grid, nwb * 32, smem, stream>>>(P, T, gx, CH, chunks, header, va, vb, rects, M, ranges, point_list, bl.capacity);
+    const int slabs = (chunks + BIN_SLAB - 1) / BIN_SLAB;
+    const dim3 sgrid((T + 31) / 32, slabs), sblock(32, 32);
+    bin_count_kernel<<<chunks, 256, smem_count, stream>>>(P, T, gx, CH, header, va, vb, rects, M);
     mark(3, stream);
-    bin_scan_kernel<<<(T + 31) / 32, dim3(32, 32), 0, stream>>>(T, chunks, M, tile_total);
-    bin_tile_start_kernel<<<1, 1024, 0, stream>>>(T, tile_total, ranges, header, bl.capacity);
+    bin_colsum_kernel<<<sgrid, sblock, 0, stream>>>(T, chunks, M, slab_sum);
+    bin_starts_kernel<<<1, 1024, 0, stream>>>(T, slabs, slab_sum, ranges, header, bl.capacity);
+    bin_apply_kernel<<<sgrid, sblock, 0, stream>>>(T, chunks, M, slab_sum);
     mark(4, stream);
-    bin_pass_kernel<true><<<grid, nwb * 32, smem, stream>>>(P, T, gx, CH, chunks, header, va, vb, rects, M, ranges, point_list, bl.capacity);
+    bin_scatter_kernel<<<chunks, BIN_SCATTER_THREADS, smem_scatter, stream>>>(P, T, gx, CH, cap, header, va, vb, rects, M,
+                                                                               point_list, bl.capacity);
     R3DG_CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -50,9 +50,10 @@ inline __host__ __device__ size_t align_up(size_t x, size_t a) { return (x + a -
 
 struct SortLayout {
     size_t keys_a, keys_b, vals_a, vals_b, hist, lookback, total;
-    long long n, tiles;
+    long long n, tiles, plane_words;
     __host__ __device__ SortLayout(long long n_) : n(n_) {
         tiles = (n_ + R3DG_SORT_TILE - 1) / R3DG_SORT_TILE + 1;
+        plane_words = (tiles + tiles / 32 + 2) * 256;      // tile-level + group-level descriptors
         size_t off = 0;
         keys_a = off; off = align_up(off + (size_t)n_ * 4, 256);
         keys_b = off; off = align_up(off + (size_t)n_ * 4, 256);
@@ -60,7 +61,7 @@ struct SortLayout {
         vals_b = off; off = align_up(off + (size_t)n_ * 4, 256);
         hist = off;   off = align_up(off + (size_t)R3DG_SORT_MAX_PASSES * 256 * 4, 256);
         lookback = off;                                   // two descriptor planes, used alternately
-        off = align_up(off + (size_t)2 * tiles * 256 * 4, 256);
+        off = align_up(off + (size_t)2 * plane_words * 4, 256);
         total = off;
     }
 };
@@ -97,20 +98,23 @@ struct GeomLayout {
 // The depth-sorted Gaussians are cut into `chunks` runs of CH; M[chunk][tile] first counts the
 // instances a chunk adds to a tile, then (scanned down the columns) is the chunk's first slot
 // inside the tile's list.
-#define R3DG_BIN_MAX_CHUNKS 2048
+#define R3DG_BIN_MAX_CHUNKS 1024
 __host__ __device__ inline int bin_max_chunks(size_t T) {
     size_t c = ((size_t)1 << 26) / (T ? T : 1);
     return (int)(c < 296 ? 296 : (c > R3DG_BIN_MAX_CHUNKS ? R3DG_BIN_MAX_CHUNKS : c));
 }
-__host__ __device__ inline int bin_chunk_len(int P, size_t T) {     // Gaussians per chunk, multiple of 32
+__host__ __device__ inline int bin_chunk_len(int P, size_t T) {     // Gaussians per chunk, multiple of 256
+    // ~3 chunks per SM for load balance, 512..2048 Gaussians (longer per-tile runs coalesce better,
+    // the staging area of bin_scatter bounds it), and never more chunks than M has rows
+    int ch = ((P + 443) / 444 + 255) / 256 * 256;
+    ch = ch < 512 ? 512 : (ch > 2048 ? 2048 : ch);
     const int mc = bin_max_chunks(T);
-    int ch = (P + mc - 1) / mc;
-    ch = (ch + 31) / 32 * 32;
-    return ch < 32 ? 32 : ch;
+    const int need = ((P + mc - 1) / mc + 255) / 256 * 256;
+    return ch > need ? ch : need;
 }
 
 struct ImgLayout {
-    size_t final_T, n_contrib, ranges, tile_order, tile_total, bin_matrix, total;
+    size_t final_T, n_contrib, ranges, tile_order, slab_sum, bin_matrix, total;
     __host__ __device__ ImgLayout(int W, int H) {
         size_t HW = (size_t)W * H;
         size_t T = (size_t)((W + R3DG_TILE - 1) / R3DG_TILE) * ((H + R3DG_TILE - 1) / R3DG_TILE);
@@ -119,7 +123,7 @@ struct ImgLayout {
         n_contrib = off; off = align_up(off + HW * 4, 256);
         ranges = off;    off = align_up(off + T * 8, 256);
         tile_order = off; off = align_up(off + T * 4, 256);      // tiles by descending list length
-        tile_total = off; off = align_up(off + T * 4, 256);
+        slab_sum = off;  off = align_up(off + T * 4 * ((R3DG_BIN_MAX_CHUNKS + 511) / 512), 256);   // per 512-chunk slab
         bin_matrix = off; off = align_up(off + (size_t)bin_max_chunks(T) * T * 4, 256);
         total = off;
     }

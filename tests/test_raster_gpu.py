@@ -97,6 +97,20 @@ def test_matches_reference_cuda_golden(C, path):
         assert max_rel_above_floor(npy(o["grads"][n]), g["grad_" + n], floor=1e-3) < 1e-2, n
 
 
+def test_binning_multi_window_path(C, monkeypatch):
+    """bin_scatter stages a chunk's instances in shared memory; a chunk that does not fit is handled in
+    several windows of tiles.  Force a tiny staging area and require the same bit-exact lists."""
+    g = np.load(RASTER_CASES[0])
+    kw, (P, W, H, S, R) = golden_kwargs(g)
+    monkeypatch.setenv("R3DG_BIN_STAGE_CAP", "1")          # clamped up to the chunk length by the library
+    o = run_ours(C, **kw)
+    assert o["num_rendered"] == R
+    assert np.array_equal(npy(o["mid"]("point_list")), g["mid_point_list"])
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    assert np.array_equal(npy(o["mid"]("ranges")), g["mid_ranges"][:T])
+    assert np.array_equal(npy(o["n_contrib"]).reshape(-1), g["mid_n_contrib"])
+
+
 @pytest.mark.parametrize("S,pseudo", [(0, False), (5, True), (16, True)])
 def test_matches_cpu_oracle_midsize(C, S, pseudo):
     from oracle import oracle
