@@ -201,34 +201,55 @@ def bench_ours(args, cfg, rank, local, world):
     params = [t.clone().requires_grad_(True) for t in (means3D, opac, shs, scales, rots, feats)]
     pinned_gt = [g.pin_memory() for g in gts]
     pinned_cam = [torch.cat([c.viewmatrix.reshape(-1), c.projmatrix.reshape(-1), c.campos]).pin_memory() for c in cams]
-    gt_dev = torch.empty(3, H, W, device=dev)
-    cam_dev = torch.empty(35, device=dev)
-    loss_host = torch.zeros(1).pin_memory()
-    h2d = gt_dev.numel() * 4 + cam_dev.numel() * 4
+    # double-buffered device inputs: the H2D copy of step i+1 is issued on a copy stream while step i
+    # computes (every step still copies its own inputs from pinned host memory inside the timed region)
+    gt_dev = [torch.empty(3, H, W, device=dev) for _ in range(2)]
+    cam_dev = [torch.empty(35, device=dev) for _ in range(2)]
+    loss_host = torch.zeros(64).pin_memory()
+    h2d = gt_dev[0].numel() * 4 + cam_dev[0].numel() * 4
     d2h = 4
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready_ev = [torch.cuda.Event() for _ in range(2)]
+    free_ev = [torch.cuda.Event() for _ in range(2)]
+    pre = {"issued": None}
+
+    def issue_copy(i):
+        slot = i % 2
+        v = rdist.view_for_rank(i, rank, world, cfg["views"])
+        copy_stream.wait_event(free_ev[slot])              # the step that last read this slot has finished
+        with torch.cuda.stream(copy_stream):
+            gt_dev[slot].copy_(pinned_gt[v], non_blocking=True)
+            cam_dev[slot].copy_(pinned_cam[v], non_blocking=True)
+            ready_ev[slot].record(copy_stream)
+        pre["issued"] = i
 
     def step_e2e(i):
-        v = rdist.view_for_rank(i, rank, world, cfg["views"])
-        c = cams[v]
-        gt_dev.copy_(pinned_gt[v], non_blocking=True)
-        cam_dev.copy_(pinned_cam[v], non_blocking=True)
+        if pre["issued"] != i:                             # very first call only
+            issue_copy(i)
+        slot = i % 2
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(ready_ev[slot])
+        c = cams[rdist.view_for_rank(i, rank, world, cfg["views"])]
+        cd, gd = cam_dev[slot], gt_dev[slot]
         rs = GaussianRasterizationSettings(H, W, c.tanfovx, c.tanfovy, c.cx, c.cy, bg, 1.0,
-                                           cam_dev[:16].view(4, 4), cam_dev[16:32].view(4, 4), 3, cam_dev[32:35],
+                                           cd[:16].view(4, 4), cd[16:32].view(4, 4), 3, cd[32:35],
                                            False, True, True, False)
         p_means, p_opac, p_shs, p_scales, p_rots, p_feats = params
         means2D = torch.zeros_like(p_means, requires_grad=True)
         out = GaussianRasterizer(rs)(means3D=p_means, means2D=means2D, opacities=p_opac, shs=p_shs,
                                      scales=p_scales, rotations=p_rots, features=p_feats)
+        issue_copy(i + 1)                                  # next step's inputs travel while this step computes
         color, opacity, depth, feature = out[2], out[3], out[4], out[5]
-        loss = (color - gt_dev).abs().mean() + 0.01 * opacity.mean() + 0.01 * depth.mean() + 0.01 * feature.square().mean()
+        loss = (color - gd).abs().mean() + 0.01 * opacity.mean() + 0.01 * depth.mean() + 0.01 * feature.square().mean()
         for p_ in params:
             p_.grad = None
         loss.backward()
+        free_ev[slot].record(cur)
         if world > 1:
             flat = torch.cat([p_.grad.reshape(-1) for p_ in params])
             flat.mul_(1.0 / world)
             tdist.all_reduce(flat)
-        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        loss_host[i % 64:i % 64 + 1].copy_(loss.detach().reshape(1), non_blocking=True)
 
     e_steps = max(3, args.steps // 2)
     set_deferred_count(True)          # documented opt-in of the public API: no host round trip mid-step
@@ -258,7 +279,7 @@ def bench_ours(args, cfg, rank, local, world):
                        "l2": "inputs larger than L2 (236 MB Gaussian parameters + ~190 MB binning per step vs 126 MB L2)"},
             "e2e": {"value": e2e_value, "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e_steps, "ms_per_step": ms_e / e_steps,
-                    "what": "GaussianRasterizer module (set_deferred_count(True)) + autograd + L1 loss; per step H2D of ground-truth image + camera from pinned memory, D2H of the loss"},
+                    "what": "GaussianRasterizer module (set_deferred_count(True)) + autograd + L1 loss; per step H2D of ground-truth image + camera from pinned memory (double-buffered, copy stream overlapping the previous step), D2H of the loss"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "stage_ms": stage,

@@ -3,6 +3,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #define R3DG_TILE 16                 // 16x16 pixel tiles (reference config.h:15-17, fixed by parity)
@@ -76,10 +77,21 @@ __device__ __forceinline__ void sort_plan(uint32_t diff, int& passes, int& w) {
     w = passes ? (nb + passes - 1) / passes : 0;
 }
 
+// Tuning knob (tools/pad_sweep.py): extra bytes in front of the gradient rows, read from the
+// environment on the host.  Used to probe address-mapping effects between rec[] and grad[].
+inline __host__ size_t geom_grad_pad() {
+#ifndef __CUDA_ARCH__
+    const char* e = getenv("R3DG_PAD_GRAD");
+    return e ? align_up((size_t)atoll(e), 256) : 0;
+#else
+    return 0;
+#endif
+}
+
 struct GeomLayout {
     size_t header, rec, tiles_touched, rects, clamped, scan_state, sort, grad, total;
     int P, S, recf;
-    __host__ __device__ GeomLayout(int P_, int S_) : P(P_), S(S_) {
+    __host__ GeomLayout(int P_, int S_) : P(P_), S(S_) {
         recf = rec_floats(S_);
         size_t off = 0;
         header = off;        off = align_up(off + sizeof(GeomHeader), 256);
@@ -89,6 +101,7 @@ struct GeomLayout {
         clamped = off;       off = align_up(off + (size_t)P_, 256);
         scan_state = off;    off = align_up(off + ((size_t)P_ / R3DG_SCAN_ITEMS + 2) * 4, 256);
         sort = off;          off = align_up(off + SortLayout(P_).total, 256);   // depth sort of the Gaussians
+        off += geom_grad_pad();
         grad = off;          off = align_up(off + (size_t)P_ * recf * 4, 256);   // backward scratch
         total = off;
     }

@@ -39,7 +39,9 @@ struct CompositeFwdParams {
 // NW = warps per CTA: 8 (one CTA per tile) or 4 (two CTAs per tile).  Warps are autonomous: no
 // CTA-wide barrier anywhere; the CTA only exists so that the warps of a tile share L1 lines.
 template <int NG, int NW>
-__global__ void __launch_bounds__(32 * NW) composite_fwd_kernel(const CompositeFwdParams p) {
+// occupancy pin for the headline shape (S <= 5 channels): keeps the register allocation at the
+// count that fits one more CTA per SM (ptxas otherwise drifts a few registers above it)
+__global__ void __launch_bounds__(32 * NW, (NG == 2 && NW == 4) ? 9 : 1) composite_fwd_kernel(const CompositeFwdParams p) {
     constexpr int RG = 2 + NG;                       // float4 groups per record
     __shared__ float4 sRec[NW][RG][32];              // this warp's current 32-entry chunk, SoA
     __shared__ int sId[NW][32];

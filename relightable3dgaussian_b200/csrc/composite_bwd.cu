@@ -55,7 +55,9 @@ __device__ __forceinline__ float reduce_scatter(float (&v)[N], int lane) {
 }
 
 template <int NG, int NW>
-__global__ void __launch_bounds__(32 * NW) composite_bwd_kernel(const CompositeBwdParams p) {
+// occupancy pin for the headline shape (S <= 5 channels): keeps the register allocation at the
+// count that fits one more CTA per SM (ptxas otherwise drifts a few registers above it)
+__global__ void __launch_bounds__(32 * NW, (NG == 2 && NW == 4) ? 5 : 1) composite_bwd_kernel(const CompositeBwdParams p) {
     constexpr int NC = 4 * NG;              // padded channel count {r,g,b,f...}
     constexpr int V = 8 + NC;               // gradient row width
     constexpr int V0 = V <= 16 ? 16 : 32;   // first butterfly chunk
