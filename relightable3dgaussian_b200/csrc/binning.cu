@@ -43,9 +43,16 @@ __global__ void __launch_bounds__(256) bin_count_kernel(int P, int T, int gx, in
     for (int j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
         const uint2 r = rects[order[j]];
         const uint32_t w = r.y & 0xffffu, h = r.y >> 16;
-        uint32_t tile_row = (r.x >> 16) * (uint32_t)gx + (r.x & 0xffffu);
-        for (uint32_t y = 0; y < h; ++y, tile_row += (uint32_t)gx)
-            for (uint32_t x = 0; x < w; ++x) atomicAdd(&tbl[tile_row + x], 1u);
+        // one flat loop over the w*h tiles (lanes have different rectangles: nested loops would
+        // serialise max(h) * max(w) trips per warp instead of max(w*h))
+        uint32_t tile = (r.x >> 16) * (uint32_t)gx + (r.x & 0xffffu), x = 0;
+        const uint32_t n = w * h, skip = (uint32_t)gx - w;
+#pragma unroll 1
+        for (uint32_t k = 0; k < n; ++k) {
+            atomicAdd(&tbl[tile], 1u);
+            ++tile;
+            if (++x == w) { x = 0; tile += skip; }
+        }
     }
     __syncthreads();
     uint32_t* row = M + (size_t)c * T;
@@ -91,9 +98,16 @@ __global__ void __launch_bounds__(BIN_SCATTER_THREADS) bin_scatter_kernel(
     for (int j = j0 + tid; j < j1; j += BIN_SCATTER_THREADS) {
         const uint2 r = rects[order[j]];
         const uint32_t w = r.y & 0xffffu, h = r.y >> 16;
-        uint32_t tile_row = (r.x >> 16) * (uint32_t)gx + (r.x & 0xffffu);
-        for (uint32_t y = 0; y < h; ++y, tile_row += (uint32_t)gx)
-            for (uint32_t x = 0; x < w; ++x) atomicAdd(&a[tile_row + x], 1u);
+        // one flat loop over the w*h tiles (lanes have different rectangles: nested loops would
+        // serialise max(h) * max(w) trips per warp instead of max(w*h))
+        uint32_t tile = (r.x >> 16) * (uint32_t)gx + (r.x & 0xffffu), x = 0;
+        const uint32_t n = w * h, skip = (uint32_t)gx - w;
+#pragma unroll 1
+        for (uint32_t k = 0; k < n; ++k) {
+            atomicAdd(&a[tile], 1u);
+            ++tile;
+            if (++x == w) { x = 0; tile += skip; }
+        }
     }
     __syncthreads();
     const int per = (T + BIN_SCATTER_THREADS - 1) / BIN_SCATTER_THREADS;
@@ -144,16 +158,18 @@ __global__ void __launch_bounds__(BIN_SCATTER_THREADS) bin_scatter_kernel(
             const uint32_t g = order[j];
             const uint2 r = rects[g];
             const uint32_t w = r.y & 0xffffu, h = r.y >> 16;
-            uint32_t tile_row = (r.x >> 16) * (uint32_t)gx + (r.x & 0xffffu);
+            uint32_t tile = (r.x >> 16) * (uint32_t)gx + (r.x & 0xffffu), x = 0;
+            const uint32_t n = w * h, skip = (uint32_t)gx - w;
             const uint32_t seq = (uint32_t)(j - j0);
-            for (uint32_t y = 0; y < h; ++y, tile_row += (uint32_t)gx)
-                for (uint32_t x = 0; x < w; ++x) {
-                    const uint32_t tile = tile_row + x;
-                    if ((int)tile >= lo && (int)tile < hi) {
-                        const uint32_t slot = atomicAdd(&a[tile], 1u) - first;
-                        stage[slot] = make_uint2(g, (tile << 16) | seq);
-                    }
+#pragma unroll 1
+            for (uint32_t k = 0; k < n; ++k) {
+                if ((int)tile >= lo && (int)tile < hi) {
+                    const uint32_t slot = atomicAdd(&a[tile], 1u) - first;
+                    stage[slot] = make_uint2(g, (tile << 16) | seq);
                 }
+                ++tile;
+                if (++x == w) { x = 0; tile += skip; }
+            }
         }
         __syncthreads();
         // now a[t] = first slot of tile t+1 for t in [lo, hi)
@@ -173,6 +189,7 @@ __global__ void __launch_bounds__(BIN_SCATTER_THREADS) bin_scatter_kernel(
             const uint32_t rb = (t > lo ? a[t - 1] : first) - first, re = a[t] - first;
             if (re - rb > BIN_LONG_RUN) continue;
             uint32_t rank = 0;
+#pragma unroll 2
             for (uint32_t k = rb; k < re; ++k) rank += ((stage[k].y & 0xffffu) < seq) ? 1u : 0u;
             const long long pos = (long long)row[t] + rank;
             if (pos < capacity) point_list[pos] = e.x;
@@ -187,9 +204,11 @@ __global__ void __launch_bounds__(BIN_SCATTER_THREADS) bin_scatter_kernel(
                 const uint32_t rb = (t > lo ? a[t - 1] : first) - first, re = a[t] - first;
                 for (int k = lane; k < words; k += 32) bm[k] = 0u;
                 __syncwarp();
+#pragma unroll 1
                 for (uint32_t k = rb + lane; k < re; k += 32) { const uint32_t sq = stage[k].y & 0xffffu; atomicOr(&bm[sq >> 5], 1u << (sq & 31u)); }
                 __syncwarp();
                 uint32_t carry = 0;
+#pragma unroll 1
                 for (int k0 = 0; k0 < words; k0 += 32) {
                     const uint32_t c = (k0 + lane < words) ? (uint32_t)__popc(bm[k0 + lane]) : 0u;
                     uint32_t inc = c;
@@ -200,6 +219,7 @@ __global__ void __launch_bounds__(BIN_SCATTER_THREADS) bin_scatter_kernel(
                 }
                 __syncwarp();
                 const uint32_t base = row[t];
+#pragma unroll 1
                 for (uint32_t k = rb + lane; k < re; k += 32) {
                     const uint2 e = stage[k];
                     const uint32_t sq = e.y & 0xffffu;

@@ -13,6 +13,7 @@
 //    float[24] arrays in local memory and 36 KB of shared memory per CTA;
 //  * gradients differ from the reference only by fp32 summation order (the reference's own
 //    atomics make it run-to-run nondeterministic), tolerance 1e-3 relative.
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -56,7 +57,8 @@ __device__ __forceinline__ float reduce_scatter(float (&v)[N], int lane) {
 
 template <int NG, int NW>
 // occupancy pin for the headline shape (S <= 5 channels): keeps the register allocation at the
-// count that fits one more CTA per SM (ptxas otherwise drifts a few registers above it)
+// count that fits one more CTA per SM (ptxas otherwise drifts a few registers above it; 6 CTAs
+// = 80 registers spills and measured 9% slower)
 __global__ void __launch_bounds__(32 * NW, (NG == 2 && NW == 4) ? 5 : 1) composite_bwd_kernel(const CompositeBwdParams p) {
     constexpr int NC = 4 * NG;              // padded channel count {r,g,b,f...}
     constexpr int V = 8 + NC;               // gradient row width
