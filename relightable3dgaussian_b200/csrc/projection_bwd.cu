@@ -50,7 +50,7 @@ __device__ __forceinline__ void cov3d_plain(const float* s3, float mod, const fl
 
 #define PROJ_THREADS 128
 #define SLAB_LD (PROJ_THREADS + 1)
-__global__ void __launch_bounds__(PROJ_THREADS) projection_bwd_kernel(const ProjBwdParams p) {
+__global__ void __launch_bounds__(PROJ_THREADS, 5) projection_bwd_kernel(const ProjBwdParams p) {
     // SH rows (192 B at M=16) travel through a transposed shared slab s[k * SLAB_LD + t]: the
     // block reads its [128][3M] slab of shs with coalesced 16B vectors, every thread turns its
     // column into dL/dsh in place, and the slab is written back coalesced (zeros for culled rows).
@@ -64,6 +64,22 @@ __global__ void __launch_bounds__(PROJ_THREADS) projection_bwd_kernel(const Proj
     const int idx = in_range ? idx_raw : p.P - 1;      // clamp: out-of-range threads only help with the slab
     const int rowf = 3 * p.M, block_base = blockIdx.x * PROJ_THREADS;
     const int nvalid = min(PROJ_THREADS, p.P - block_base);
+    // the thread's own rows are requested before the cooperative slab load so that both are in flight
+    // together (nothing can be hoisted across the barrier below by the compiler)
+    const float4* g4 = reinterpret_cast<const float4*>(p.grad + (size_t)idx * p.recf);
+    const bool visible = in_range && p.radii_rec[idx] > 0;
+    float4 gA = make_float4(0, 0, 0, 0), gB = gA, gC = gA, q4 = gA;
+    float m3[3] = {0, 0, 0}, s3[3] = {0, 0, 0};
+    unsigned cl = 0;
+    if (visible) {
+        gA = g4[0]; gB = g4[1]; gC = g4[2];
+        m3[0] = p.means3D[3 * (size_t)idx]; m3[1] = p.means3D[3 * (size_t)idx + 1]; m3[2] = p.means3D[3 * (size_t)idx + 2];
+        if (!p.cov3D_precomp) {
+            q4 = *reinterpret_cast<const float4*>(p.rotations + 4 * (size_t)idx);
+            s3[0] = p.scales[3 * (size_t)idx]; s3[1] = p.scales[3 * (size_t)idx + 1]; s3[2] = p.scales[3 * (size_t)idx + 2];
+        }
+        if (p.shs) cl = p.clamped[idx];
+    }
     if (p.shs) {
         const int total = nvalid * rowf;
         const float* src = p.shs + (size_t)block_base * rowf;
@@ -85,16 +101,10 @@ __global__ void __launch_bounds__(PROJ_THREADS) projection_bwd_kernel(const Proj
     }
     const float* V = sV;
     const float* proj = sPr;
-    const float4* rec4 = reinterpret_cast<const float4*>(p.rec + (size_t)idx * p.recf);
-    const float4* g4 = reinterpret_cast<const float4*>(p.grad + (size_t)idx * p.recf);
-    // radius lives in the record only for Gaussians that passed every cull; read it from there
-    // is unsafe for culled ones (row never written) -> visibility comes from tiles/radii arrays.
-    const bool visible = in_range && p.radii_rec[idx] > 0;
+    // (visibility comes from tiles_touched: the record row of a culled Gaussian is never written)
 
     float dmean2[3] = {0, 0, 0}, dcol[3] = {0, 0, 0}, dop = 0, dmean3[3] = {0, 0, 0};
     float dcov[6] = {0, 0, 0, 0, 0, 0}, dscale[3] = {0, 0, 0}, drot[4] = {0, 0, 0, 0};
-    float4 gA = make_float4(0, 0, 0, 0), gB = gA;
-    if (visible) { gA = g4[0]; gB = g4[1]; }
 
     // feature gradients: straight copy-out of the packed row
     if (p.S > 0 && in_range) {
@@ -103,9 +113,8 @@ __global__ void __launch_bounds__(PROJ_THREADS) projection_bwd_kernel(const Proj
     }
     if (visible) {
         dmean2[0] = gA.x; dmean2[1] = gA.y; dmean2[2] = gA.z; dop = gA.w;
-        const float4 gC = g4[2];
         dcol[0] = gC.x; dcol[1] = gC.y; dcol[2] = gC.z;
-        const float mx = p.means3D[3 * (size_t)idx], my = p.means3D[3 * (size_t)idx + 1], mz = p.means3D[3 * (size_t)idx + 2];
+        const float mx = m3[0], my = m3[1], mz = m3[2];
         const float dcx = gB.x, dcy = gB.y, dcz = gB.z;      // dL/d conic a,b,c
         float c6[6], R[3][3], s[3];
         const bool have_sr = p.scales != nullptr;
@@ -113,8 +122,7 @@ __global__ void __launch_bounds__(PROJ_THREADS) projection_bwd_kernel(const Proj
 #pragma unroll
             for (int i = 0; i < 6; ++i) c6[i] = p.cov3D_precomp[6 * (size_t)idx + i];
         } else {
-            const float q[4] = {p.rotations[4 * (size_t)idx], p.rotations[4 * (size_t)idx + 1], p.rotations[4 * (size_t)idx + 2], p.rotations[4 * (size_t)idx + 3]};
-            const float s3[3] = {p.scales[3 * (size_t)idx], p.scales[3 * (size_t)idx + 1], p.scales[3 * (size_t)idx + 2]};
+            const float q[4] = {q4.x, q4.y, q4.z, q4.w};
             cov3d_plain(s3, p.scale_modifier, q, c6, R, s);
         }
         // ---- computeCov2DCUDA (backward.cu:144-276) -------------------------------------------
@@ -198,7 +206,6 @@ __global__ void __launch_bounds__(PROJ_THREADS) projection_bwd_kernel(const Proj
             const float len = sqrtf(dox * dox + doy * doy + doz * doz);
             const float x = dox / len, y = doy / len, z = doz / len;
             float* slab = sSH + threadIdx.x;                 // element (k, c) at slab[(3k + c) * SLAB_LD]
-            const unsigned cl = p.clamped[idx];
             const float dRGB[3] = {(cl & 1u) ? 0.f : dcol[0], (cl & 2u) ? 0.f : dcol[1], (cl & 4u) ? 0.f : dcol[2]};
             float w[16], wx[16], wy[16], wz[16];   // basis and its derivatives w.r.t. x,y,z
 #pragma unroll
