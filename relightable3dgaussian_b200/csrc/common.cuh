@@ -166,6 +166,29 @@ inline __host__ uint32_t higher_msb(uint32_t n) {
 
 // Relaxed GPU-scope accesses for the look-back descriptors (flag and value share one word, so no
 // further ordering is needed); `volatile` asm so that polling loops really re-load.
+// ---- asynchronous global -> shared copies (LDGSTS): no register staging, overlap with math -----
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// Asynchronous, coalesced copy of a CTA's [nvalid][rowf] float slab into the TRANSPOSED shared slab
+// s[k * ld + t] (element k of row t): every warp instruction moves 32 consecutive floats (128 B of
+// global memory) to 32 different banks.  nthreads = blockDim.x.
+__device__ __forceinline__ void load_rows_transposed_async(float* s, int ld, const float* __restrict__ src,
+                                                           int nvalid, int rowf, int nthreads) {
+    const int total = nvalid * rowf;
+    const int dq = nthreads / rowf, dm = nthreads - dq * rowf;
+    int t = (int)threadIdx.x / rowf, k = (int)threadIdx.x - t * rowf;
+    for (int i = threadIdx.x; i < total; i += nthreads) {
+        cp_async4(s + k * ld + t, src + i);
+        k += dm; t += dq;
+        if (k >= rowf) { k -= rowf; ++t; }
+    }
+}
+
 __device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

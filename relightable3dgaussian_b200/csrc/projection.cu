@@ -165,6 +165,20 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjParams 
             alive = false;
         }
     }
+    // SH rows ([M][3] floats, 192 B at M=16 = 3/4 of the kernel's input bytes) are staged through a
+    // transposed shared slab.  The copy is asynchronous (LDGSTS) and is issued as soon as the depth
+    // cull is known, so that it overlaps the covariance / projection math below; blocks whose
+    // Gaussians are all behind the camera skip it.
+    bool slab_loaded = false;
+    if (p.colors_precomp == nullptr) {
+        slab_loaded = __syncthreads_or(alive) != 0;
+        if (slab_loaded) {
+            const int rowf = 3 * p.M, block_base = blockIdx.x * PROJ_THREADS;
+            load_rows_transposed_async(sSH, PROJ_THREADS + 1, p.shs + (size_t)block_base * rowf,
+                                       min(PROJ_THREADS, p.P - block_base), rowf, PROJ_THREADS);
+            cp_async_commit();
+        }
+    }
     float pix_x = 0.f, pix_y = 0.f, con_a = 0.f, con_b = 0.f, con_c = 0.f;
     int my_radius = 0, x0 = 0, y0 = 0, x1 = 0, y1 = 0;
     if (alive) {
@@ -225,11 +239,8 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjParams 
     }
     float rgb[3] = {0.f, 0.f, 0.f};
     if (p.colors_precomp == nullptr) {
-        // SH rows ([M][3] floats, 192 B at M=16) are staged through a transposed shared slab so the
-        // global reads are fully coalesced 16B vectors instead of 48 strided scalar loads per thread.
-        if (__syncthreads_or(alive)) {
-            const int rowf = 3 * p.M, block_base = blockIdx.x * PROJ_THREADS;
-            load_rows_transposed(sSH, p.shs + (size_t)block_base * rowf, min(PROJ_THREADS, p.P - block_base), rowf);
+        if (slab_loaded) {
+            cp_async_wait_all();
             __syncthreads();
             if (alive) {
                 unsigned cl = 0;

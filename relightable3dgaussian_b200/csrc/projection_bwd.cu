@@ -80,24 +80,9 @@ __global__ void __launch_bounds__(PROJ_THREADS, 5) projection_bwd_kernel(const P
         }
         if (p.shs) cl = p.clamped[idx];
     }
-    if (p.shs) {
-        const int total = nvalid * rowf;
-        const float* src = p.shs + (size_t)block_base * rowf;
-        if ((rowf & 3) == 0) {
-            const float4* src4 = reinterpret_cast<const float4*>(src);
-            for (int i4 = threadIdx.x; i4 < total / 4; i4 += PROJ_THREADS) {
-                const float4 v = src4[i4];
-                const int i = 4 * i4, t = i / rowf, k = i - t * rowf;
-                sSH[(k + 0) * SLAB_LD + t] = v.x; sSH[(k + 1) * SLAB_LD + t] = v.y;
-                sSH[(k + 2) * SLAB_LD + t] = v.z; sSH[(k + 3) * SLAB_LD + t] = v.w;
-            }
-        } else {
-            for (int i = threadIdx.x; i < total; i += PROJ_THREADS) {
-                const int t = i / rowf, k = i - t * rowf;
-                sSH[k * SLAB_LD + t] = src[i];
-            }
-        }
-        __syncthreads();
+    if (p.shs) {     // asynchronous (LDGSTS) transposed copy, overlapped with the covariance chain below
+        load_rows_transposed_async(sSH, SLAB_LD, p.shs + (size_t)block_base * rowf, nvalid, rowf, PROJ_THREADS);
+        cp_async_commit();
     }
     const float* V = sV;
     const float* proj = sPr;
@@ -200,9 +185,48 @@ __global__ void __launch_bounds__(PROJ_THREADS, 5) projection_bwd_kernel(const P
         dmean3[1] += (proj[4] * m_w - proj[7] * mul1) * dmean2[0] + (proj[5] * m_w - proj[7] * mul2) * dmean2[1];
         dmean3[2] += (proj[8] * m_w - proj[11] * mul1) * dmean2[0] + (proj[9] * m_w - proj[11] * mul2) * dmean2[1];
 
+        // ---- cov3D -> scale / rotation (backward.cu:280-343) ----------------------------------
+        if (have_sr) {
+            const float r = p.rotations[4 * (size_t)idx], x = p.rotations[4 * (size_t)idx + 1],
+                        y = p.rotations[4 * (size_t)idx + 2], z = p.rotations[4 * (size_t)idx + 3];
+            if (p.cov3D_precomp) {   // not reachable through the reference wrapper, kept for safety
+                const float q[4] = {r, x, y, z};
+                const float s3[3] = {p.scales[3 * (size_t)idx], p.scales[3 * (size_t)idx + 1], p.scales[3 * (size_t)idx + 2]};
+                float tmp[6];
+                cov3d_plain(s3, p.scale_modifier, q, tmp, R, s);
+            }
+            float Mm[3][3];
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc)
+#pragma unroll
+                for (int rr = 0; rr < 3; ++rr) Mm[cc][rr] = s[rr] * R[cc][rr];
+            const float dSig[3][3] = {{dcov[0], 0.5f * dcov[1], 0.5f * dcov[2]},
+                                      {0.5f * dcov[1], dcov[3], 0.5f * dcov[4]},
+                                      {0.5f * dcov[2], 0.5f * dcov[4], dcov[5]}};
+            float dMt[3][3];       // dL_dMt[c][r] = dL_dM[r][c], dL_dM = 2 * M * dL_dSigma
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc)
+#pragma unroll
+                for (int rr = 0; rr < 3; ++rr)
+                    dMt[rr][cc] = 2.0f * (Mm[0][rr] * dSig[cc][0] + Mm[1][rr] * dSig[cc][1] + Mm[2][rr] * dSig[cc][2]);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) dscale[k] = R[0][k] * dMt[k][0] + R[1][k] * dMt[k][1] + R[2][k] * dMt[k][2];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int rr = 0; rr < 3; ++rr) dMt[k][rr] *= s[k];
+            drot[0] = 2 * z * (dMt[0][1] - dMt[1][0]) + 2 * y * (dMt[2][0] - dMt[0][2]) + 2 * x * (dMt[1][2] - dMt[2][1]);
+            drot[1] = 2 * y * (dMt[1][0] + dMt[0][1]) + 2 * z * (dMt[2][0] + dMt[0][2]) + 2 * r * (dMt[1][2] - dMt[2][1]) - 4 * x * (dMt[2][2] + dMt[1][1]);
+            drot[2] = 2 * x * (dMt[1][0] + dMt[0][1]) + 2 * r * (dMt[2][0] - dMt[0][2]) + 2 * z * (dMt[1][2] + dMt[2][1]) - 4 * y * (dMt[2][2] + dMt[0][0]);
+            drot[3] = 2 * r * (dMt[0][1] - dMt[1][0]) + 2 * x * (dMt[2][0] + dMt[0][2]) + 2 * y * (dMt[1][2] + dMt[2][1]) - 4 * z * (dMt[1][1] + dMt[0][0]);
+        }
+    }
+    // the SH slab was requested asynchronously at the top; it is first needed here
+    if (p.shs) { cp_async_wait_all(); __syncthreads(); }
+    if (visible) {
         // ---- SH backward (backward.cu:20-139) -------------------------------------------------
         if (p.shs) {
-            const float dox = mx - sCam[0], doy = my - sCam[1], doz = mz - sCam[2];
+            const float dox = m3[0] - sCam[0], doy = m3[1] - sCam[1], doz = m3[2] - sCam[2];
             const float len = sqrtf(dox * dox + doy * doy + doz * doz);
             const float x = dox / len, y = doy / len, z = doz / len;
             float* slab = sSH + threadIdx.x;                 // element (k, c) at slab[(3k + c) * SLAB_LD]
@@ -263,41 +287,6 @@ __global__ void __launch_bounds__(PROJ_THREADS, 5) projection_bwd_kernel(const P
             dmean3[0] += ((+sum2 - dox * dox) * ddx - doy * dox * ddy - doz * dox * ddz) * invsum32;
             dmean3[1] += (-dox * doy * ddx + (sum2 - doy * doy) * ddy - doz * doy * ddz) * invsum32;
             dmean3[2] += (-dox * doz * ddx - doy * doz * ddy + (sum2 - doz * doz) * ddz) * invsum32;
-        }
-        // ---- cov3D -> scale / rotation (backward.cu:280-343) ----------------------------------
-        if (have_sr) {
-            const float r = p.rotations[4 * (size_t)idx], x = p.rotations[4 * (size_t)idx + 1],
-                        y = p.rotations[4 * (size_t)idx + 2], z = p.rotations[4 * (size_t)idx + 3];
-            if (p.cov3D_precomp) {   // not reachable through the reference wrapper, kept for safety
-                const float q[4] = {r, x, y, z};
-                const float s3[3] = {p.scales[3 * (size_t)idx], p.scales[3 * (size_t)idx + 1], p.scales[3 * (size_t)idx + 2]};
-                float tmp[6];
-                cov3d_plain(s3, p.scale_modifier, q, tmp, R, s);
-            }
-            float Mm[3][3];
-#pragma unroll
-            for (int cc = 0; cc < 3; ++cc)
-#pragma unroll
-                for (int rr = 0; rr < 3; ++rr) Mm[cc][rr] = s[rr] * R[cc][rr];
-            const float dSig[3][3] = {{dcov[0], 0.5f * dcov[1], 0.5f * dcov[2]},
-                                      {0.5f * dcov[1], dcov[3], 0.5f * dcov[4]},
-                                      {0.5f * dcov[2], 0.5f * dcov[4], dcov[5]}};
-            float dMt[3][3];       // dL_dMt[c][r] = dL_dM[r][c], dL_dM = 2 * M * dL_dSigma
-#pragma unroll
-            for (int cc = 0; cc < 3; ++cc)
-#pragma unroll
-                for (int rr = 0; rr < 3; ++rr)
-                    dMt[rr][cc] = 2.0f * (Mm[0][rr] * dSig[cc][0] + Mm[1][rr] * dSig[cc][1] + Mm[2][rr] * dSig[cc][2]);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) dscale[k] = R[0][k] * dMt[k][0] + R[1][k] * dMt[k][1] + R[2][k] * dMt[k][2];
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-#pragma unroll
-                for (int rr = 0; rr < 3; ++rr) dMt[k][rr] *= s[k];
-            drot[0] = 2 * z * (dMt[0][1] - dMt[1][0]) + 2 * y * (dMt[2][0] - dMt[0][2]) + 2 * x * (dMt[1][2] - dMt[2][1]);
-            drot[1] = 2 * y * (dMt[1][0] + dMt[0][1]) + 2 * z * (dMt[2][0] + dMt[0][2]) + 2 * r * (dMt[1][2] - dMt[2][1]) - 4 * x * (dMt[2][2] + dMt[1][1]);
-            drot[2] = 2 * x * (dMt[1][0] + dMt[0][1]) + 2 * r * (dMt[2][0] - dMt[0][2]) + 2 * z * (dMt[1][2] + dMt[2][1]) - 4 * y * (dMt[2][2] + dMt[0][0]);
-            drot[3] = 2 * r * (dMt[0][1] - dMt[1][0]) + 2 * x * (dMt[2][0] + dMt[0][2]) + 2 * y * (dMt[1][2] + dMt[2][1]) - 4 * z * (dMt[1][1] + dMt[0][0]);
         }
     } else if (p.shs) {
         for (int k = 0; k < rowf; ++k) sSH[k * SLAB_LD + threadIdx.x] = 0.f;
