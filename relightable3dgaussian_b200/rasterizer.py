@@ -78,6 +78,11 @@ class _RasterizeGaussians(torch.autograd.Function):
          radii, geomBuffer, binningBuffer, imgBuffer) = out
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
+        # cotangents of outputs the reference's backward ignores (num_contrib, normal, surface_xyz, weights, radii)
+        # stay None instead of being materialised as zero tensors (5 fill kernels per step); the four image
+        # cotangents are filled in below when a loss does not touch one of them
+        ctx.set_materialize_grads(False)
+        ctx.out_shapes = (color.shape, opacity.shape, depth.shape, feature.shape)
         ctx.save_for_backward(colors_precomp, means3D, features, scales, rotations, cov3Ds_precomp,
                               radii, sh, geomBuffer, binningBuffer, imgBuffer)
         return (num_rendered, num_contrib, color, opacity, depth, feature, normal, surface_xyz,
@@ -89,6 +94,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         rs = ctx.raster_settings
         (colors_precomp, means3D, features, scales, rotations, cov3Ds_precomp, radii, sh,
          geomBuffer, binningBuffer, imgBuffer) = ctx.saved_tensors
+        zeros = lambda g, shape: g if g is not None else torch.zeros(shape, dtype=torch.float32, device=means3D.device)
+        g_color, g_opacity = zeros(g_color, ctx.out_shapes[0]), zeros(g_opacity, ctx.out_shapes[1])
+        g_depth, g_feature = zeros(g_depth, ctx.out_shapes[2]), zeros(g_feature, ctx.out_shapes[3])
         args = (rs.bg, means3D, features, radii, colors_precomp, scales, rotations,
                 rs.scale_modifier, cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx,
                 rs.tanfovy, g_color, g_opacity, g_depth, g_feature, sh, rs.sh_degree, rs.campos,
