@@ -50,18 +50,18 @@ inline __host__ __device__ size_t align_up(size_t x, size_t a) { return (x + a -
 #define R3DG_SORT_MAX_PASSES 4
 
 struct SortLayout {
-    size_t keys_a, keys_b, vals_a, vals_b, hist, lookback, total;
+    size_t keys_a, keys_b, vals_a, vals_b, hist, tilecnt, total;
     long long n, tiles, plane_words;
     __host__ __device__ SortLayout(long long n_) : n(n_) {
         tiles = (n_ + R3DG_SORT_TILE - 1) / R3DG_SORT_TILE + 1;
-        plane_words = (tiles + tiles / 32 + 2) * 256;      // tile-level + group-level descriptors
+        plane_words = tiles * 256;                          // digit counts per tile; two planes, used alternately
         size_t off = 0;
         keys_a = off; off = align_up(off + (size_t)n_ * 4, 256);
         keys_b = off; off = align_up(off + (size_t)n_ * 4, 256);
         vals_a = off; off = align_up(off + (size_t)n_ * 4, 256);
         vals_b = off; off = align_up(off + (size_t)n_ * 4, 256);
         hist = off;   off = align_up(off + (size_t)R3DG_SORT_MAX_PASSES * 256 * 4, 256);
-        lookback = off;                                   // two descriptor planes, used alternately
+        tilecnt = off;
         off = align_up(off + (size_t)2 * plane_words * 4, 256);
         total = off;
     }
