@@ -37,6 +37,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 HEADLINE = dict(P=1_000_000, W=800, H=800, S=5, views=8, recipe="shell-v1", seed=0)
+# DRAM bytes per launch of the compositors at the headline config, from ncu --set full (profiles/)
+NCU_TRAFFIC = {"composite_bwd": 98067712 + 7328000, "composite_fwd": 56485632 + 6283776}
 STAGES = ["project", "depth_sort", "bin_count", "bin_offsets", "bin_scatter", "composite_fwd",
           "surface_normal", "composite_bwd", "project_bwd"]
 
@@ -91,13 +93,15 @@ class ClockSampler:
 
 def alg_bytes(P, Pv, R, HW, T, S):
     """Algorithmic bytes per stage and view (R, Pv measured in this run)."""
+    ch = min(2048, max(512, -(-(-(-P // 444)) // 256) * 256))          # bin_chunk_len (csrc/common.cuh)
+    chunks = -(-P // ch)
     return {
         "project": 236 * P + 48 * Pv,
-        # depth-ordered binning (DESIGN.md): 3 x (read + write) of P (key, id) pairs + histogram read;
-        # two walks over (id, rect) of the sorted Gaussians; the chunk x tile matrix (~P/512 rows)
-        "depth_sort": 52 * P, "bin_count": 12 * P + 4 * T * (P // 512 + 1),
-        "bin_offsets": 16 * T * (P // 512 + 1) + 12 * T,
-        "bin_scatter": 12 * P + 4 * T * (P // 512 + 1) + 4 * R + 12 * T,
+        # depth-ordered binning (DESIGN.md section 4): 3 x (read + write) of P (key, id) pairs + first-pass count
+        # read; walks over (id, rect) of the depth-sorted Gaussians; the chunk x tile matrix M
+        "depth_sort": 52 * P, "bin_count": 12 * P + 4 * T * chunks,
+        "bin_offsets": 12 * T * chunks + 12 * T,
+        "bin_scatter": 24 * P + 4 * T * chunks + 4 * R,
         "composite_fwd": R * (4 + 40 + 4 * S) + HW * 4 * (3 + 1 + 1 + S) + 8 * HW + 4 * P,
         "surface_normal": 44 * HW,
         "composite_bwd": R * (44 + 4 * S) + HW * 4 * (5 + S) + 8 * HW + Pv * 4 * (11 + S),
@@ -246,9 +250,8 @@ def bench_ours(args, cfg, rank, local, world):
         loss.backward()
         free_ev[slot].record(cur)
         if world > 1:
-            flat = torch.cat([p_.grad.reshape(-1) for p_ in params])
-            flat.mul_(1.0 / world)
-            tdist.all_reduce(flat)
+            for p_ in params:                               # averaged in place, largest (SH, 192 MB) first in flight
+                tdist.all_reduce(p_.grad, op=tdist.ReduceOp.AVG)
         loss_host[i % 64:i % 64 + 1].copy_(loss.detach().reshape(1), non_blocking=True)
 
     e_steps = max(3, args.steps // 2)
@@ -284,7 +287,9 @@ def bench_ours(args, cfg, rank, local, world):
             "clocks": clocks,
             "stage_ms": stage,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(dom) if cfg == HEADLINE else None,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture per launch (profiles/r01_ncu_composite_*_final.md)",
+                         "peak_source": peak_src,
                          "alg_bytes_per_launch": ab[dom],
                          "step_alg_bytes": step_alg, "step_frac_of_peak": step_alg / (ms / args.steps * 1e-3) / 1e9 / peak},
         }

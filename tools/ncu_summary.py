@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Turn an .ncu-rep (ncu --set full --import-source on) into a small committed text summary:
 key metrics, per-segment instruction / stall-sample shares, top stalled SASS lines.
-usage: ncu_summary.py report.ncu-rep out.md [title]"""
+usage: ncu_summary.py report.ncu-rep out.md [title] [kernel-name-regex]   (regex: pick one kernel of a multi-kernel report)"""
 import csv
 import io
 import subprocess
@@ -19,13 +19,18 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
 
 
+FILTER = []
+
+
 def run(args):
-    return subprocess.run(["ncu", "-i"] + args, capture_output=True, text=True).stdout
+    return subprocess.run(["ncu", "-i"] + args + FILTER, capture_output=True, text=True).stdout
 
 
 def main():
     rep, out = sys.argv[1], sys.argv[2]
     title = sys.argv[3] if len(sys.argv) > 3 else rep
+    if len(sys.argv) > 4:
+        FILTER.extend(["--kernel-name", "regex:" + sys.argv[4]])
     raw = list(csv.reader(io.StringIO(run([rep, "--page", "raw", "--csv"]))))
     hdr, units, val = raw[0], raw[1], raw[2]
     lines = [f"# {title}", "", f"kernel: `{val[hdr.index('Kernel Name')] if 'Kernel Name' in hdr else '?'}`", "",
