@@ -113,6 +113,9 @@ struct GeomLayout {
 // inside the tile's list.
 #define R3DG_BIN_MAX_CHUNKS 1024
 __host__ __device__ inline int bin_max_chunks(size_t T) {
+#ifndef __CUDA_ARCH__
+    if (const char* e = getenv("R3DG_BIN_MAX_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= R3DG_BIN_MAX_CHUNKS) return v; }   // tests: long chunks
+#endif
     size_t c = ((size_t)1 << 26) / (T ? T : 1);
     return (int)(c < 296 ? 296 : (c > R3DG_BIN_MAX_CHUNKS ? R3DG_BIN_MAX_CHUNKS : c));
 }
