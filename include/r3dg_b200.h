@@ -226,6 +226,25 @@ size_t r3dg_knn_tmp_bytes(int P);
 int r3dg_knn_dist2(int P, const float* points /* [P,3] */, float* mean_dist2 /* [P] */, void* tmp,
                    size_t tmp_bytes, r3dg_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Optimiser step.  Replaces, for all parameter groups at once, the
+ * per-group `torch.optim.Adam(l, lr=0.0, eps=1e-15).step()` of scene/gaussian_model.py:489,495-497
+ * (torch 1.12.1 torch/optim/adam.py:_single_tensor_adam: no weight decay, no amsgrad, no
+ * maximize — the only configuration the reference uses).  `tensors` is a HOST array; every
+ * entry updates param / exp_avg / exp_avg_sq in place from grad.  `step` is the 1-based count of
+ * this update for that tensor (torch increments state['step'] before using it).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct r3dg_adam_tensor {
+    float* param;              /* [n] */
+    const float* grad;         /* [n] */
+    float* exp_avg;            /* [n] */
+    float* exp_avg_sq;         /* [n] */
+    long long n;
+    long long step;
+    double lr, beta1, beta2, eps;
+} r3dg_adam_tensor;
+int r3dg_adam_step(int num_tensors, const r3dg_adam_tensor* tensors, r3dg_stream_t stream);
+
 /* Measurement hooks used by bench.py (never needed by the reference's callers).
  * r3dg_launch_count: number of this library's kernels launched so far in the process.
  * r3dg_prof_begin/end: while active, every forward/backward records CUDA events on the launching
@@ -235,6 +254,16 @@ int r3dg_knn_dist2(int P, const float* points /* [P,3] */, float* mean_dist2 /* 
 unsigned long long r3dg_launch_count(void);
 int r3dg_prof_begin(int max_calls);
 int r3dg_prof_end(float* stage_ms /* [9] */, int* fwd_calls, int* bwd_calls);
+
+/* Tuning knobs (development / measurement; results are identical for every setting, only the
+ * kernel variant changes).  Sets knob `key` to `value`, stores the old value in *previous (may be
+ * NULL); R3DG_ERR_UNSUPPORTED for an unknown key, R3DG_ERR_BAD_ARG for an out-of-range value.
+ *   "shade_group"     lanes per Gaussian in the shading kernels: 8 (default), 16, 32
+ *   "shade_env_mode"  env-map gradient accumulation in r3dg_render_equation_backward:
+ *                     2 warp-private tagged copies (default), 1 shared-memory atomics,
+ *                     0 global atomics; larger textures fall back to the lower modes
+ * Initial values can also be given by the environment (R3DG_SHADE_GROUP, R3DG_SHADE_ENV_MODE). */
+int r3dg_tune(const char* key, int value, int* previous);
 
 /* Library identification: returns a static string such as "r3dg_b200 0.1 sm_100a". */
 const char* r3dg_version(void);

@@ -57,6 +57,12 @@ class ShadeArgs(ctypes.Structure):
                                  "dL_droughness", "dL_dviewdirs", "dL_dincidents", "dL_denv")])
 
 
+class AdamTensor(ctypes.Structure):
+    _fields_ = ([(n, c_void_p) for n in ("param", "grad", "exp_avg", "exp_avg_sq")] +
+                [("n", c_ll), ("step", c_ll)] +
+                [(n, ctypes.c_double) for n in ("lr", "beta1", "beta2", "eps")])
+
+
 # every symbol include/r3dg_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("r3dg_version", ctypes.c_char_p, []),
@@ -78,7 +84,9 @@ SYMBOLS = [
     ("r3dg_render_equation_backward", c_int, [ctypes.POINTER(ShadeArgs), c_void_p]),
     ("r3dg_knn_tmp_bytes", c_size_t, [c_int]),
     ("r3dg_knn_dist2", c_int, [c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    ("r3dg_adam_step", c_int, [c_int, ctypes.POINTER(AdamTensor), c_void_p]),
     ("r3dg_launch_count", ctypes.c_ulonglong, []),
+    ("r3dg_tune", c_int, [ctypes.c_char_p, c_int, ctypes.POINTER(c_int)]),
     ("r3dg_prof_begin", c_int, [c_int]),
     ("r3dg_prof_end", c_int, [ctypes.POINTER(c_float), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     ("r3dg_raster_debug_copy", c_ll, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
@@ -104,6 +112,13 @@ def load():
         fn.argtypes = argtypes
     _lib = lib
     return lib
+
+
+def tune(key, value):
+    """Set a tuning knob (include/r3dg_b200.h: r3dg_tune); returns the previous value."""
+    prev = c_int(0)
+    check(load().r3dg_tune(key.encode(), int(value), ctypes.byref(prev)), f"r3dg_tune({key})")
+    return prev.value
 
 
 def check(rc, what):

@@ -121,7 +121,16 @@ int r3dg_raster_backward(const r3dg_raster_bwd_args* a, r3dg_stream_t stream_) {
     return 0;
 }
 
-unsigned long long r3dg_launch_count(void) { return g_launches; }
+extern unsigned long long r3dg_adam_launches;
+unsigned long long r3dg_launch_count(void) { return g_launches + r3dg_adam_launches; }
+
+int r3dg_tune(const char* key, int value, int* previous) {
+    if (!key) return R3DG_ERR_BAD_ARG;
+    int prev = 0;
+    const int rc = shade_tune(key, value, &prev);
+    if (previous) *previous = prev;
+    return rc;
+}
 
 int r3dg_prof_begin(int max_calls) {
     for (auto& e : g_prof.ev) cudaEventDestroy(e);

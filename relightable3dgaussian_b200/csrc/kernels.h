@@ -42,6 +42,11 @@ int launch_bvh_trace(int P, long long num_rays, const int32_t* nodes, const floa
                      const float* normals, int32_t* num_contributes, float* rendered_opacity,
                      void* packets, size_t packets_bytes, int num_sms, cudaStream_t stream);
 
+int shade_tune(const char* key, int value, int* previous);
+
+// adam.cu: one launch per <= 16 parameter tensors
+int launch_adam(int num, const r3dg_adam_tensor* tensors, cudaStream_t stream, int* launches);
+
 size_t knn_tmp_bytes(int P);
 int launch_knn(int P, const float* points, float* out, void* tmp, size_t tmp_bytes, int num_sms, cudaStream_t stream);
 

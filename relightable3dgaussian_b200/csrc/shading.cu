@@ -5,15 +5,21 @@
 // graph keeps >= 15 such tensors alive — as ONE forward and ONE backward kernel.
 //
 // B200 design notes
-//  * one warp per Gaussian, lanes stride the N incident samples: the baked [P,N,*] tensors
-//    (direction 12 B + visibility 4 B + area 4 B per sample — the only per-sample HBM traffic) are
-//    read once per direction with fully coalesced warp-wide loads; nothing of size [P,N,*] is
-//    written unless the caller asks for the eval-only per-sample lights;
+//  * a group of 8 lanes per Gaussian (4 Gaussians per warp), lanes stride the N incident samples:
+//    the baked [P,N,*] tensors (direction 12 B + visibility 4 B + area 4 B per sample — the only
+//    per-sample HBM traffic) are read once per direction, rows of neighbouring Gaussians are
+//    contiguous so the warp's loads stay coalesced; nothing of size [P,N,*] is written unless the
+//    caller asks for the eval-only per-sample lights.  (One warp per Gaussian left 1-2 samples per
+//    lane at the training sample counts N = 32 / 64 and paid 290 shuffles per Gaussian.)
 //  * per-Gaussian operands (material, normal, view direction, 48 SH coefficients) live in
-//    registers, the (small) environment texture and, in the backward, its gradient live in shared
-//    memory of a persistent CTA: the grid_sample scatter-add of P*N samples becomes shared-memory
-//    atomics plus ONE flush of H*W*3 global atomics per CTA;
+//    registers; the backward reduces its 48 SH-coefficient gradients with a transposed butterfly
+//    (42 shuffles per 4 Gaussians) and the group writes the 192 B row contiguously;
+//  * the (small) environment texture lives in shared memory of a persistent CTA; its gradient —
+//    grid_sample's scatter-add of P*N*4 taps — is accumulated in warp-private shared-memory copies
+//    without atomics (see "environment-map gradient" below), summed and flushed once per CTA;
 //  * the backward recomputes the forward per sample instead of saving [P,N,*] activations.
+#include <cstdlib>
+#include <cstring>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -157,28 +163,63 @@ __device__ __forceinline__ void eval_sample(const ShadeArgs& a, const GaussianOp
     e.fs = e.frac0 * o.a2 / e.nom;
 }
 
-__device__ __forceinline__ float warp_sum(float v) {
+// ---- sub-warp groups ---------------------------------------------------------------------------
+// A group of G lanes (G = 8, 16 or 32) owns one Gaussian, so a warp shades 32/G Gaussians at once:
+// at the training sample counts (N = 32 / 64, script/run_*.sh) a whole warp per Gaussian leaves each
+// lane 1-2 samples and the per-Gaussian work (operand loads, 58 values x 5 shuffle levels in the
+// backward) dominates.  Groups read consecutive rows of the baked tensors, so loads stay coalesced.
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 
-template <bool SMEM_ENV>
+// Transposed butterfly ("reduce-scatter") over the G lanes of a group: V values per lane in, and
+// lane `sub` returns with v[0 .. V/G) = the group totals of components [sub*V/G, (sub+1)*V/G).
+// V*(1 - 1/G) shuffles instead of V*log2(G).
+template <int G, int V>
+__device__ __forceinline__ void group_reduce_scatter(float (&v)[V], int sub) {
+    static_assert(V % G == 0, "V must be a multiple of the group width");
+    int n = V;
+#pragma unroll
+    for (int m = G / 2; m > 0; m >>= 1) {
+        const bool upper = (sub & m) != 0;
+        const int h = n / 2;
+#pragma unroll
+        for (int i = 0; i < V / 2; ++i) {
+            if (i < h) {
+                const float send = upper ? v[i] : v[i + h];
+                const float keep = upper ? v[i + h] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+            }
+        }
+        n = h;
+    }
+}
+
+template <bool SMEM_ENV, int G>
 __global__ void __launch_bounds__(SHADE_THREADS) shade_fwd_kernel(const ShadeArgs a) {
     extern __shared__ float s_env[];
+    constexpr int GPW = 32 / G;                    // Gaussians per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane & (G - 1), grp = lane / G;
     if (SMEM_ENV) {
         for (int i = threadIdx.x; i < a.He * a.We * 3; i += SHADE_THREADS) s_env[i] = a.env[i];
         __syncthreads();
     }
     const float* env = SMEM_ENV ? s_env : a.env;
     const float invN = 1.0f / (float)a.N;
-    for (int g = blockIdx.x * SHADE_WARPS + warp; g < a.P; g += gridDim.x * SHADE_WARPS) {
+    const int units = (a.P + GPW - 1) / GPW;
+    for (int u = blockIdx.x * SHADE_WARPS + warp; u < units; u += gridDim.x * SHADE_WARPS) {
+        const int g_raw = u * GPW + grp;
+        const bool valid = g_raw < a.P;
+        const int g = valid ? g_raw : a.P - 1;      // idle groups of the last warp shade a copy, write nothing
         GaussianOperands o;
         load_operands(a, g, o);
         float pbr[3] = {0, 0, 0}, spec[3] = {0, 0, 0}, diff[3] = {0, 0, 0}, ml[3] = {0, 0, 0}, mloc[3] = {0, 0, 0}, mg[3] = {0, 0, 0}, mv = 0;
         const size_t row = (size_t)g * a.N;
-        for (int i = lane; i < a.N; i += 32) {
+        for (int i = sub; i < a.N; i += G) {
             const float dx = a.dirs[3 * (row + i)], dy = a.dirs[3 * (row + i) + 1], dz = a.dirs[3 * (row + i) + 2];
             const float vis = a.visibility[row + i], area = a.areas[row + i];
             SampleEval e;
@@ -191,17 +232,18 @@ __global__ void __launch_bounds__(SHADE_THREADS) shade_fwd_kernel(const ShadeArg
                 const float fd = o.base[c] / PI_F;
                 pbr[c] += (fd + e.fs) * T; spec[c] += e.fs * T; diff[c] += T;
                 ml[c] += Lc; mloc[c] += loc; mg[c] += e.glob[c];
-                if (a.s_lights) { a.s_lights[3 * (row + i) + c] = Lc; a.s_local[3 * (row + i) + c] = loc; a.s_global[3 * (row + i) + c] = e.glob[c]; }
+                if (a.s_lights && valid) { a.s_lights[3 * (row + i) + c] = Lc; a.s_local[3 * (row + i) + c] = loc; a.s_global[3 * (row + i) + c] = e.glob[c]; }
             }
             mv += vis;
         }
+        __syncwarp();
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            pbr[c] = warp_sum(pbr[c]); spec[c] = warp_sum(spec[c]); diff[c] = warp_sum(diff[c]);
-            if (a.mean_lights) { ml[c] = warp_sum(ml[c]); mloc[c] = warp_sum(mloc[c]); mg[c] = warp_sum(mg[c]); }
+            pbr[c] = group_sum<G>(pbr[c]); spec[c] = group_sum<G>(spec[c]); diff[c] = group_sum<G>(diff[c]);
+            if (a.mean_lights) { ml[c] = group_sum<G>(ml[c]); mloc[c] = group_sum<G>(mloc[c]); mg[c] = group_sum<G>(mg[c]); }
         }
-        if (a.mean_vis) mv = warp_sum(mv);
-        if (lane == 0) {
+        if (a.mean_vis) mv = group_sum<G>(mv);
+        if (sub == 0 && valid) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 a.pbr[3 * (size_t)g + c] = pbr[c] * invN; a.specular[3 * (size_t)g + c] = spec[c] * invN; a.diffuse[3 * (size_t)g + c] = diff[c] * invN;
@@ -212,21 +254,63 @@ __global__ void __launch_bounds__(SHADE_THREADS) shade_fwd_kernel(const ShadeArg
     }
 }
 
-template <bool SMEM_ENV>
+// ---- environment-map gradient (grid_sample backward: a scatter-add of P*N*4 taps) ----------------
+// There is no native fp32 shared-memory atomic add on sm_100: `atomicAdd(float*)` on shared memory
+// compiles to an LDS / FADD / ATOMS.CAST.SPIN loop that occupies the LSU for ~64 cycles per warp
+// instruction, and 12 of them per sample bounded the whole backward kernel.  ENV_TAG mode gives
+// every warp a PRIVATE float4 {r,g,b,-} copy of the texture gradient and resolves the (rare)
+// intra-warp collisions with a one-byte tag per texel: every pending lane stores its lane id, the
+// id that survives owns the texel this round and does a plain 128-bit read-modify-write, the losers
+// retry.  The copies are summed and flushed once per CTA.
+enum { ENV_GLOBAL = 0, ENV_CAS = 1, ENV_TAG = 2 };
+
+__device__ __forceinline__ void warp_private_add(float4* wg, volatile unsigned char* tag, int texel, float x, float y, float z, int lane) {
+    bool pending = texel >= 0;
+    while (true) {                                   // warp-uniform trip count
+        if (pending) tag[texel] = (unsigned char)lane;
+        __syncwarp();
+        if (pending && tag[texel] == (unsigned char)lane) {
+            float4 acc = wg[texel];
+            acc.x += x; acc.y += y; acc.z += z;
+            wg[texel] = acc;
+            pending = false;
+        }
+        __syncwarp();
+        if (!__any_sync(0xffffffffu, pending)) break;
+    }
+}
+
+template <int ENV_MODE, int G>
 __global__ void __launch_bounds__(SHADE_THREADS) shade_bwd_kernel(const ShadeArgs a) {
-    extern __shared__ float s_mem[];                // [env][env grad] when SMEM_ENV
+    extern __shared__ __align__(16) float s_mem[];
+    constexpr bool SMEM_ENV = ENV_MODE != ENV_GLOBAL;
+    constexpr int GPW = 32 / G;
+    constexpr int VP = (48 + G - 1) / G * G;         // SH-gradient row padded to a multiple of G
+    constexpr int RQ = VP / G;                       // finished components per lane
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ne = a.He * a.We * 3;
+    const int sub = lane & (G - 1), grp = lane / G;
+    const int nt = a.He * a.We, ne = nt * 3;
+    // ENV_CAS: [env ne][grad ne]; ENV_TAG: [env ne (padded to 4)][per warp: float4 grad[nt]][per warp: tag[nt] padded to 16]
     float* s_env = s_mem;
     float* s_genv = s_mem + ne;
+    const int ne4 = (ne + 3) & ~3, ntp = (nt + 15) & ~15;
+    float4* wgrad_all = reinterpret_cast<float4*>(s_mem + ne4);
+    float4* wgrad = wgrad_all + (size_t)warp * nt;
+    volatile unsigned char* wtag = reinterpret_cast<unsigned char*>(wgrad_all + (size_t)SHADE_WARPS * nt) + (size_t)warp * ntp;
     if (SMEM_ENV) {
-        for (int i = threadIdx.x; i < ne; i += SHADE_THREADS) { s_env[i] = a.env[i]; s_genv[i] = 0.f; }
+        for (int i = threadIdx.x; i < ne; i += SHADE_THREADS) s_env[i] = a.env[i];
+        if (ENV_MODE == ENV_CAS) for (int i = threadIdx.x; i < ne; i += SHADE_THREADS) s_genv[i] = 0.f;
+        if (ENV_MODE == ENV_TAG) for (int i = threadIdx.x; i < SHADE_WARPS * nt; i += SHADE_THREADS) wgrad_all[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
     }
     const float* env = SMEM_ENV ? s_env : a.env;
-    float* genv = SMEM_ENV ? s_genv : a.d_env;
+    float* genv = ENV_MODE == ENV_CAS ? s_genv : a.d_env;
     const float invN = 1.0f / (float)a.N;
-    for (int g = blockIdx.x * SHADE_WARPS + warp; g < a.P; g += gridDim.x * SHADE_WARPS) {
+    const int units = (a.P + GPW - 1) / GPW;
+    for (int u = blockIdx.x * SHADE_WARPS + warp; u < units; u += gridDim.x * SHADE_WARPS) {
+        const int g_raw = u * GPW + grp;
+        const bool valid = g_raw < a.P;
+        const int g = valid ? g_raw : a.P - 1;
         GaussianOperands o;
         load_operands(a, g, o);
         float gp[3], gs[3], gd[3];
@@ -237,96 +321,174 @@ __global__ void __launch_bounds__(SHADE_THREADS) shade_bwd_kernel(const ShadeArg
             gd[c] = a.g_diffuse ? a.g_diffuse[3 * (size_t)g + c] * invN : 0.f;
         }
         float dbase[3] = {0, 0, 0}, drough = 0.f, dV[3] = {0, 0, 0};
-        float dinc[48];
+        float dinc[VP];
 #pragma unroll
-        for (int q = 0; q < 48; ++q) dinc[q] = 0.f;
+        for (int q = 0; q < VP; ++q) dinc[q] = 0.f;
         const size_t row = (size_t)g * a.N;
-        for (int i = lane; i < a.N; i += 32) {
+        for (int i0 = 0; i0 < a.N; i0 += G) {          // warp-uniform trip count (collectives inside in ENV_TAG mode)
+            const bool act = valid && (i0 + sub) < a.N;
+            const int i = (i0 + sub) < a.N ? (i0 + sub) : a.N - 1;
             const float dx = a.dirs[3 * (row + i)], dy = a.dirs[3 * (row + i) + 1], dz = a.dirs[3 * (row + i) + 2];
             const float vis = a.visibility[row + i], area = a.areas[row + i];
             SampleEval e;
             eval_sample<SMEM_ENV>(a, o, env, dx, dy, dz, vis, e);
             float dfs = 0.f;
+            float dG[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const float loc = fmaxf(e.local_raw[c], 0.f);
                 const float T = (loc + e.glob[c]) * area * e.ndi;
                 const float fd = o.base[c] / PI_F;
-                const float dT = gp[c] * (fd + e.fs) + gs[c] * e.fs + gd[c];
-                dbase[c] += gp[c] * T / PI_F;
-                dfs += (gp[c] + gs[c]) * T;
+                const float dT = act ? gp[c] * (fd + e.fs) + gs[c] * e.fs + gd[c] : 0.f;
+                if (act) { dbase[c] += gp[c] * T / PI_F; dfs += (gp[c] + gs[c]) * T; }
                 const float dL = dT * area * e.ndi;
-                if (e.local_raw[c] >= 0.f) {                       // clamp_min(0) passes the gradient at equality
+                if (act && e.local_raw[c] >= 0.f) {                // clamp_min(0) passes the gradient at equality
 #pragma unroll
                     for (int k = 0; k < 16; ++k) dinc[3 * k + c] = fmaf(dL, e.w[k], dinc[3 * k + c]);
                 }
-                const float dG = dL * vis;                           // -> env texels (grid_sample backward)
-                if (dG != 0.f) {
+                dG[c] = act ? dL * vis : 0.f;                        // -> env texels (grid_sample backward)
+            }
+            if (ENV_MODE == ENV_TAG) {
+                const bool any = dG[0] != 0.f || dG[1] != 0.f || dG[2] != 0.f;
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) if (e.taps.idx[t] >= 0) atomicAdd(genv + e.taps.idx[t] + c, dG * e.taps.w[t]);
+                for (int t = 0; t < 4; ++t) {
+                    const int texel = (any && e.taps.idx[t] >= 0) ? e.taps.idx[t] / 3 : -1;
+                    warp_private_add(wgrad, wtag, texel, dG[0] * e.taps.w[t], dG[1] * e.taps.w[t], dG[2] * e.taps.w[t], lane);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    if (dG[c] != 0.f) {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) if (e.taps.idx[t] >= 0) atomicAdd(genv + e.taps.idx[t] + c, dG[c] * e.taps.w[t]);
+                    }
+            }
+            if (act) {
+                // ---- GGX backward --------------------------------------------------------------
+                const float dfrac = dfs / e.nom;
+                const float dnom = -dfs * (e.frac0 * o.a2) / (e.nom * e.nom);
+                const float dnom_r = (e.nom_r >= 1e-6f && e.nom_r <= 4.0f * PI_F) ? dnom : 0.f;
+                const float dnom0 = dnom_r * 8.0f * PI_F * e.nom0 * e.nom1 * e.nom2;
+                const float dnom1 = dnom_r * 4.0f * PI_F * e.nom0 * e.nom0 * e.nom2;
+                const float dnom2 = dnom_r * 4.0f * PI_F * e.nom0 * e.nom0 * e.nom1;
+                const float dfrac0 = dfrac * o.a2;
+                const float da2 = dfrac * e.frac0 + dnom0 * e.NoH * e.NoH;
+                const float dk = dnom1 * (1.0f - e.NoV) + dnom2 * (1.0f - e.NoL);
+                const float r = o.rough;
+                drough += da2 * 4.0f * r * r * r + dk * (2.0f * r + 2.0f) / 8.0f;
+                const float dNoH = (e.NoH_r >= 1e-6f && e.NoH_r <= 1.f) ? dnom0 * 2.0f * e.NoH * (o.a2 - 1.0f) : 0.f;
+                const float dNoV = (e.NoV_r >= 1e-6f && e.NoV_r <= 1.f) ? dnom1 * (1.0f - o.k) : 0.f;
+                const float dVoH = (e.VoH_r >= 1e-6f && e.VoH_r <= 1.f)
+                                       ? dfrac0 * (1.0f - 0.04f) * e.p2 * 0.693147180559945f * (2.0f * -5.55473f * e.VoH - 6.98316f) : 0.f;
+                float dH[3], hdot = 0.f;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { dH[c] = dNoH * o.Ns[c] + dVoH * o.V[c]; hdot += e.H[c] * dH[c]; }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float dHraw = (dH[c] - e.H[c] * hdot) / e.hn;
+                    dV[c] += dNoV * o.Ns[c] + dVoH * e.H[c] + 0.5f * dHraw;
                 }
             }
-            // ---- GGX backward ------------------------------------------------------------------
-            const float dfrac = dfs / e.nom;
-            const float dnom = -dfs * (e.frac0 * o.a2) / (e.nom * e.nom);
-            const float dnom_r = (e.nom_r >= 1e-6f && e.nom_r <= 4.0f * PI_F) ? dnom : 0.f;
-            const float dnom0 = dnom_r * 8.0f * PI_F * e.nom0 * e.nom1 * e.nom2;
-            const float dnom1 = dnom_r * 4.0f * PI_F * e.nom0 * e.nom0 * e.nom2;
-            const float dnom2 = dnom_r * 4.0f * PI_F * e.nom0 * e.nom0 * e.nom1;
-            const float dfrac0 = dfrac * o.a2;
-            const float da2 = dfrac * e.frac0 + dnom0 * e.NoH * e.NoH;
-            const float dk = dnom1 * (1.0f - e.NoV) + dnom2 * (1.0f - e.NoL);
-            const float r = o.rough;
-            drough += da2 * 4.0f * r * r * r + dk * (2.0f * r + 2.0f) / 8.0f;
-            const float dNoH = (e.NoH_r >= 1e-6f && e.NoH_r <= 1.f) ? dnom0 * 2.0f * e.NoH * (o.a2 - 1.0f) : 0.f;
-            const float dNoV = (e.NoV_r >= 1e-6f && e.NoV_r <= 1.f) ? dnom1 * (1.0f - o.k) : 0.f;
-            const float dVoH = (e.VoH_r >= 1e-6f && e.VoH_r <= 1.f)
-                                   ? dfrac0 * (1.0f - 0.04f) * e.p2 * 0.693147180559945f * (2.0f * -5.55473f * e.VoH - 6.98316f) : 0.f;
-            float dH[3], hdot = 0.f;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { dH[c] = dNoH * o.Ns[c] + dVoH * o.V[c]; hdot += e.H[c] * dH[c]; }
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float dHraw = (dH[c] - e.H[c] * hdot) / e.hn;
-                dV[c] += dNoV * o.Ns[c] + dVoH * e.H[c] + 0.5f * dHraw;
-            }
         }
-        // ---- warp reduction and per-Gaussian outputs ----------------------------------------------
+        __syncwarp();
+        // ---- group reduction and per-Gaussian outputs ---------------------------------------------
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { dbase[c] = warp_sum(dbase[c]); dV[c] = warp_sum(dV[c]); }
-        drough = warp_sum(drough);
+        for (int c = 0; c < 3; ++c) { dbase[c] = group_sum<G>(dbase[c]); dV[c] = group_sum<G>(dV[c]); }
+        drough = group_sum<G>(drough);
+        group_reduce_scatter<G, VP>(dinc, sub);        // lane `sub` now owns components [sub*RQ, sub*RQ + RQ)
+        if (valid) {
+            if (sub == 0) {
+                const float vd = o.V[0] * dV[0] + o.V[1] * dV[1] + o.V[2] * dV[2];
 #pragma unroll
-        for (int q = 0; q < 48; ++q) dinc[q] = warp_sum(dinc[q]);
-        if (lane == 0) {
-            const float vd = o.V[0] * dV[0] + o.V[1] * dV[1] + o.V[2] * dV[2];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                a.d_base[3 * (size_t)g + c] = dbase[c];
-                a.d_view[3 * (size_t)g + c] = (dV[c] - o.V[c] * vd) / o.vnorm;        // through V = normalize(viewdirs)
+                for (int c = 0; c < 3; ++c) {
+                    a.d_base[3 * (size_t)g + c] = dbase[c];
+                    a.d_view[3 * (size_t)g + c] = (dV[c] - o.V[c] * vd) / o.vnorm;        // through V = normalize(viewdirs)
+                }
+                a.d_rough[g] = drough;
             }
-            a.d_rough[g] = drough;
-        }
-        float4* dp = reinterpret_cast<float4*>(a.d_incidents + 48 * (size_t)g);
-        if (lane < 12) {                          // 12 lanes write the 192 B row as float4s
-            float4 v;
-            // dinc is warp-uniform after the reduction; pick this lane's four values without dynamic indexing
-            float sel[4] = {0, 0, 0, 0};
+            float* dp = a.d_incidents + 48 * (size_t)g + sub * RQ;    // the group writes the 192 B row contiguously
+            if (RQ % 2 == 0) {
 #pragma unroll
-            for (int q = 0; q < 48; ++q) if ((q >> 2) == lane) sel[q & 3] = dinc[q];
-            v.x = sel[0]; v.y = sel[1]; v.z = sel[2]; v.w = sel[3];
-            dp[lane] = v;
+                for (int q = 0; q < RQ; q += 2)
+                    if (sub * RQ + q < 48) *reinterpret_cast<float2*>(dp + q) = make_float2(dinc[q], dinc[q + 1]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < RQ; ++q)
+                    if (sub * RQ + q < 48) dp[q] = dinc[q];
+            }
         }
     }
-    if (SMEM_ENV) {
+    if (ENV_MODE == ENV_CAS) {
         __syncthreads();
         for (int i = threadIdx.x; i < ne; i += SHADE_THREADS) { const float v = s_genv[i]; if (v != 0.f) atomicAdd(a.d_env + i, v); }
     }
+    if (ENV_MODE == ENV_TAG) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < nt; t += SHADE_THREADS) {
+            float4 s = wgrad_all[t];
+#pragma unroll
+            for (int w = 1; w < SHADE_WARPS; ++w) { const float4 v = wgrad_all[(size_t)w * nt + t]; s.x += v.x; s.y += v.y; s.z += v.z; }
+            if (s.x != 0.f) atomicAdd(a.d_env + 3 * t, s.x);
+            if (s.y != 0.f) atomicAdd(a.d_env + 3 * t + 1, s.y);
+            if (s.z != 0.f) atomicAdd(a.d_env + 3 * t + 2, s.z);
+        }
+    }
 }
 
-static int shade_grid(int P, int num_sms, int per_sm) {
-    const int want = (P + SHADE_WARPS - 1) / SHADE_WARPS;
-    const int cap = num_sms * per_sm;
+// ---- launch ---------------------------------------------------------------------------------------
+// tuning knobs (A/B measurements and tests of the non-default paths): initial value from the
+// environment, changed at run time through r3dg_tune (include/r3dg_b200.h)
+static int g_shade_group = -1;      // lanes per Gaussian: 8 (default), 16 or 32
+static int g_shade_env_mode = -1;   // highest env-gradient mode allowed: 2 tag (default), 1 smem atomics, 0 global atomics
+
+static int shade_group_width() {
+    if (g_shade_group < 0) {
+        const char* e = getenv("R3DG_SHADE_GROUP");
+        const int g = e ? atoi(e) : 8;
+        g_shade_group = (g == 8 || g == 16 || g == 32) ? g : 8;
+    }
+    return g_shade_group;
+}
+static int shade_env_mode_cap() {
+    if (g_shade_env_mode < 0) {
+        const char* e = getenv("R3DG_SHADE_ENV_MODE");
+        const int m = e ? atoi(e) : ENV_TAG;
+        g_shade_env_mode = (m >= ENV_GLOBAL && m <= ENV_TAG) ? m : ENV_TAG;
+    }
+    return g_shade_env_mode;
+}
+int shade_tune(const char* key, int value, int* previous) {
+    if (!strcmp(key, "shade_group")) {
+        *previous = shade_group_width();
+        if (value != 8 && value != 16 && value != 32) return R3DG_ERR_BAD_ARG;
+        g_shade_group = value;
+        return 0;
+    }
+    if (!strcmp(key, "shade_env_mode")) {
+        *previous = shade_env_mode_cap();
+        if (value < ENV_GLOBAL || value > ENV_TAG) return R3DG_ERR_BAD_ARG;
+        g_shade_env_mode = value;
+        return 0;
+    }
+    return R3DG_ERR_UNSUPPORTED;
+}
+
+template <typename K>
+static int shade_grid(K kernel, int units, int num_sms, size_t smem) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SHADE_THREADS, smem) != cudaSuccess || per_sm <= 0) per_sm = 2;
+    const int want = (units + SHADE_WARPS - 1) / SHADE_WARPS;
+    const int cap = num_sms * per_sm;                 // persistent CTAs: one env staging / flush per resident CTA
     return want < cap ? (want > 0 ? want : 1) : cap;
+}
+
+template <bool SMEM, int G>
+static int launch_fwd_g(const ShadeArgs& a, int num_sms, size_t smem, cudaStream_t stream) {
+    const int units = (a.P + 32 / G - 1) / (32 / G);
+    const int grid = shade_grid(shade_fwd_kernel<SMEM, G>, units, num_sms, smem);
+    shade_fwd_kernel<SMEM, G><<<grid, SHADE_THREADS, smem, stream>>>(a);
+    R3DG_CUDA_TRY(cudaGetLastError());
+    return 0;
 }
 
 int launch_shade_forward(ShadeArgs a, int num_sms, cudaStream_t stream) {
@@ -334,24 +496,41 @@ int launch_shade_forward(ShadeArgs a, int num_sms, cudaStream_t stream) {
     const size_t env_bytes = (size_t)a.He * a.We * 3 * sizeof(float);
     const bool smem = env_bytes <= 40 * 1024;
     a.env_in_smem = smem;
-    const int grid = shade_grid(a.P, num_sms, 16);
-    if (smem) shade_fwd_kernel<true><<<grid, SHADE_THREADS, env_bytes, stream>>>(a);
-    else shade_fwd_kernel<false><<<grid, SHADE_THREADS, 0, stream>>>(a);
+    const int G = shade_group_width();
+    if (smem) return G == 8 ? launch_fwd_g<true, 8>(a, num_sms, env_bytes, stream) : G == 16 ? launch_fwd_g<true, 16>(a, num_sms, env_bytes, stream)
+                                                                                              : launch_fwd_g<true, 32>(a, num_sms, env_bytes, stream);
+    return G == 8 ? launch_fwd_g<false, 8>(a, num_sms, 0, stream) : G == 16 ? launch_fwd_g<false, 16>(a, num_sms, 0, stream)
+                                                                            : launch_fwd_g<false, 32>(a, num_sms, 0, stream);
+}
+
+template <int MODE, int G>
+static int launch_bwd_g(const ShadeArgs& a, int num_sms, size_t smem, cudaStream_t stream) {
+    const int units = (a.P + 32 / G - 1) / (32 / G);
+    const int grid = shade_grid(shade_bwd_kernel<MODE, G>, units, num_sms, smem);
+    shade_bwd_kernel<MODE, G><<<grid, SHADE_THREADS, smem, stream>>>(a);
     R3DG_CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
+template <int MODE>
+static int launch_bwd_mode(const ShadeArgs& a, int num_sms, size_t smem, cudaStream_t stream) {
+    const int G = shade_group_width();
+    return G == 8 ? launch_bwd_g<MODE, 8>(a, num_sms, smem, stream) : G == 16 ? launch_bwd_g<MODE, 16>(a, num_sms, smem, stream)
+                                                                              : launch_bwd_g<MODE, 32>(a, num_sms, smem, stream);
+}
+
 int launch_shade_backward(ShadeArgs a, int num_sms, cudaStream_t stream) {
-    const size_t env_bytes = (size_t)a.He * a.We * 3 * sizeof(float);
+    const size_t nt = (size_t)a.He * a.We, env_bytes = nt * 3 * sizeof(float);
     R3DG_CUDA_TRY(cudaMemsetAsync(a.d_env, 0, env_bytes, stream));
     if (a.P <= 0) return 0;
-    const bool smem = 2 * env_bytes <= 40 * 1024;
-    a.env_in_smem = smem;
-    const int grid = shade_grid(a.P, num_sms, 8);
-    if (smem) shade_bwd_kernel<true><<<grid, SHADE_THREADS, 2 * env_bytes, stream>>>(a);
-    else shade_bwd_kernel<false><<<grid, SHADE_THREADS, 0, stream>>>(a);
-    R3DG_CUDA_TRY(cudaGetLastError());
-    return 0;
+    // shared-memory budget of the three env-gradient modes (static 48 KB limit, no opt-in)
+    const size_t tag_bytes = ((nt * 3 + 3) & ~(size_t)3) * sizeof(float) + SHADE_WARPS * (nt * sizeof(float4) + ((nt + 15) & ~(size_t)15));
+    const size_t cas_bytes = 2 * env_bytes;
+    const int cap = shade_env_mode_cap();
+    if (cap >= ENV_TAG && tag_bytes <= 48 * 1024) { a.env_in_smem = 1; return launch_bwd_mode<ENV_TAG>(a, num_sms, tag_bytes, stream); }
+    if (cap >= ENV_CAS && cas_bytes <= 40 * 1024) { a.env_in_smem = 1; return launch_bwd_mode<ENV_CAS>(a, num_sms, cas_bytes, stream); }
+    a.env_in_smem = 0;
+    return launch_bwd_mode<ENV_GLOBAL>(a, num_sms, 0, stream);
 }
 
 }  // namespace r3dg

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_field_order_matches_header():
     hdr = open(os.path.join(ROOT, "include", "r3dg_b200.h")).read()
     for cname, cls in (("r3dg_raster_fwd_args", _lib.RasterFwdArgs), ("r3dg_raster_bwd_args", _lib.RasterBwdArgs),
-                       ("r3dg_shade_args", _lib.ShadeArgs)):
+                       ("r3dg_shade_args", _lib.ShadeArgs), ("r3dg_adam_tensor", _lib.AdamTensor)):
         body = re.search(r"typedef struct " + cname + r" \{(.*?)\} " + cname + ";", hdr, re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         fields = []
@@ -39,7 +39,7 @@ def test_struct_field_order_matches_header():
             decl = decl.strip()
             if not decl:
                 continue
-            names = re.sub(r"^(const\s+)?(float|int|void|size_t)\s*\**", "", decl)
+            names = re.sub(r"^(const\s+)?(float|int|void|size_t|long long|double)\s*\**", "", decl)
             for n in names.split(","):
                 fields.append(n.replace("*", "").strip())
         assert fields == [f[0] for f in cls._fields_], cname
@@ -75,3 +75,34 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(ImportError):
         _lib.load()
+
+
+def test_adam_step_argument_checks_and_host_mirror():
+    """r3dg_adam_step validates its host descriptor table before any launch; FusedAdam mirrors
+    torch.optim.Adam's constructor / state layout and has no CPU path."""
+    import torch
+    from relightable3dgaussian_b200.optim import FusedAdam, install, uninstall
+    lib = _lib.load()
+    assert lib.r3dg_adam_step(0, None, None) == 0
+    assert lib.r3dg_adam_step(1, None, None) == -10001
+    t = (_lib.AdamTensor * 1)()
+    t[0].n, t[0].step, t[0].lr, t[0].beta1, t[0].beta2, t[0].eps = 8, 0, 1e-3, 0.9, 0.999, 1e-15
+    assert lib.r3dg_adam_step(1, t, None) == -10001          # step counts from 1
+    t[0].step = 1
+    assert lib.r3dg_adam_step(1, t, None) == -10001          # null tensors with n > 0
+    t[0].n = 0
+    assert lib.r3dg_adam_step(1, t, None) == 0               # empty tensor: nothing launched
+    p = torch.zeros(4, requires_grad=True)
+    opt = FusedAdam([{"params": [p], "lr": 1e-3, "name": "xyz"}], lr=0.0, eps=1e-15)
+    assert opt.param_groups[0]["name"] == "xyz" and opt.param_groups[0]["eps"] == 1e-15 and opt.param_groups[0]["betas"] == (0.9, 0.999)
+    p.grad = torch.ones(4)
+    with pytest.raises(RuntimeError):
+        opt.step()
+    with pytest.raises(ValueError):
+        FusedAdam([p], betas=(1.0, 0.999))
+    orig = torch.optim.Adam
+    try:
+        assert install() is FusedAdam and torch.optim.Adam is FusedAdam
+    finally:
+        uninstall()
+    assert torch.optim.Adam is orig

@@ -178,3 +178,32 @@ def test_shading_oracle_matches_reference_function_golden(path):
     ((pbr * t("cot_pbr")).sum() + (ex["diffuse_light"] * t("cot_diffuse")).sum() + (ex["specular"] * t("cot_specular")).sum()).backward()
     for k, v in leaves.items():
         assert rel_l2(v.grad.numpy(), g["grad_" + k]) < 1e-5, k
+
+
+def test_adam_oracle_matches_torch_adam():
+    """oracle_adam restates torch's `_single_tensor_adam`; pin it against torch.optim.Adam run here
+    on CPU with the reference's settings (lr per group, eps=1e-15; scene/gaussian_model.py:489)."""
+    import torch
+    from oracle import oracle_adam
+    g = torch.Generator().manual_seed(3)
+    shapes, lrs = [(1000, 3), (1000, 15, 3), (1000, 1)], [1.6e-4, 2.5e-3 / 20, 5e-2]
+    params = [torch.randn(s, generator=g).requires_grad_(True) for s in shapes]
+    opt = torch.optim.Adam([{"params": [p], "lr": lr} for p, lr in zip(params, lrs)], lr=0.0, eps=1e-15)
+    ours = [(p.detach().numpy().copy(), np.zeros(s, np.float32), np.zeros(s, np.float32)) for p, s in zip(params, shapes)]
+    p0 = [o[0].copy() for o in ours]
+    for step in range(1, 8):
+        grads = [torch.randn(s, generator=g) * (0.0 if (step == 3 and i == 0) else 1e-3) for i, s in enumerate(shapes)]
+        grads[1][::2] = 0.0                                  # never-seen Gaussians: exp_avg_sq stays 0, eps decides
+        if step == 5:
+            opt.param_groups[0]["lr"] = lrs[0] = 1.0e-4      # update_learning_rate (gaussian_model.py:499-505)
+        for p, gr in zip(params, grads):
+            p.grad = gr.clone()
+        opt.step()
+        ours = [oracle_adam.adam_step(o[0], gr.numpy(), o[1], o[2], step, lr, eps=1e-15) for o, gr, lr in zip(ours, grads, lrs)]
+    for p, o, q0 in zip(params, ours, p0):
+        st = opt.state[p]
+        # parameters are O(1): a last-ulp difference of one update is 6e-8 absolute, 7 updates accumulate a few
+        np.testing.assert_allclose(o[0], p.detach().numpy(), rtol=1e-6, atol=1e-7)
+        assert np.linalg.norm(o[0] - p.detach().numpy()) <= 1e-5 * np.linalg.norm(p.detach().numpy() - q0)
+        np.testing.assert_allclose(o[1], st["exp_avg"].numpy(), rtol=2e-6, atol=1e-6 * float(st["exp_avg"].abs().max()))   # a signed sum: cancellation
+        np.testing.assert_allclose(o[2], st["exp_avg_sq"].numpy(), rtol=2e-6, atol=1e-18)

@@ -58,8 +58,26 @@ def test_matches_reference_function_golden(path):
     assert rel_l2(npy(env_raw.grad), g["grad_env_raw"]) < 1e-3
 
 
-@pytest.mark.parametrize("P,N,He,fixed", [(30_000, 64, 16, False), (5_000, 384, 16, False), (2_000, 24, 128, True)])
+# env sizes pick the env-gradient mode of the backward: 16x32 warp-private tagged copies, 24x48
+# shared-memory atomics, 128x256 global atomics; (1,3) (5,7) (33,8): idle groups / lanes, N < group
+@pytest.mark.parametrize("P,N,He,fixed", [(30_000, 64, 16, False), (5_000, 384, 16, False), (2_000, 24, 128, True),
+                                          (3_000, 40, 24, False), (1, 3, 16, False), (5, 7, 16, False), (33, 8, 16, True)])
 def test_matches_pytorch_oracle(P, N, He, fixed):
+    _check_against_oracle(P, N, He, fixed)
+
+
+@pytest.mark.parametrize("group,env_mode", [(16, 2), (32, 2), (8, 1), (32, 1), (8, 0)])
+def test_kernel_variants_match_oracle(group, env_mode):
+    """Non-default kernel variants (r3dg_tune): lanes per Gaussian, env-gradient accumulation mode."""
+    from relightable3dgaussian_b200 import _lib
+    old = _lib.tune("shade_group", group), _lib.tune("shade_env_mode", env_mode)
+    try:
+        _check_against_oracle(4_001, 40, 16, False)
+    finally:
+        _lib.tune("shade_group", old[0]); _lib.tune("shade_env_mode", old[1])
+
+
+def _check_against_oracle(P, N, He, fixed):
     from oracle import oracle_shading as osh
     c = {k: v.cuda() for k, v in shading_case(P, N, He, seed=7).items()}
     rot = torch.tensor([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]]).cuda()

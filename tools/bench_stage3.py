@@ -88,7 +88,70 @@ def shade(P, N):
                           ours_GBps_of_baked_tensors=2 * P * N * 20 / t_o / 1e6)), flush=True)
 
 
+def shade_kernels(P, N):
+    """Kernel-only timing of r3dg_render_equation_forward / _backward (no autograd glue) for every
+    kernel variant (r3dg_tune): lanes per Gaussian x env-gradient mode."""
+    import ctypes
+    from relightable3dgaussian_b200 import _lib
+    lib = _lib.load()
+    c = {k: v.cuda() for k, v in shading_case(P, N, 16, seed=2).items()}
+    env = F.softplus(c["env_raw"])[0].contiguous()
+    f = dict(dtype=torch.float32, device="cuda")
+    outs = [torch.empty((P, 3), **f) for _ in range(3)]
+    grads = dict(d_base=torch.empty((P, 3), **f), d_rough=torch.empty((P, 1), **f), d_view=torch.empty((P, 3), **f),
+                 d_inc=torch.empty((P, 16, 3), **f), d_env=torch.empty(env.shape, **f))
+    a = _lib.ShadeArgs()
+    a.P, a.N, a.sh_coeffs, a.env_h, a.env_w = P, N, 16, env.shape[0], env.shape[1]
+    (a.base_color, a.roughness, a.normals, a.viewdirs, a.incidents, a.env, a.visibility, a.incident_dirs, a.incident_areas) = [
+        c[k].contiguous().data_ptr() for k in ("base_color", "roughness", "normals", "viewdirs", "incidents")] + [env.data_ptr()] + [
+        c[k].contiguous().data_ptr() for k in ("visibility", "incident_dirs", "incident_areas")]
+    a.pbr, a.diffuse_light, a.specular = [t.data_ptr() for t in outs]
+    a.dL_dpbr, a.dL_ddiffuse_light = c["cot_pbr"].data_ptr(), c["cot_diffuse"].data_ptr()
+    a.dL_dbase_color, a.dL_droughness, a.dL_dviewdirs = grads["d_base"].data_ptr(), grads["d_rough"].data_ptr(), grads["d_view"].data_ptr()
+    a.dL_dincidents, a.dL_denv = grads["d_inc"].data_ptr(), grads["d_env"].data_ptr()
+    st = torch.cuda.current_stream().cuda_stream
+    ref = None
+    for group, mode in ((8, 2), (16, 2), (32, 2), (8, 1), (32, 1), (8, 0)):
+        old = _lib.tune("shade_group", group), _lib.tune("shade_env_mode", mode)
+        t_f = timeit(lambda: _lib.check(lib.r3dg_render_equation_forward(ctypes.byref(a), st), "fwd"), n=10, warm=2)
+        t_b = timeit(lambda: _lib.check(lib.r3dg_render_equation_backward(ctypes.byref(a), st), "bwd"), n=10, warm=2)
+        sig = [float(outs[0].double().sum()), float(grads["d_inc"].double().abs().sum()), float(grads["d_env"].double().abs().sum())]
+        ref = ref or sig
+        _lib.tune("shade_group", old[0]); _lib.tune("shade_env_mode", old[1])
+        print(json.dumps(dict(what="shading kernels", P=P, N=N, group=group, env_mode=mode, fwd_ms=t_f, bwd_ms=t_b,
+                              fwd_GBps=P * N * 20 / t_f / 1e6, bwd_GBps=P * N * 20 / t_b / 1e6,
+                              checksum_rel=[abs(x - y) / (abs(y) + 1e-30) for x, y in zip(sig, ref)])), flush=True)
+
+
+def adam(P):
+    """Fused optimiser step over the reference's stage-1 parameter groups (62 floats per Gaussian)
+    vs torch.optim.Adam (foreach) and torch's own fused implementation."""
+    from relightable3dgaussian_b200.optim import FusedAdam
+    shapes = [(3,), (3,), (4,), (3,), (1,), (1, 3), (15, 3)]
+    res = {}
+    for name, cls, kw in (("ours", FusedAdam, {}), ("torch_foreach", torch.optim.Adam, {}), ("torch_fused", torch.optim.Adam, {"fused": True})):
+        ps = [torch.randn((P,) + s, device="cuda").requires_grad_(True) for s in shapes]
+        for q in ps:
+            q.grad = torch.randn_like(q) * 1e-3
+        opt = cls([{"params": [q], "lr": 1e-3} for q in ps], lr=0.0, eps=1e-15, **kw)
+        res[name] = timeit(opt.step, n=20, warm=3)
+        del opt, ps
+    elems = P * 62
+    print(json.dumps(dict(what="adam step", P=P, elems=elems, ours_ms=res["ours"], torch_foreach_ms=res["torch_foreach"],
+                          torch_fused_ms=res["torch_fused"], ours_GBps=elems * 28 / res["ours"] / 1e6,
+                          speedup_vs_foreach=res["torch_foreach"] / res["ours"], speedup_vs_torch_fused=res["torch_fused"] / res["ours"])), flush=True)
+
+
 if __name__ == "__main__":
-    bvh(300_000, 64)
-    shade(300_000, 64)
-    shade(1_000_000, 32)
+    which = sys.argv[1:] or ["bvh", "shade", "kernels", "adam"]
+    if "bvh" in which:
+        bvh(300_000, 64)
+    if "shade" in which:
+        shade(300_000, 64)
+        shade(1_000_000, 32)
+    if "kernels" in which:
+        shade_kernels(300_000, 64)
+        shade_kernels(1_000_000, 32)
+        shade_kernels(100_000, 384)
+    if "adam" in which:
+        adam(1_000_000)
