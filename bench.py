@@ -133,7 +133,7 @@ def make_inputs(cfg, device):
 
 def bench_ours(args, cfg, rank, local, world):
     from relightable3dgaussian_b200 import _C_raster as C, _lib, dist as rdist
-    from relightable3dgaussian_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer, set_deferred_count
+    from relightable3dgaussian_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer, set_deferred_count, set_grad_exchange
     import torch.distributed as tdist
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
@@ -147,7 +147,17 @@ def bench_ours(args, cfg, rank, local, world):
     camd = [dict(view=d(c.viewmatrix), proj=d(c.projmatrix), pos=d(c.campos), c=c) for c in cams]
     dcot = {k: d(v) for k, v in cot.items()}
     E = torch.Tensor([])
-    bucket = rdist.GradBucket(P, S, M, dev)
+    # exchange step (N > 1): dense = one all-reduce of all per-Gaussian gradients (256 MB); factored = all-reduce
+    # of the dense rest (64 MB) + all-gather of the rank-1 SH-gradient factors (12 MB per rank) + local rebuild
+    factored = world > 1 and args.exchange == "factored"
+    bucket = rdist.FactoredGradExchange(P, S, M, dev) if factored else rdist.GradBucket(P, S, M, dev)
+    campos_tab = {}
+
+    def campos_all(i):      # camera centres of the views the ranks render in step i, rank order
+        key = (i * world) % cfg["views"]
+        if key not in campos_tab:
+            campos_tab[key] = torch.stack([camd[rdist.view_for_rank(i, r, world, cfg["views"])]["pos"] for r in range(world)]).contiguous()
+        return campos_tab[key]
     stats = {}
 
     def step_resident(i):
@@ -160,7 +170,10 @@ def bench_ours(args, cfg, rank, local, world):
                                        c.tanfovx, c.tanfovy, dcot["color"], dcot["opacity"], dcot["depth"],
                                        dcot["feature"], shs, 3, cam["pos"], out[10], out[0], out[11], out[12],
                                        True, False, _out=bucket.views)
-        bucket.allreduce_mean()
+        if factored:
+            bucket.exchange(means3D, campos_all(i), 3)
+        else:
+            bucket.allreduce_mean()
 
     def timed(fn, steps, warmup, profile=False):
         for i in range(warmup):
@@ -247,9 +260,11 @@ def bench_ours(args, cfg, rank, local, world):
         loss = (color - gd).abs().mean() + 0.01 * opacity.mean() + 0.01 * depth.mean() + 0.01 * feature.square().mean()
         for p_ in params:
             p_.grad = None
+        if factored:
+            set_grad_exchange(bucket, campos_all(i))       # backward runs the collectives; grads arrive averaged
         loss.backward()
         free_ev[slot].record(cur)
-        if world > 1:
+        if world > 1 and not factored:
             for p_ in params:                               # averaged in place, largest (SH, 192 MB) first in flight
                 tdist.all_reduce(p_.grad, op=tdist.ReduceOp.AVG)
         loss_host[i % 64:i % 64 + 1].copy_(loss.detach().reshape(1), non_blocking=True)
@@ -258,6 +273,7 @@ def bench_ours(args, cfg, rank, local, world):
     set_deferred_count(True)          # documented opt-in of the public API: no host round trip mid-step
     ms_e, _, _ = timed(step_e2e, e_steps, min(args.warmup, 3))
     set_deferred_count(False)
+    set_grad_exchange(None)
     e2e_value = world * e_steps / (ms_e / 1e3)
 
     res = None
@@ -278,7 +294,9 @@ def bench_ours(args, cfg, rank, local, world):
             "config": {"workload": f"rasterizer fwd+bwd, {cfg['recipe']} seed {cfg['seed']}, P={P}, {W}x{H}, S={S}, SH deg 3, "
                                    f"{cfg['views']}-camera ring, one view per GPU per step",
                        "P": P, "W": W, "H": H, "S": S, "num_rendered": R, "P_visible": Pv,
-                       "parallelism": f"view-parallel x{world}, 1 NCCL all-reduce of {bucket.bytes() / 1e6:.0f} MB grads/step" if world > 1 else "single GPU",
+                       "parallelism": (f"view-parallel x{world}, per step 1 NCCL all-reduce of {bucket.dense.bytes() / 1e6:.0f} MB dense grads + 1 all-gather of "
+                                       f"{bucket.factor.numel() * 4 / 1e6:.0f} MB SH-gradient factors per rank + local rebuild" if factored else
+                                       f"view-parallel x{world}, 1 NCCL all-reduce of {bucket.bytes() / 1e6:.0f} MB grads/step") if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (236 MB Gaussian parameters + ~190 MB binning per step vs 126 MB L2)"},
             "e2e": {"value": e2e_value, "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e_steps, "ms_per_step": ms_e / e_steps,
@@ -400,6 +418,8 @@ def main():
     ap.add_argument("--H", type=int, default=None)
     ap.add_argument("--S", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="dense", choices=["dense", "factored"],
+                    help="N > 1: gradient exchange per step (DESIGN.md section 5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     cfg = dict(HEADLINE)

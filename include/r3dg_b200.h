@@ -109,9 +109,10 @@ typedef struct r3dg_raster_bwd_args {
     float* dL_dmeans3D;            /* [P,3] */
     float* dL_dfeatures;           /* [P,S] */
     float* dL_dcov3D;              /* [P,6] */
-    float* dL_dsh;                 /* [P,M,3] */
+    float* dL_dsh;                 /* [P,M,3]; may be NULL when dL_dsh_factor is given */
     float* dL_dscales;             /* [P,3] */
     float* dL_drotations;          /* [P,4] */
+    float* dL_dsh_factor;          /* [P,3] or NULL: the view's rank-1 factor of dL_dsh, see r3dg_sh_grad_from_factors */
     /* work buffers written by the matching forward */
     void* geom;   size_t geom_bytes;
     void* img;    size_t img_bytes;
@@ -121,6 +122,19 @@ typedef struct r3dg_raster_bwd_args {
 /* Replaces CudaRasterizer::Rasterizer::backward (rasterizer.h:67-100, rasterizer_impl.cu:384-491)
  * == `_C.rasterize_gaussians_backward` (rasterize_points.cu:143-235). */
 int r3dg_raster_backward(const r3dg_raster_bwd_args* args, r3dg_stream_t stream);
+
+/* Multi-GPU exchange step (the reference is single-GPU).  For one view the SH
+ * gradient is rank-1 per Gaussian: dL_dsh[g,k,:] = basis_k(normalize(mean_g - campos)) * f[g,:]
+ * with f = dL_dRGB gated by the forward's clamp flags (backward.cu:20-139) and zero for culled
+ * Gaussians — r3dg_raster_backward writes f to `dL_dsh_factor`.  Instead of all-reducing the dense
+ * [P,M,3] tensor (192 B per Gaussian) the ranks all-gather f (12 B per Gaussian and view) and every
+ * rank rebuilds the reduced gradient locally:
+ *     dL_dsh[g,k,c] = scale * sum_v basis_k(normalize(means3D[g] - campos[v])) * factors[v][g][c]
+ * for k < (D+1)^2 (zero above), v = 0..num_views-1 in order (deterministic, identical on every
+ * rank).  campos: [num_views,3]; factors: [num_views,P,3]; dL_dsh: [P,M,3] (every element written). */
+int r3dg_sh_grad_from_factors(int P, int D, int M, int num_views, const float* means3D,
+                              const float* campos, const float* factors, float scale,
+                              float* dL_dsh, r3dg_stream_t stream);
 
 /* Replaces Rasterizer::markVisible (rasterizer_impl.cu:141-153) == `_C.mark_visible`
  * (rasterize_points.cu:237-256).  present: uint8/bool [P]. */
@@ -259,10 +273,13 @@ int r3dg_prof_end(float* stage_ms /* [9] */, int* fwd_calls, int* bwd_calls);
  * kernel variant changes).  Sets knob `key` to `value`, stores the old value in *previous (may be
  * NULL); R3DG_ERR_UNSUPPORTED for an unknown key, R3DG_ERR_BAD_ARG for an out-of-range value.
  *   "shade_group"     lanes per Gaussian in the shading kernels: 8 (default), 16, 32
+ *   "shade_fwd_variant" / "shade_bwd_variant"  0 per-Gaussian SH state in registers, 1 incident
+ *                     coefficients in shared memory, 2 (backward) + gradient accumulators in shared memory
  *   "shade_env_mode"  env-map gradient accumulation in r3dg_render_equation_backward:
  *                     2 warp-private tagged copies (default), 1 shared-memory atomics,
  *                     0 global atomics; larger textures fall back to the lower modes
- * Initial values can also be given by the environment (R3DG_SHADE_GROUP, R3DG_SHADE_ENV_MODE). */
+ * Initial values can also be given by the environment (R3DG_SHADE_GROUP, R3DG_SHADE_ENV_MODE,
+ * R3DG_SHADE_FWD_VARIANT, R3DG_SHADE_BWD_VARIANT). */
 int r3dg_tune(const char* key, int value, int* previous);
 
 /* Library identification: returns a static string such as "r3dg_b200 0.1 sm_100a". */

@@ -202,6 +202,50 @@ _C4 = np.array([2.5033429417967046, -1.7701307697799304, 0.9461746957575601, -0.
                 -1.7701307697799304, 0.6258357354491761], np.float32)
 
 
+def sh_basis(deg, dirs):
+    """Real SH basis values [..., (deg+1)^2] with the reference's constants and signs
+    (auxiliary.h:22-39 == utils/sh_utils.py:71-128), float32."""
+    d = np.asarray(dirs, np.float32)
+    x, y, z = d[..., 0], d[..., 1], d[..., 2]
+    f = np.float32
+    w = [np.full(x.shape, 0.28209479177387814, np.float32)]
+    if deg > 0:
+        w += [f(-0.4886025119029199) * y, f(0.4886025119029199) * z, f(-0.4886025119029199) * x]
+    if deg > 1:
+        xx, yy, zz, xy, yz, xz = x * x, y * y, z * z, x * y, y * z, x * z
+        w += [f(1.0925484305920792) * xy, f(-1.0925484305920792) * yz, f(0.31539156525252005) * (f(2) * zz - xx - yy),
+              f(-1.0925484305920792) * xz, f(0.5462742152960396) * (xx - yy)]
+    if deg > 2:
+        w += [f(-0.5900435899266435) * y * (f(3) * xx - yy), f(2.890611442640554) * xy * z,
+              f(-0.4570457994644658) * y * (f(4) * zz - xx - yy), f(0.3731763325901154) * z * (f(2) * zz - f(3) * xx - f(3) * yy),
+              f(-0.4570457994644658) * x * (f(4) * zz - xx - yy), f(1.445305721320277) * z * (xx - yy),
+              f(-0.5900435899266435) * x * (xx - f(3) * yy)]
+    return np.stack(w, axis=-1).astype(np.float32)
+
+
+def sh_grad_factor(bwd, fwd):
+    """The per-view rank-1 factor of dL_dsh: dL_dRGB gated by the forward's clamp flags
+    (backward.cu:20-139 `dL_dRGB.x *= clamped[3*idx+0] ? 0 : 1`), zero for culled Gaussians."""
+    pre = fwd["pre"]
+    gate = (pre["clamped"].reshape(-1, 3) == 0) & (pre["radii"].reshape(-1, 1) > 0)
+    return (bwd["dL_dcolors"] * gate).astype(np.float32)
+
+
+def sh_grad_from_factors(means3D, campos_all, factors, deg, M, scale):
+    """Restatement of the multi-GPU exchange identity (include/r3dg_b200.h: r3dg_sh_grad_from_factors):
+    dL_dsh[g,k,:] = scale * sum_v basis_k(normalize(mean_g - campos_v)) * factors[v][g,:]; the
+    per-view term is backward.cu:20-139's `dL_dsh[k] = basis_k * dL_dRGB`."""
+    means3D = np.asarray(means3D, np.float32)
+    P = means3D.shape[0]
+    out = np.zeros((P, M, 3), np.float32)
+    n = (deg + 1) ** 2
+    for v in range(len(campos_all)):
+        d = means3D - np.asarray(campos_all[v], np.float32)[None]
+        d = d / np.sqrt((d * d).sum(-1, keepdims=True), dtype=np.float32)
+        out[:, :n] += sh_basis(deg, d)[:, :, None] * np.asarray(factors[v], np.float32)[:, None, :]
+    return (out * np.float32(scale)).astype(np.float32)
+
+
 def eval_sh(deg, sh, dirs):
     assert 0 <= deg <= 4
     sh = np.asarray(sh, np.float32)

@@ -199,7 +199,16 @@ def rasterize_gaussians_backward(background, means3D, features, radii, colors, s
     dL_dcolors = _alloc("colors", (P, 3))
     dL_dopacity = _alloc("opacity", (P, 1))
     dL_dcov3D = _alloc("cov3D", (P, 6))
-    dL_dsh = _alloc("sh", (P, M, 3))
+    # multi-GPU exchange (dist.FactoredGradExchange): `_out["sh_factor"]` [P,3] asks for the view's rank-1
+    # factor of dL_dsh INSTEAD of the dense tensor (returned empty), see r3dg_sh_grad_from_factors
+    sh_factor = _out.get("sh_factor") if _out is not None else None
+    if sh_factor is not None:
+        assert sh_factor.is_contiguous() and tuple(sh_factor.shape) == (P, 3) and sh_factor.dtype == torch.float32
+        if M == 0:
+            raise RuntimeError("the SH-gradient factor needs `sh` inputs (colors_precomp has no SH gradient)")
+        dL_dsh = _alloc("sh", (P, M, 3)) if "sh" in _out else torch.empty((0,), **f32)     # both on request (tests)
+    else:
+        dL_dsh = _alloc("sh", (P, M, 3))
     dL_dscales = _alloc("scales", (P, 3))
     dL_drotations = _alloc("rotations", (P, 4))
     if P != 0:
@@ -217,6 +226,7 @@ def rasterize_gaussians_backward(background, means3D, features, radii, colors, s
         a.dL_dopacity = _ptr(dL_dopacity); a.dL_dmeans3D = _ptr(dL_dmeans3D)
         a.dL_dfeatures = _ptr(dL_dfeatures); a.dL_dcov3D = _ptr(dL_dcov3D); a.dL_dsh = _ptr(dL_dsh)
         a.dL_dscales = _ptr(dL_dscales); a.dL_drotations = _ptr(dL_drotations)
+        a.dL_dsh_factor = _ptr(sh_factor)
         a.geom = geomBuffer.data_ptr(); a.geom_bytes = geomBuffer.numel()
         a.img = imageBuffer.data_ptr(); a.img_bytes = imageBuffer.numel()
         a.binning = binningBuffer.data_ptr(); a.binning_bytes = binningBuffer.numel()

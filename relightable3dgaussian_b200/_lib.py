@@ -40,7 +40,7 @@ class RasterBwdArgs(ctypes.Structure):
         [(n, c_void_p) for n in ("dL_dout_color", "dL_dout_opacity", "dL_dout_depth",
                                  "dL_dout_feature", "dL_dmeans2D", "dL_dcolors", "dL_dopacity",
                                  "dL_dmeans3D", "dL_dfeatures", "dL_dcov3D", "dL_dsh",
-                                 "dL_dscales", "dL_drotations")] +
+                                 "dL_dscales", "dL_drotations", "dL_dsh_factor")] +
         [("geom", c_void_p), ("geom_bytes", c_size_t), ("img", c_void_p), ("img_bytes", c_size_t),
          ("binning", c_void_p), ("binning_bytes", c_size_t)])
 
@@ -72,6 +72,7 @@ SYMBOLS = [
     ("r3dg_raster_img_n_contrib_offset", c_size_t, [c_int, c_int]),
     ("r3dg_raster_forward", c_int, [ctypes.POINTER(RasterFwdArgs), c_void_p]),
     ("r3dg_raster_backward", c_int, [ctypes.POINTER(RasterBwdArgs), c_void_p]),
+    ("r3dg_sh_grad_from_factors", c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
     ("r3dg_mark_visible", c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("r3dg_bvh_build_tmp_bytes", c_size_t, [c_int]),
     ("r3dg_bvh_trace_tmp_bytes", c_size_t, [c_int]),

@@ -121,8 +121,8 @@ int r3dg_raster_backward(const r3dg_raster_bwd_args* a, r3dg_stream_t stream_) {
     return 0;
 }
 
-extern unsigned long long r3dg_adam_launches;
-unsigned long long r3dg_launch_count(void) { return g_launches + r3dg_adam_launches; }
+extern unsigned long long r3dg_adam_launches, r3dg_shx_launches;
+unsigned long long r3dg_launch_count(void) { return g_launches + r3dg_adam_launches + r3dg_shx_launches; }
 
 int r3dg_tune(const char* key, int value, int* previous) {
     if (!key) return R3DG_ERR_BAD_ARG;

@@ -24,6 +24,7 @@ struct ProjBwdParams {
     const uint8_t* clamped;
     float *dL_dmeans2D, *dL_dcolors, *dL_dopacity, *dL_dmeans3D, *dL_dfeatures, *dL_dcov3D, *dL_dsh,
         *dL_dscales, *dL_drotations;
+    float* dL_dsh_factor;       // [P,3] gated dL_dRGB (multi-GPU exchange, sh_exchange.cu); dL_dsh may then be NULL
 };
 
 __device__ __forceinline__ void cov3d_plain(const float* s3, float mod, const float* q, float* c6,
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, 5) projection_bwd_kernel(const P
     const float* proj = sPr;
     // (visibility comes from tiles_touched: the record row of a culled Gaussian is never written)
 
-    float dmean2[3] = {0, 0, 0}, dcol[3] = {0, 0, 0}, dop = 0, dmean3[3] = {0, 0, 0};
+    float dmean2[3] = {0, 0, 0}, dcol[3] = {0, 0, 0}, dop = 0, dmean3[3] = {0, 0, 0}, dfac[3] = {0, 0, 0};
     float dcov[6] = {0, 0, 0, 0, 0, 0}, dscale[3] = {0, 0, 0}, drot[4] = {0, 0, 0, 0};
 
     // feature gradients: straight copy-out of the packed row
@@ -231,6 +232,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, 5) projection_bwd_kernel(const P
             const float x = dox / len, y = doy / len, z = doz / len;
             float* slab = sSH + threadIdx.x;                 // element (k, c) at slab[(3k + c) * SLAB_LD]
             const float dRGB[3] = {(cl & 1u) ? 0.f : dcol[0], (cl & 2u) ? 0.f : dcol[1], (cl & 4u) ? 0.f : dcol[2]};
+            dfac[0] = dRGB[0]; dfac[1] = dRGB[1]; dfac[2] = dRGB[2];
             float w[16], wx[16], wy[16], wz[16];   // basis and its derivatives w.r.t. x,y,z
 #pragma unroll
             for (int k = 0; k < 16; ++k) { w[k] = 0.f; wx[k] = 0.f; wy[k] = 0.f; wz[k] = 0.f; }
@@ -276,9 +278,11 @@ __global__ void __launch_bounds__(PROJ_THREADS, 5) projection_bwd_kernel(const P
                     if (act) { s0 = slab[(3 * k) * SLAB_LD]; s1 = slab[(3 * k + 1) * SLAB_LD]; s2 = slab[(3 * k + 2) * SLAB_LD]; }
                     const float dotc = s0 * dRGB[0] + s1 * dRGB[1] + s2 * dRGB[2];
                     ddx += wx[k] * dotc; ddy += wy[k] * dotc; ddz += wz[k] * dotc;
-                    slab[(3 * k) * SLAB_LD] = act ? w[k] * dRGB[0] : 0.f;        // in place: sh -> dL/dsh
-                    slab[(3 * k + 1) * SLAB_LD] = act ? w[k] * dRGB[1] : 0.f;
-                    slab[(3 * k + 2) * SLAB_LD] = act ? w[k] * dRGB[2] : 0.f;
+                    if (p.dL_dsh) {
+                        slab[(3 * k) * SLAB_LD] = act ? w[k] * dRGB[0] : 0.f;        // in place: sh -> dL/dsh
+                        slab[(3 * k + 1) * SLAB_LD] = act ? w[k] * dRGB[1] : 0.f;
+                        slab[(3 * k + 2) * SLAB_LD] = act ? w[k] * dRGB[2] : 0.f;
+                    }
                 }
             }
             // dnormvdv (auxiliary.h:105-116)
@@ -288,10 +292,10 @@ __global__ void __launch_bounds__(PROJ_THREADS, 5) projection_bwd_kernel(const P
             dmean3[1] += (-dox * doy * ddx + (sum2 - doy * doy) * ddy - doz * doy * ddz) * invsum32;
             dmean3[2] += (-dox * doz * ddx - doy * doz * ddy + (sum2 - doz * doz) * ddz) * invsum32;
         }
-    } else if (p.shs) {
+    } else if (p.shs && p.dL_dsh) {
         for (int k = 0; k < rowf; ++k) sSH[k * SLAB_LD + threadIdx.x] = 0.f;
     }
-    if (p.shs) {                                    // coalesced write-back of the dL/dsh slab
+    if (p.shs && p.dL_dsh) {                        // coalesced write-back of the dL/dsh slab
         __syncthreads();
         const int total = nvalid * rowf;
         float* dst = p.dL_dsh + (size_t)block_base * rowf;
@@ -318,6 +322,10 @@ __global__ void __launch_bounds__(PROJ_THREADS, 5) projection_bwd_kernel(const P
         p.dL_dscales[3 * (size_t)idx + k] = dscale[k];
     }
     p.dL_dopacity[idx] = dop;
+    if (p.dL_dsh_factor) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) p.dL_dsh_factor[3 * (size_t)idx + k] = dfac[k];
+    }
 #pragma unroll
     for (int k = 0; k < 6; ++k) p.dL_dcov3D[6 * (size_t)idx + k] = dcov[k];
     *reinterpret_cast<float4*>(p.dL_drotations + 4 * (size_t)idx) = make_float4(drot[0], drot[1], drot[2], drot[3]);
@@ -339,6 +347,7 @@ int launch_projection_backward(const r3dg_raster_bwd_args& a, const GeomLayout& 
     p.dL_dmeans2D = a.dL_dmeans2D; p.dL_dcolors = a.dL_dcolors; p.dL_dopacity = a.dL_dopacity;
     p.dL_dmeans3D = a.dL_dmeans3D; p.dL_dfeatures = a.dL_dfeatures; p.dL_dcov3D = a.dL_dcov3D;
     p.dL_dsh = a.dL_dsh; p.dL_dscales = a.dL_dscales; p.dL_drotations = a.dL_drotations;
+    p.dL_dsh_factor = a.dL_dsh_factor;
     const size_t sh_smem = a.shs ? (size_t)3 * a.M * SLAB_LD * sizeof(float) : 0;
     projection_bwd_kernel<<<(a.P + PROJ_THREADS - 1) / PROJ_THREADS, PROJ_THREADS, sh_smem, stream>>>(p);
     R3DG_CUDA_TRY(cudaGetLastError());

@@ -1,0 +1,131 @@
+// Multi-GPU exchange step: rebuild the view-averaged SH gradient from the
+// all-gathered per-view rank-1 factors instead of all-reducing the dense [P,M,3] tensor.
+//
+// For one view the reference's SH backward (backward.cu:20-139) gives
+//     dL_dsh[g,k,:] = basis_k(normalize(mean_g - campos)) * f[g,:],    f = clamp-gated dL_dRGB
+// so 192 B of every Gaussian's 248 B gradient row are an outer product of 16 numbers every rank can
+// recompute (means3D is replicated, the step's camera centres are known to all ranks) with 3
+// numbers only the rendering rank has.  Exchanging f (12 B per Gaussian and view, all-gather)
+// and summing the outer products locally replaces 2*(N-1)/N * 192 B of all-reduce traffic per
+// Gaussian and GPU by (N-1) * 12 B, and the projection backward no longer writes the dense tensor.
+//
+// B200 design notes: HBM-bound (reads 12 B + N*12 B, writes 192 B per Gaussian); one thread per
+// Gaussian accumulates its 3*M values in a transposed shared slab column (conflict-free), the CTA
+// writes the [128][3M] slab back with coalesced 16-byte stores — the same slab scheme as
+// projection_bwd.cu.  The basis is evaluated with the expressions of projection_bwd.cu so a
+// one-view "exchange" reproduces that kernel's dL_dsh.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace r3dg {
+
+#define SHX_THREADS 128
+#define SHX_LD (SHX_THREADS + 1)
+#define SHX_MAX_VIEWS 64
+
+struct ShxParams {
+    int P, D, M, num_views;
+    const float *means3D, *campos, *factors;
+    float scale;
+    float* dL_dsh;
+};
+
+__device__ __forceinline__ void shx_basis(int D, float x, float y, float z, float* w) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) w[k] = 0.f;
+    const float C1 = 0.4886025119029199f;
+    w[0] = 0.28209479177387814f;
+    if (D > 0) {
+        w[1] = -C1 * y; w[2] = C1 * z; w[3] = -C1 * x;
+        if (D > 1) {
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            w[4] = 1.0925484305920792f * xy; w[5] = -1.0925484305920792f * yz; w[6] = 0.31539156525252005f * (2.f * zz - xx - yy);
+            w[7] = -1.0925484305920792f * xz; w[8] = 0.5462742152960396f * (xx - yy);
+            if (D > 2) {
+                w[9] = -0.5900435899266435f * y * (3.f * xx - yy); w[10] = 2.890611442640554f * xy * z;
+                w[11] = -0.4570457994644658f * y * (4.f * zz - xx - yy);
+                w[12] = 0.3731763325901154f * z * (2.f * zz - 3.f * xx - 3.f * yy);
+                w[13] = -0.4570457994644658f * x * (4.f * zz - xx - yy);
+                w[14] = 1.445305721320277f * z * (xx - yy); w[15] = -0.5900435899266435f * x * (xx - 3.f * yy);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SHX_THREADS) sh_from_factors_kernel(const ShxParams p) {
+    extern __shared__ float sOut[];                       // [3M][SHX_LD]
+    __shared__ float sCam[3 * SHX_MAX_VIEWS];
+    for (int i = threadIdx.x; i < 3 * p.num_views; i += SHX_THREADS) sCam[i] = p.campos[i];
+    __syncthreads();
+    const int block_base = blockIdx.x * SHX_THREADS;
+    const int idx = block_base + threadIdx.x;
+    const int rowf = 3 * p.M;
+    const int nvalid = min(SHX_THREADS, p.P - block_base);
+    if (idx < p.P) {
+        const float mx = p.means3D[3 * (size_t)idx], my = p.means3D[3 * (size_t)idx + 1], mz = p.means3D[3 * (size_t)idx + 2];
+        float acc[48];
+#pragma unroll
+        for (int q = 0; q < 48; ++q) acc[q] = 0.f;
+        for (int v = 0; v < p.num_views; ++v) {
+            const float* f = p.factors + ((size_t)v * p.P + idx) * 3;
+            const float f0 = f[0], f1 = f[1], f2 = f[2];
+            if (f0 == 0.f && f1 == 0.f && f2 == 0.f) continue;      // culled in this view (or fully clamped): contributes exact zeros
+            const float dox = mx - sCam[3 * v], doy = my - sCam[3 * v + 1], doz = mz - sCam[3 * v + 2];
+            const float len = sqrtf(dox * dox + doy * doy + doz * doz);
+            float w[16];
+            shx_basis(p.D, dox / len, doy / len, doz / len, w);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                acc[3 * k] += w[k] * f0; acc[3 * k + 1] += w[k] * f1; acc[3 * k + 2] += w[k] * f2;
+            }
+        }
+        float* col = sOut + threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if (k < p.M) {
+                col[(3 * k) * SHX_LD] = acc[3 * k] * p.scale;
+                col[(3 * k + 1) * SHX_LD] = acc[3 * k + 1] * p.scale;
+                col[(3 * k + 2) * SHX_LD] = acc[3 * k + 2] * p.scale;
+            }
+    }
+    __syncthreads();
+    const int total = nvalid * rowf;
+    float* dst = p.dL_dsh + (size_t)block_base * rowf;
+    if ((rowf & 3) == 0) {
+        float4* dst4 = reinterpret_cast<float4*>(dst);
+        for (int i4 = threadIdx.x; i4 < total / 4; i4 += SHX_THREADS) {
+            const int i = 4 * i4, t = i / rowf, k = i - t * rowf;
+            dst4[i4] = make_float4(sOut[(k + 0) * SHX_LD + t], sOut[(k + 1) * SHX_LD + t], sOut[(k + 2) * SHX_LD + t], sOut[(k + 3) * SHX_LD + t]);
+        }
+    } else {
+        for (int i = threadIdx.x; i < total; i += SHX_THREADS) {
+            const int t = i / rowf, k = i - t * rowf;
+            dst[i] = sOut[k * SHX_LD + t];
+        }
+    }
+}
+
+}  // namespace r3dg
+
+using namespace r3dg;
+extern "C" {
+
+unsigned long long r3dg_shx_launches = 0;      // folded into r3dg_launch_count (api.cu)
+
+int r3dg_sh_grad_from_factors(int P, int D, int M, int num_views, const float* means3D, const float* campos,
+                              const float* factors, float scale, float* dL_dsh, r3dg_stream_t stream) {
+    if (P < 0 || D < 0 || D > 3 || M < 1 || M > 16 || (D + 1) * (D + 1) > M || num_views < 1) return R3DG_ERR_BAD_ARG;
+    if (num_views > SHX_MAX_VIEWS) return R3DG_ERR_UNSUPPORTED;
+    if (P == 0) return 0;
+    if (!means3D || !campos || !factors || !dL_dsh) return R3DG_ERR_BAD_ARG;
+    ShxParams p;
+    p.P = P; p.D = D; p.M = M; p.num_views = num_views;
+    p.means3D = means3D; p.campos = campos; p.factors = factors; p.scale = scale; p.dL_dsh = dL_dsh;
+    const size_t smem = (size_t)3 * M * SHX_LD * sizeof(float);
+    sh_from_factors_kernel<<<(P + SHX_THREADS - 1) / SHX_THREADS, SHX_THREADS, smem, (cudaStream_t)stream>>>(p);
+    R3DG_CUDA_TRY(cudaGetLastError());
+    ++r3dg_shx_launches;
+    return 0;
+}
+
+}  // extern "C"

@@ -86,6 +86,7 @@ struct GaussianOperands {
     float inc[48];
 };
 
+template <bool INC_REGS>
 __device__ __forceinline__ void load_operands(const ShadeArgs& a, int g, GaussianOperands& o) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) { o.base[c] = a.base_color[3 * (size_t)g + c]; o.n[c] = a.normals[3 * (size_t)g + c]; }
@@ -101,9 +102,27 @@ __device__ __forceinline__ void load_operands(const ShadeArgs& a, int g, Gaussia
     const float al = o.rough * o.rough;
     o.a2 = al * al;
     o.k = (al + 2.0f * o.rough + 1.0f) / 8.0f;
-    const float4* ip = reinterpret_cast<const float4*>(a.incidents + 48 * (size_t)g);
+    if (INC_REGS) {
+        const float4* ip = reinterpret_cast<const float4*>(a.incidents + 48 * (size_t)g);
 #pragma unroll
-    for (int q = 0; q < 12; ++q) { const float4 v = ip[q]; o.inc[4 * q] = v.x; o.inc[4 * q + 1] = v.y; o.inc[4 * q + 2] = v.z; o.inc[4 * q + 3] = v.w; }
+        for (int q = 0; q < 12; ++q) { const float4 v = ip[q]; o.inc[4 * q] = v.x; o.inc[4 * q + 1] = v.y; o.inc[4 * q + 2] = v.z; o.inc[4 * q + 3] = v.w; }
+    }
+}
+
+// Kernel variants (r3dg_tune "shade_fwd_variant" / "shade_bwd_variant"): where the per-Gaussian SH
+// state lives.  0: registers.  1: the 48 incident-light coefficients of each group in shared memory
+// (broadcast LDS.128 reads, -48 registers).  2 (backward): additionally the 48 per-lane gradient
+// accumulators in shared memory ([48][threads], conflict-free), loaded back once per Gaussian for
+// the group reduction.  Fewer registers = more resident warps for a kernel that is bound by the
+// latency of its dependent arithmetic (acos / atan2 / divisions), not by HBM.
+#define SHADE_INC_STRIDE 52       // floats per group slot: 16-byte aligned, bank-staggered (52 mod 32 = 20)
+
+template <int G>
+__device__ __forceinline__ void stage_incidents(const ShadeArgs& a, int g, float* slot, int sub) {
+    const float4* src = reinterpret_cast<const float4*>(a.incidents + 48 * (size_t)g);
+    float4* dst = reinterpret_cast<float4*>(slot);
+    for (int q = sub; q < 12; q += G) dst[q] = src[q];
+    __syncwarp();
 }
 
 struct SampleEval {       // forward quantities of one (Gaussian, direction) pair
@@ -114,9 +133,9 @@ struct SampleEval {       // forward quantities of one (Gaussian, direction) pai
     float H[3], hn, NoL, NoV, NoH, VoH, NoL_r, NoV_r, NoH_r, VoH_r, p2, frac0, nom0, nom1, nom2, nom_r, nom;
 };
 
-template <bool SMEM_ENV>
+template <bool SMEM_ENV, bool INC_SMEM>
 __device__ __forceinline__ void eval_sample(const ShadeArgs& a, const GaussianOperands& o, const float* __restrict__ env,
-                                            float dx, float dy, float dz, float vis, SampleEval& e) {
+                                            const float* __restrict__ sinc, float dx, float dy, float dz, float vis, SampleEval& e) {
     // ---- environment + local SH light --------------------------------------------------------
     float ex = dx, ey = dy, ez = dz;
     if (a.transform) {                                     // dirs @ transform.T  (scene/envmap.py:39-42)
@@ -132,12 +151,25 @@ __device__ __forceinline__ void eval_sample(const ShadeArgs& a, const GaussianOp
         e.glob[c] = s * vis;
     }
     sh_basis3(dx, dy, dz, e.w);
+    if (INC_SMEM) {
+        float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        float s = 0.f;
+        for (int q = 0; q < 12; ++q) {
+            const float4 v = reinterpret_cast<const float4*>(sinc)[q];
+            const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int k = 0; k < 16; ++k) s += e.w[k] * o.inc[3 * k + c];      // eval_sh's left-to-right order
-        e.local_raw[c] = s;
+            for (int j = 0; j < 4; ++j) acc[(4 * q + j) % 3] += e.w[(4 * q + j) / 3] * vv[j];   // per channel still k = 0..15 in order
+            if (q % 3 == 2) asm volatile("" ::: "memory");     // keep at most 3 LDS.128 in flight: hoisting all 12 costs the 48 registers back
+        }
+        e.local_raw[0] = acc[0]; e.local_raw[1] = acc[1]; e.local_raw[2] = acc[2];
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) s += e.w[k] * o.inc[3 * k + c];      // eval_sh's left-to-right order
+            e.local_raw[c] = s;
+        }
     }
     e.ndi = fmaxf(o.n[0] * dx + o.n[1] * dy + o.n[2] * dz, 0.f);
     // ---- GGX_specular (neilf.py:374-406) ----------------------------------------------------------
@@ -198,12 +230,15 @@ __device__ __forceinline__ void group_reduce_scatter(float (&v)[V], int sub) {
     }
 }
 
-template <bool SMEM_ENV, int G>
-__global__ void __launch_bounds__(SHADE_THREADS) shade_fwd_kernel(const ShadeArgs a) {
-    extern __shared__ float s_env[];
+template <bool SMEM_ENV, int G, int VAR>
+__global__ void __launch_bounds__(SHADE_THREADS, VAR == 1 ? 6 : 1) shade_fwd_kernel(const ShadeArgs a) {
+    extern __shared__ __align__(16) float s_fwd[];     // [incident slots (VAR 1)][env texture (SMEM_ENV)]
     constexpr int GPW = 32 / G;                    // Gaussians per warp
+    constexpr int INC_FLOATS = VAR >= 1 ? SHADE_WARPS * GPW * SHADE_INC_STRIDE : 0;
+    float* s_env = s_fwd + INC_FLOATS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane & (G - 1), grp = lane / G;
+    float* sinc = s_fwd + (warp * GPW + grp) * SHADE_INC_STRIDE;
     if (SMEM_ENV) {
         for (int i = threadIdx.x; i < a.He * a.We * 3; i += SHADE_THREADS) s_env[i] = a.env[i];
         __syncthreads();
@@ -216,14 +251,15 @@ __global__ void __launch_bounds__(SHADE_THREADS) shade_fwd_kernel(const ShadeArg
         const bool valid = g_raw < a.P;
         const int g = valid ? g_raw : a.P - 1;      // idle groups of the last warp shade a copy, write nothing
         GaussianOperands o;
-        load_operands(a, g, o);
+        load_operands<VAR == 0>(a, g, o);
+        if (VAR >= 1) stage_incidents<G>(a, g, sinc, sub);
         float pbr[3] = {0, 0, 0}, spec[3] = {0, 0, 0}, diff[3] = {0, 0, 0}, ml[3] = {0, 0, 0}, mloc[3] = {0, 0, 0}, mg[3] = {0, 0, 0}, mv = 0;
         const size_t row = (size_t)g * a.N;
         for (int i = sub; i < a.N; i += G) {
             const float dx = a.dirs[3 * (row + i)], dy = a.dirs[3 * (row + i) + 1], dz = a.dirs[3 * (row + i) + 2];
             const float vis = a.visibility[row + i], area = a.areas[row + i];
             SampleEval e;
-            eval_sample<SMEM_ENV>(a, o, env, dx, dy, dz, vis, e);
+            eval_sample<SMEM_ENV, (VAR >= 1)>(a, o, env, sinc, dx, dy, dz, vis, e);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const float loc = fmaxf(e.local_raw[c], 0.f);
@@ -280,11 +316,18 @@ __device__ __forceinline__ void warp_private_add(float4* wg, volatile unsigned c
     }
 }
 
-template <int ENV_MODE, int G>
-__global__ void __launch_bounds__(SHADE_THREADS) shade_bwd_kernel(const ShadeArgs a) {
-    extern __shared__ __align__(16) float s_mem[];
+// resident CTAs the register allocation is pinned to: variant 1 -> 3 (<= 168 registers); variant 2 ->
+// 3 with the warp-private env copies (67 KB of shared memory per CTA), 5 otherwise (<= 102 registers)
+template <int ENV_MODE, int G, int VAR>
+__global__ void __launch_bounds__(SHADE_THREADS, VAR == 0 ? 1 : VAR == 1 ? 3 : (ENV_MODE == 2 ? 3 : 5)) shade_bwd_kernel(const ShadeArgs a) {
+    extern __shared__ __align__(16) float s_bwd[];    // [incident slots (VAR >= 1)][gradient accumulators (VAR 2)][env ...]
     constexpr bool SMEM_ENV = ENV_MODE != ENV_GLOBAL;
     constexpr int GPW = 32 / G;
+    constexpr int INC_FLOATS = VAR >= 1 ? SHADE_WARPS * GPW * SHADE_INC_STRIDE : 0;
+    constexpr int DINC_FLOATS = VAR == 2 ? 48 * SHADE_THREADS : 0;
+    float* s_mem = s_bwd + INC_FLOATS + DINC_FLOATS;
+    float* sinc = s_bwd + ((threadIdx.x >> 5) * GPW + (threadIdx.x & 31) / G) * SHADE_INC_STRIDE;
+    float* sdinc = s_bwd + INC_FLOATS + threadIdx.x;  // this lane's accumulator q lives at sdinc[q * SHADE_THREADS]
     constexpr int VP = (48 + G - 1) / G * G;         // SH-gradient row padded to a multiple of G
     constexpr int RQ = VP / G;                       // finished components per lane
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -312,7 +355,8 @@ __global__ void __launch_bounds__(SHADE_THREADS) shade_bwd_kernel(const ShadeArg
         const bool valid = g_raw < a.P;
         const int g = valid ? g_raw : a.P - 1;
         GaussianOperands o;
-        load_operands(a, g, o);
+        load_operands<VAR == 0>(a, g, o);
+        if (VAR >= 1) stage_incidents<G>(a, g, sinc, sub);
         float gp[3], gs[3], gd[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -324,6 +368,10 @@ __global__ void __launch_bounds__(SHADE_THREADS) shade_bwd_kernel(const ShadeArg
         float dinc[VP];
 #pragma unroll
         for (int q = 0; q < VP; ++q) dinc[q] = 0.f;
+        if (VAR == 2) {
+#pragma unroll
+            for (int q = 0; q < 48; ++q) sdinc[q * SHADE_THREADS] = 0.f;
+        }
         const size_t row = (size_t)g * a.N;
         for (int i0 = 0; i0 < a.N; i0 += G) {          // warp-uniform trip count (collectives inside in ENV_TAG mode)
             const bool act = valid && (i0 + sub) < a.N;
@@ -331,7 +379,7 @@ __global__ void __launch_bounds__(SHADE_THREADS) shade_bwd_kernel(const ShadeArg
             const float dx = a.dirs[3 * (row + i)], dy = a.dirs[3 * (row + i) + 1], dz = a.dirs[3 * (row + i) + 2];
             const float vis = a.visibility[row + i], area = a.areas[row + i];
             SampleEval e;
-            eval_sample<SMEM_ENV>(a, o, env, dx, dy, dz, vis, e);
+            eval_sample<SMEM_ENV, (VAR >= 1)>(a, o, env, sinc, dx, dy, dz, vis, e);
             float dfs = 0.f;
             float dG[3];
 #pragma unroll
@@ -343,8 +391,13 @@ __global__ void __launch_bounds__(SHADE_THREADS) shade_bwd_kernel(const ShadeArg
                 if (act) { dbase[c] += gp[c] * T / PI_F; dfs += (gp[c] + gs[c]) * T; }
                 const float dL = dT * area * e.ndi;
                 if (act && e.local_raw[c] >= 0.f) {                // clamp_min(0) passes the gradient at equality
+                    if (VAR == 2) {
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) dinc[3 * k + c] = fmaf(dL, e.w[k], dinc[3 * k + c]);
+                        for (int k = 0; k < 16; ++k) sdinc[(3 * k + c) * SHADE_THREADS] = fmaf(dL, e.w[k], sdinc[(3 * k + c) * SHADE_THREADS]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) dinc[3 * k + c] = fmaf(dL, e.w[k], dinc[3 * k + c]);
+                    }
                 }
                 dG[c] = act ? dL * vis : 0.f;                        // -> env texels (grid_sample backward)
             }
@@ -395,6 +448,10 @@ __global__ void __launch_bounds__(SHADE_THREADS) shade_bwd_kernel(const ShadeArg
 #pragma unroll
         for (int c = 0; c < 3; ++c) { dbase[c] = group_sum<G>(dbase[c]); dV[c] = group_sum<G>(dV[c]); }
         drough = group_sum<G>(drough);
+        if (VAR == 2) {
+#pragma unroll
+            for (int q = 0; q < 48; ++q) dinc[q] = sdinc[q * SHADE_THREADS];
+        }
         group_reduce_scatter<G, VP>(dinc, sub);        // lane `sub` now owns components [sub*RQ, sub*RQ + RQ)
         if (valid) {
             if (sub == 0) {
@@ -438,57 +495,62 @@ __global__ void __launch_bounds__(SHADE_THREADS) shade_bwd_kernel(const ShadeArg
 // ---- launch ---------------------------------------------------------------------------------------
 // tuning knobs (A/B measurements and tests of the non-default paths): initial value from the
 // environment, changed at run time through r3dg_tune (include/r3dg_b200.h)
-static int g_shade_group = -1;      // lanes per Gaussian: 8 (default), 16 or 32
-static int g_shade_env_mode = -1;   // highest env-gradient mode allowed: 2 tag (default), 1 smem atomics, 0 global atomics
-
-static int shade_group_width() {
-    if (g_shade_group < 0) {
-        const char* e = getenv("R3DG_SHADE_GROUP");
-        const int g = e ? atoi(e) : 8;
-        g_shade_group = (g == 8 || g == 16 || g == 32) ? g : 8;
-    }
-    return g_shade_group;
+struct ShadeKnob { const char* key; const char* env; int lo, hi, dflt, value; };
+static ShadeKnob g_knobs[] = {
+    {"shade_group", "R3DG_SHADE_GROUP", 8, 32, 8, -1},            // lanes per Gaussian: 8, 16 or 32
+    {"shade_env_mode", "R3DG_SHADE_ENV_MODE", 0, 2, ENV_TAG, -1}, // highest env-gradient mode allowed
+    {"shade_fwd_variant", "R3DG_SHADE_FWD_VARIANT", 0, 1, 0, -1}, // 1: incident SH coefficients in shared memory
+    {"shade_bwd_variant", "R3DG_SHADE_BWD_VARIANT", 0, 2, 0, -1}, // 1: as forward; 2: + gradient accumulators in shared memory
+};
+static bool knob_ok(const ShadeKnob& k, int v) {
+    if (v < k.lo || v > k.hi) return false;
+    return strcmp(k.key, "shade_group") != 0 || v == 8 || v == 16 || v == 32;
 }
-static int shade_env_mode_cap() {
-    if (g_shade_env_mode < 0) {
-        const char* e = getenv("R3DG_SHADE_ENV_MODE");
-        const int m = e ? atoi(e) : ENV_TAG;
-        g_shade_env_mode = (m >= ENV_GLOBAL && m <= ENV_TAG) ? m : ENV_TAG;
+static int knob(int i) {
+    ShadeKnob& k = g_knobs[i];
+    if (k.value < 0) {
+        const char* e = getenv(k.env);
+        const int v = e ? atoi(e) : k.dflt;
+        k.value = knob_ok(k, v) ? v : k.dflt;
     }
-    return g_shade_env_mode;
+    return k.value;
 }
 int shade_tune(const char* key, int value, int* previous) {
-    if (!strcmp(key, "shade_group")) {
-        *previous = shade_group_width();
-        if (value != 8 && value != 16 && value != 32) return R3DG_ERR_BAD_ARG;
-        g_shade_group = value;
-        return 0;
-    }
-    if (!strcmp(key, "shade_env_mode")) {
-        *previous = shade_env_mode_cap();
-        if (value < ENV_GLOBAL || value > ENV_TAG) return R3DG_ERR_BAD_ARG;
-        g_shade_env_mode = value;
+    for (int i = 0; i < (int)(sizeof(g_knobs) / sizeof(g_knobs[0])); ++i) {
+        if (strcmp(key, g_knobs[i].key)) continue;
+        *previous = knob(i);
+        if (!knob_ok(g_knobs[i], value)) return R3DG_ERR_BAD_ARG;
+        g_knobs[i].value = value;
         return 0;
     }
     return R3DG_ERR_UNSUPPORTED;
 }
 
 template <typename K>
-static int shade_grid(K kernel, int units, int num_sms, size_t smem) {
+static int shade_launch(K kernel, const ShadeArgs& a, int units, int num_sms, size_t smem, cudaStream_t stream) {
+    if (smem > 48 * 1024) R3DG_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SHADE_THREADS, smem) != cudaSuccess || per_sm <= 0) per_sm = 2;
     const int want = (units + SHADE_WARPS - 1) / SHADE_WARPS;
     const int cap = num_sms * per_sm;                 // persistent CTAs: one env staging / flush per resident CTA
-    return want < cap ? (want > 0 ? want : 1) : cap;
-}
-
-template <bool SMEM, int G>
-static int launch_fwd_g(const ShadeArgs& a, int num_sms, size_t smem, cudaStream_t stream) {
-    const int units = (a.P + 32 / G - 1) / (32 / G);
-    const int grid = shade_grid(shade_fwd_kernel<SMEM, G>, units, num_sms, smem);
-    shade_fwd_kernel<SMEM, G><<<grid, SHADE_THREADS, smem, stream>>>(a);
+    const int grid = want < cap ? (want > 0 ? want : 1) : cap;
+    kernel<<<grid, SHADE_THREADS, smem, stream>>>(a);
     R3DG_CUDA_TRY(cudaGetLastError());
     return 0;
+}
+
+static size_t inc_slot_bytes(int G, int var) { return var >= 1 ? (size_t)SHADE_WARPS * (32 / G) * SHADE_INC_STRIDE * sizeof(float) : 0; }
+
+template <bool SMEM>
+static int launch_fwd(const ShadeArgs& a, int num_sms, size_t env_smem, cudaStream_t stream) {
+    const int G = knob(0);
+    const int var = G == 8 ? knob(2) : 0;              // the shared-memory variants are built for the default group width
+    const size_t smem = env_smem + inc_slot_bytes(G, var);
+    const int units = (a.P + 32 / G - 1) / (32 / G);
+    if (G == 8) return var ? shade_launch(shade_fwd_kernel<SMEM, 8, 1>, a, units, num_sms, smem, stream)
+                           : shade_launch(shade_fwd_kernel<SMEM, 8, 0>, a, units, num_sms, smem, stream);
+    if (G == 16) return shade_launch(shade_fwd_kernel<SMEM, 16, 0>, a, units, num_sms, smem, stream);
+    return shade_launch(shade_fwd_kernel<SMEM, 32, 0>, a, units, num_sms, smem, stream);
 }
 
 int launch_shade_forward(ShadeArgs a, int num_sms, cudaStream_t stream) {
@@ -496,41 +558,34 @@ int launch_shade_forward(ShadeArgs a, int num_sms, cudaStream_t stream) {
     const size_t env_bytes = (size_t)a.He * a.We * 3 * sizeof(float);
     const bool smem = env_bytes <= 40 * 1024;
     a.env_in_smem = smem;
-    const int G = shade_group_width();
-    if (smem) return G == 8 ? launch_fwd_g<true, 8>(a, num_sms, env_bytes, stream) : G == 16 ? launch_fwd_g<true, 16>(a, num_sms, env_bytes, stream)
-                                                                                              : launch_fwd_g<true, 32>(a, num_sms, env_bytes, stream);
-    return G == 8 ? launch_fwd_g<false, 8>(a, num_sms, 0, stream) : G == 16 ? launch_fwd_g<false, 16>(a, num_sms, 0, stream)
-                                                                            : launch_fwd_g<false, 32>(a, num_sms, 0, stream);
-}
-
-template <int MODE, int G>
-static int launch_bwd_g(const ShadeArgs& a, int num_sms, size_t smem, cudaStream_t stream) {
-    const int units = (a.P + 32 / G - 1) / (32 / G);
-    const int grid = shade_grid(shade_bwd_kernel<MODE, G>, units, num_sms, smem);
-    shade_bwd_kernel<MODE, G><<<grid, SHADE_THREADS, smem, stream>>>(a);
-    R3DG_CUDA_TRY(cudaGetLastError());
-    return 0;
+    return smem ? launch_fwd<true>(a, num_sms, env_bytes, stream) : launch_fwd<false>(a, num_sms, 0, stream);
 }
 
 template <int MODE>
-static int launch_bwd_mode(const ShadeArgs& a, int num_sms, size_t smem, cudaStream_t stream) {
-    const int G = shade_group_width();
-    return G == 8 ? launch_bwd_g<MODE, 8>(a, num_sms, smem, stream) : G == 16 ? launch_bwd_g<MODE, 16>(a, num_sms, smem, stream)
-                                                                              : launch_bwd_g<MODE, 32>(a, num_sms, smem, stream);
+static int launch_bwd(const ShadeArgs& a, int num_sms, size_t env_smem, cudaStream_t stream) {
+    const int G = knob(0);
+    const int var = G == 8 ? knob(3) : 0;
+    const size_t smem = env_smem + inc_slot_bytes(G, var) + (var == 2 ? (size_t)48 * SHADE_THREADS * sizeof(float) : 0);
+    const int units = (a.P + 32 / G - 1) / (32 / G);
+    if (G == 8) return var == 2 ? shade_launch(shade_bwd_kernel<MODE, 8, 2>, a, units, num_sms, smem, stream)
+                     : var == 1 ? shade_launch(shade_bwd_kernel<MODE, 8, 1>, a, units, num_sms, smem, stream)
+                                : shade_launch(shade_bwd_kernel<MODE, 8, 0>, a, units, num_sms, smem, stream);
+    if (G == 16) return shade_launch(shade_bwd_kernel<MODE, 16, 0>, a, units, num_sms, smem, stream);
+    return shade_launch(shade_bwd_kernel<MODE, 32, 0>, a, units, num_sms, smem, stream);
 }
 
 int launch_shade_backward(ShadeArgs a, int num_sms, cudaStream_t stream) {
     const size_t nt = (size_t)a.He * a.We, env_bytes = nt * 3 * sizeof(float);
     R3DG_CUDA_TRY(cudaMemsetAsync(a.d_env, 0, env_bytes, stream));
     if (a.P <= 0) return 0;
-    // shared-memory budget of the three env-gradient modes (static 48 KB limit, no opt-in)
+    // shared-memory cost of the env-gradient modes (kept within the 48 KB that need no opt-in on their own)
     const size_t tag_bytes = ((nt * 3 + 3) & ~(size_t)3) * sizeof(float) + SHADE_WARPS * (nt * sizeof(float4) + ((nt + 15) & ~(size_t)15));
     const size_t cas_bytes = 2 * env_bytes;
-    const int cap = shade_env_mode_cap();
-    if (cap >= ENV_TAG && tag_bytes <= 48 * 1024) { a.env_in_smem = 1; return launch_bwd_mode<ENV_TAG>(a, num_sms, tag_bytes, stream); }
-    if (cap >= ENV_CAS && cas_bytes <= 40 * 1024) { a.env_in_smem = 1; return launch_bwd_mode<ENV_CAS>(a, num_sms, cas_bytes, stream); }
+    const int cap = knob(1);
+    if (cap >= ENV_TAG && tag_bytes <= 48 * 1024) { a.env_in_smem = 1; return launch_bwd<ENV_TAG>(a, num_sms, tag_bytes, stream); }
+    if (cap >= ENV_CAS && cas_bytes <= 40 * 1024) { a.env_in_smem = 1; return launch_bwd<ENV_CAS>(a, num_sms, cas_bytes, stream); }
     a.env_in_smem = 0;
-    return launch_bwd_mode<ENV_GLOBAL>(a, num_sms, 0, stream);
+    return launch_bwd<ENV_GLOBAL>(a, num_sms, 0, stream);
 }
 
 }  // namespace r3dg

@@ -52,6 +52,63 @@ class GradBucket:
         return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 
 
+class FactoredGradExchange:
+    """The exchange step with the SH gradient factorised (csrc/sh_exchange.cu).
+
+    For one view dL_dsh[g,k,:] = basis_k(dir(g, campos)) * f[g,:]: 192 of the 248 gradient bytes of a
+    Gaussian are an outer product of 16 numbers every rank can recompute with 3 numbers only the
+    rendering rank has.  So per step: ONE all-reduce (mean) of the small dense rest (means3D,
+    features, opacity, scales, rotations: 64 B per Gaussian at S=5), ONE all-gather of the factors
+    (12 B per Gaussian and view) and a local kernel that rebuilds mean_v(dL_dsh) — identical on all
+    ranks (fixed summation order), equal to the dense all-reduce up to fp32 summation order.
+
+    Usage: `rasterize_gaussians_backward(..., _out=ex.views)`, then
+    `ex.exchange(means3D, campos_of_all_ranks, degree)`; gradients are `ex.grads[name]`.
+    `gather_factors()` is pure torch.distributed (runs under gloo in the CPU tests); the rebuild is
+    the CUDA kernel (no CPU path)."""
+
+    def __init__(self, P, S, M, device, world=None):
+        self.P, self.S, self.M = P, S, M
+        self.world = world if world is not None else (dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1)
+        self.dense = GradBucket(P, S, M, device, names=tuple(n for n in REDUCED if n != "sh"))
+        self.factor = torch.zeros((P, 3), dtype=torch.float32, device=device)
+        self.gathered = torch.zeros((self.world, P, 3), dtype=torch.float32, device=device) if self.world > 1 else self.factor.view(1, P, 3)
+        self.sh = torch.zeros((P, M, 3), dtype=torch.float32, device=device)
+        self.views = OrderedDict(self.dense.views)
+        self.views["sh_factor"] = self.factor
+        self.grads = OrderedDict(self.dense.views)
+        self.grads["sh"] = self.sh
+
+    def bytes(self):
+        """Bytes a rank contributes to the collectives of one step (dense all-reduce + its factor)."""
+        return self.dense.bytes() + self.factor.numel() * 4
+
+    def gather_factors(self, group=None):
+        if self.world > 1:
+            # output viewed as the dim-0 concatenation [world*P, 3] (the layout gloo insists on; NCCL accepts both)
+            dist.all_gather_into_tensor(self.gathered.view(self.world * self.P, 3), self.factor, group=group)
+        return self.gathered
+
+    def rebuild_sh(self, means3D, campos_all, degree):
+        """dL_dsh = (1/world) * sum_v basis(dir(means3D, campos_all[v])) x gathered[v]  (CUDA kernel)."""
+        from . import _lib
+        lib = _lib.load()
+        assert campos_all.shape == (self.world, 3) and campos_all.is_contiguous() and campos_all.dtype == torch.float32
+        assert means3D.is_contiguous() and means3D.dtype == torch.float32 and means3D.shape == (self.P, 3)
+        if not means3D.is_cuda:
+            raise RuntimeError("FactoredGradExchange.rebuild_sh runs on the GPU only (no CPU path)")
+        dev = means3D.device
+        _lib.check(lib.r3dg_sh_grad_from_factors(self.P, int(degree), self.M, self.world, means3D.data_ptr(), campos_all.data_ptr(),
+                                                 self.gathered.data_ptr(), 1.0 / self.world, self.sh.data_ptr(),
+                                                 torch.cuda.current_stream(dev).cuda_stream), "sh_grad_from_factors")
+        return self.sh
+
+    def exchange(self, means3D, campos_all, degree, group=None):
+        self.dense.allreduce_mean(group=group)
+        self.gather_factors(group=group)
+        return self.rebuild_sh(means3D, campos_all, degree)
+
+
 def view_for_rank(step, rank, world, num_views):
     """Views of a step are dealt round-robin: rank r of step s renders view (s*world + r) % V."""
     return (step * world + rank) % num_views

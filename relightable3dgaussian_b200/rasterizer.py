@@ -47,6 +47,22 @@ def set_deferred_count(enabled: bool):
     _DEFER_COUNT = bool(enabled)
 
 
+_EXCHANGE = None
+
+
+def set_grad_exchange(exchange, campos_all=None):
+    """Opt-in multi-GPU data parallelism over views (not part of the single-GPU reference surface;
+    SURVEY.md §8e).  With a `dist.FactoredGradExchange` installed, the backward of
+    `GaussianRasterizer` writes its per-Gaussian parameter gradients straight into the exchange
+    buffers, runs the step's collectives (one all-reduce of the dense rest, one all-gather of the
+    SH-gradient factors, the local rebuild) and hands autograd the gradients ALREADY AVERAGED over
+    the ranks' views — `loss.backward()` is the whole step.  `campos_all` [world,3] holds the camera
+    centres of the views the ranks render this step, in rank order (call again per step).
+    `means2D` / `colors_precomp` / `cov3D` gradients stay per-view.  `set_grad_exchange(None)` turns it off."""
+    global _EXCHANGE
+    _EXCHANGE = None if exchange is None else (exchange, campos_all)
+
+
 def _snapshot(args):
     return tuple(a.cpu().clone() if isinstance(a, torch.Tensor) else a for a in args)
 
@@ -110,6 +126,12 @@ class _RasterizeGaussians(torch.autograd.Function):
                 torch.save(saved, "snapshot_bw.dump")
                 print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
                 raise
+        elif _EXCHANGE is not None and sh.numel() != 0 and scales.numel() != 0:
+            ex, campos_all = _EXCHANGE
+            grads = _C.rasterize_gaussians_backward(*args, _out=ex.views)
+            ex.exchange(means3D, campos_all, rs.sh_degree)
+            g = ex.grads
+            grads = (grads[0], grads[1], g["opacity"], g["means3D"], g["features"], grads[5], g["sh"], g["scales"], g["rotations"])
         else:
             grads = _C.rasterize_gaussians_backward(*args)
         if isinstance(ctx.num_rendered, _C.DeferredCount):

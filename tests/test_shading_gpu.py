@@ -66,15 +66,22 @@ def test_matches_pytorch_oracle(P, N, He, fixed):
     _check_against_oracle(P, N, He, fixed)
 
 
-@pytest.mark.parametrize("group,env_mode", [(16, 2), (32, 2), (8, 1), (32, 1), (8, 0)])
-def test_kernel_variants_match_oracle(group, env_mode):
-    """Non-default kernel variants (r3dg_tune): lanes per Gaussian, env-gradient accumulation mode."""
+@pytest.mark.parametrize("knobs", [dict(shade_group=16), dict(shade_group=32), dict(shade_env_mode=1), dict(shade_env_mode=0),
+                                   dict(shade_group=32, shade_env_mode=1), dict(shade_fwd_variant=1, shade_bwd_variant=1),
+                                   dict(shade_fwd_variant=1, shade_bwd_variant=2), dict(shade_bwd_variant=2, shade_env_mode=1),
+                                   dict(shade_fwd_variant=0, shade_bwd_variant=0)],
+                         ids=lambda k: ",".join(f"{a[6:]}={b}" for a, b in k.items()))
+def test_kernel_variants_match_oracle(knobs):
+    """Every kernel variant selectable through r3dg_tune: lanes per Gaussian, env-gradient
+    accumulation mode, SH operands / gradient accumulators in shared memory."""
     from relightable3dgaussian_b200 import _lib
-    old = _lib.tune("shade_group", group), _lib.tune("shade_env_mode", env_mode)
+    old = {k: _lib.tune(k, v) for k, v in knobs.items()}
     try:
         _check_against_oracle(4_001, 40, 16, False)
+        _check_against_oracle(37, 5, 128, True)         # idle groups, N < group width, global env-gradient path
     finally:
-        _lib.tune("shade_group", old[0]); _lib.tune("shade_env_mode", old[1])
+        for k, v in old.items():
+            _lib.tune(k, v)
 
 
 def _check_against_oracle(P, N, He, fixed):

@@ -111,14 +111,15 @@ def shade_kernels(P, N):
     a.dL_dincidents, a.dL_denv = grads["d_inc"].data_ptr(), grads["d_env"].data_ptr()
     st = torch.cuda.current_stream().cuda_stream
     ref = None
-    for group, mode in ((8, 2), (16, 2), (32, 2), (8, 1), (32, 1), (8, 0)):
-        old = _lib.tune("shade_group", group), _lib.tune("shade_env_mode", mode)
+    for group, mode, fv, bv in ((8, 2, 0, 0), (8, 2, 1, 1), (8, 2, 1, 2), (8, 1, 1, 2), (8, 1, 1, 1), (32, 1, 0, 0)):
+        old = _lib.tune("shade_group", group), _lib.tune("shade_env_mode", mode), _lib.tune("shade_fwd_variant", fv), _lib.tune("shade_bwd_variant", bv)
         t_f = timeit(lambda: _lib.check(lib.r3dg_render_equation_forward(ctypes.byref(a), st), "fwd"), n=10, warm=2)
         t_b = timeit(lambda: _lib.check(lib.r3dg_render_equation_backward(ctypes.byref(a), st), "bwd"), n=10, warm=2)
         sig = [float(outs[0].double().sum()), float(grads["d_inc"].double().abs().sum()), float(grads["d_env"].double().abs().sum())]
         ref = ref or sig
-        _lib.tune("shade_group", old[0]); _lib.tune("shade_env_mode", old[1])
-        print(json.dumps(dict(what="shading kernels", P=P, N=N, group=group, env_mode=mode, fwd_ms=t_f, bwd_ms=t_b,
+        for k, v in zip(("shade_group", "shade_env_mode", "shade_fwd_variant", "shade_bwd_variant"), old):
+            _lib.tune(k, v)
+        print(json.dumps(dict(what="shading kernels", P=P, N=N, group=group, env_mode=mode, fwd_variant=fv, bwd_variant=bv, fwd_ms=t_f, bwd_ms=t_b,
                               fwd_GBps=P * N * 20 / t_f / 1e6, bwd_GBps=P * N * 20 / t_b / 1e6,
                               checksum_rel=[abs(x - y) / (abs(y) + 1e-30) for x, y in zip(sig, ref)])), flush=True)
 
