@@ -274,9 +274,10 @@ int r3dg_prof_end(float* stage_ms /* [9] */, int* fwd_calls, int* bwd_calls);
  * NULL); R3DG_ERR_UNSUPPORTED for an unknown key, R3DG_ERR_BAD_ARG for an out-of-range value.
  *   "shade_group"     lanes per Gaussian in the shading kernels: 8 (default), 16, 32
  *   "shade_fwd_variant" / "shade_bwd_variant"  0 per-Gaussian SH state in registers, 1 incident
- *                     coefficients in shared memory, 2 (backward) + gradient accumulators in shared memory
+ *                     coefficients in shared memory (forward default), 2 (backward, default) +
+ *                     gradient accumulators in shared memory
  *   "shade_env_mode"  env-map gradient accumulation in r3dg_render_equation_backward:
- *                     2 warp-private tagged copies (default), 1 shared-memory atomics,
+ *                     2 warp-private tagged copies, 1 shared-memory atomics (default),
  *                     0 global atomics; larger textures fall back to the lower modes
  * Initial values can also be given by the environment (R3DG_SHADE_GROUP, R3DG_SHADE_ENV_MODE,
  * R3DG_SHADE_FWD_VARIANT, R3DG_SHADE_BWD_VARIANT). */

@@ -498,9 +498,12 @@ __global__ void __launch_bounds__(SHADE_THREADS, VAR == 0 ? 1 : VAR == 1 ? 3 : (
 struct ShadeKnob { const char* key; const char* env; int lo, hi, dflt, value; };
 static ShadeKnob g_knobs[] = {
     {"shade_group", "R3DG_SHADE_GROUP", 8, 32, 8, -1},            // lanes per Gaussian: 8, 16 or 32
-    {"shade_env_mode", "R3DG_SHADE_ENV_MODE", 0, 2, ENV_TAG, -1}, // highest env-gradient mode allowed
-    {"shade_fwd_variant", "R3DG_SHADE_FWD_VARIANT", 0, 1, 0, -1}, // 1: incident SH coefficients in shared memory
-    {"shade_bwd_variant", "R3DG_SHADE_BWD_VARIANT", 0, 2, 0, -1}, // 1: as forward; 2: + gradient accumulators in shared memory
+    // defaults = the fastest measured combination (profiles/r01_stage3_shading_variants.jsonl, 300k x 64 backward:
+    // variant 0 + tag 1.92 ms, variant 1 + tag 1.42, variant 2 + tag 1.51 (3 CTAs/SM by shared memory),
+    // variant 2 + shared atomics 1.20 (5 CTAs/SM); forward variant 0 0.57 ms, variant 1 0.47)
+    {"shade_env_mode", "R3DG_SHADE_ENV_MODE", 0, 2, ENV_CAS, -1}, // highest env-gradient mode allowed
+    {"shade_fwd_variant", "R3DG_SHADE_FWD_VARIANT", 0, 1, 1, -1}, // 1: incident SH coefficients in shared memory
+    {"shade_bwd_variant", "R3DG_SHADE_BWD_VARIANT", 0, 2, 2, -1}, // 1: as forward; 2: + gradient accumulators in shared memory
 };
 static bool knob_ok(const ShadeKnob& k, int v) {
     if (v < k.lo || v > k.hi) return false;
