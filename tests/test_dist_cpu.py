@@ -115,3 +115,62 @@ def test_allreduce_mean_world2_gloo():
             exp[k] = exp.get(k, 0) + torch.randn(v.shape, generator=g) / 2
     for k in exp:
         assert torch.allclose(torch.from_numpy(res[0][k]), exp[k], atol=1e-6) and (res[0][k] == res[1][k]).all()
+
+
+def test_exchange_aware_backward_host_logic(monkeypatch):
+    """rasterizer.set_grad_exchange: the autograd backward must hand the kernels the exchange's views,
+    run the exchange, and return the AVERAGED gradients for (means3D, features, sh, opacity, scales,
+    rotations) while means2D / colors / cov3D stay the per-view tensors.  Host logic only: the C-ABI
+    calls are replaced by stand-ins that write recognisable values (no GPU here)."""
+    from relightable3dgaussian_b200 import rasterizer as R
+    P, S, M, H, W = 7, 2, 16, 4, 5
+    ex = FactoredGradExchange(P, S, M, "cpu", world=1)
+    seen = {}
+
+    def fake_fwd(*args, _defer=False):
+        z = lambda *s: torch.zeros(*s)
+        return (3, z(H, W).int(), z(3, H, W), z(1, H, W), z(1, H, W), z(S, H, W), z(3, H, W), z(3, H, W), z(P, 1), torch.ones(P).int(),
+                torch.zeros(8, dtype=torch.uint8), torch.zeros(8, dtype=torch.uint8), torch.zeros(8, dtype=torch.uint8))
+
+    def fake_bwd(*args, _out=None):
+        seen["out"] = _out
+        fill = dict(means3D=1.0, features=2.0, opacity=3.0, scales=4.0, rotations=5.0, sh_factor=6.0)
+        for k, v in fill.items():
+            _out[k].fill_(v)
+        per_view = lambda shape, v: torch.full(shape, v)
+        # 9-tuple order of rasterize_points.cu:143-235
+        return (per_view((P, 3), 10.0), per_view((P, 3), 11.0), _out["opacity"], _out["means3D"], _out["features"], per_view((P, 6), 12.0),
+                torch.empty(0), _out["scales"], _out["rotations"])
+
+    def fake_rebuild(means3D, campos_all, degree):
+        seen["rebuild"] = (tuple(means3D.shape), tuple(campos_all.shape), degree)
+        ex.sh.fill_(7.0)
+        return ex.sh
+
+    monkeypatch.setattr(R._C, "rasterize_gaussians", fake_fwd)
+    monkeypatch.setattr(R._C, "rasterize_gaussians_backward", fake_bwd)
+    monkeypatch.setattr(ex, "rebuild_sh", fake_rebuild)
+    leaf = lambda *s: torch.randn(*s, requires_grad=True)
+    means3D, means2D, feats, shs, opac, scales, rots = leaf(P, 3), leaf(P, 3), leaf(P, S), leaf(P, M, 3), leaf(P, 1), leaf(P, 3), leaf(P, 4)
+    rs = R.GaussianRasterizationSettings(H, W, 1.0, 1.0, 0.0, 0.0, torch.zeros(3), 1.0, torch.eye(4), torch.eye(4), 3, torch.zeros(3),
+                                         False, True, True, False)
+    campos_all = torch.zeros(1, 3)
+    R.set_grad_exchange(ex, campos_all)
+    try:
+        out = R.GaussianRasterizer(rs)(means3D=means3D, means2D=means2D, opacities=opac, shs=shs, scales=scales, rotations=rots, features=feats)
+        (out[2].sum() + out[3].sum() + out[4].sum() + out[5].sum()).backward()
+    finally:
+        R.set_grad_exchange(None)
+    assert seen["out"] is ex.views and seen["rebuild"] == ((P, 3), (1, 3), 3)
+    expect = {"means3D": (means3D, 1.0), "features": (feats, 2.0), "opacity": (opac, 3.0), "scales": (scales, 4.0), "rotations": (rots, 5.0),
+              "sh": (shs, 7.0), "means2D": (means2D, 10.0)}
+    for name, (t, v) in expect.items():
+        assert t.grad is not None and t.grad.shape == t.shape and bool((t.grad == v).all()), name
+    # autograd must have copied: the exchange buffers are reused by the next step
+    assert means3D.grad.data_ptr() != ex.grads["means3D"].data_ptr() and shs.grad.data_ptr() != ex.sh.data_ptr()
+    # without an exchange installed the plain backward is used (no _out)
+    out = R.GaussianRasterizer(rs)(means3D=means3D, means2D=means2D, opacities=opac, shs=shs, scales=scales, rotations=rots, features=feats)
+    monkeypatch.setattr(R._C, "rasterize_gaussians_backward", lambda *a, **k: (_ for _ in ()).throw(AssertionError("_out given")) if k else
+                        (torch.zeros(P, 3), torch.zeros(P, 3), torch.zeros(P, 1), torch.zeros(P, 3), torch.zeros(P, S), torch.zeros(P, 6),
+                         torch.zeros(P, M, 3), torch.zeros(P, 3), torch.zeros(P, 4)))
+    out[2].sum().backward()
