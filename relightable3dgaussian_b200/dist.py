@@ -109,6 +109,26 @@ class FactoredGradExchange:
         return self.rebuild_sh(means3D, campos_all, degree)
 
 
+def allreduce_densification_stats(weights, xyz_grad_norm, normal_grad_norm, update_filter, radii, group=None):
+    """Per-step densification statistics of an N-view step.  The reference accumulates,
+    per rendered view (scene/gaussian_model.py:931-937, train.py:161-165):
+        weights_accum += weights;  xyz_gradient_accum[f] += ||viewspace_grad[f,:2]||;
+        normal_gradient_accum[f] += ||normal_grad[f]||;  denom[f] += 1;  max_radii2D[f] = max(., radii[f])
+    The norms are taken per view BEFORE accumulation, so the ranks exchange their per-view terms, not a
+    summed gradient: ONE sum all-reduce of a packed [P,4] tensor (weights, masked xyz norm, masked normal
+    norm, filter as 0/1) and ONE max all-reduce of the masked radii.  Inputs are this rank's view:
+    weights [P,1], xyz_grad_norm [P,1], normal_grad_norm [P,1], update_filter bool [P], radii int [P].
+    Returns (weights_sum [P,1], xyz_norm_sum [P,1], normal_norm_sum [P,1], denom_inc [P,1], radii_max [P])
+    — the increments to add to / max into the five accumulators; identical on all ranks."""
+    f = update_filter.reshape(-1, 1).to(weights.dtype)
+    packed = torch.cat([weights.reshape(-1, 1), xyz_grad_norm.reshape(-1, 1) * f, normal_grad_norm.reshape(-1, 1) * f, f], dim=1).contiguous()
+    rmax = torch.where(update_filter.reshape(-1), radii.reshape(-1), torch.zeros_like(radii.reshape(-1))).contiguous()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(rmax, op=dist.ReduceOp.MAX, group=group)
+    return packed[:, 0:1], packed[:, 1:2], packed[:, 2:3], packed[:, 3:4], rmax
+
+
 def view_for_rank(step, rank, world, num_views):
     """Views of a step are dealt round-robin: rank r of step s renders view (s*world + r) % V."""
     return (step * world + rank) % num_views

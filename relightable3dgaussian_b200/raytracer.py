@@ -93,15 +93,41 @@ class RayTracer:
 
 
 @torch.no_grad()
-def update_visibility(xyz, scaling, rotation, inverse_covariance, opacity, normal, sample_num):
+def update_visibility(xyz, scaling, rotation, inverse_covariance, opacity, normal, sample_num, shard_group=None):
     """scene/gaussian_model.py:312-342 as a free function of the activated Gaussian tensors.
-    Returns (visibility [P,N,1], incident_dirs [P,N,3], incident_areas [P,N,1])."""
+    Returns (visibility [P,N,1], incident_dirs [P,N,3], incident_areas [P,N,1]).
+
+    `shard_group` (a torch.distributed process group, or True for the default group) shards the one-off
+    bake over the ranks: the model is replicated, so every rank builds the same LBVH,
+    traces only its contiguous slice of ceil(P / world) Gaussians and ONE all-gather of the visibility
+    slices follows (directions / areas are deterministic and cheap: computed locally for all P).
+    The reference is single-GPU; without `shard_group` this is exactly its loop."""
+    import torch.distributed as tdist
+    P = xyz.shape[0]
+    world, rank, group = 1, 0, None
+    if shard_group is not None and shard_group is not False and tdist.is_available() and tdist.is_initialized():
+        group = None if shard_group is True else shard_group
+        world, rank = tdist.get_world_size(group), tdist.get_rank(group)
     raytracer = RayTracer(xyz, scaling, rotation)
+    per_rank = -(-P // world)
+    lo, hi = min(rank * per_rank, P), min((rank + 1) * per_rank, P)
     vis, dirs, areas = [], [], []
-    chunk_size = max(1, xyz.shape[0] // ((sample_num - 1) // 24 + 1))
-    for offset in range(0, xyz.shape[0], chunk_size):
-        d, a = sample_incident_rays(normal[offset:offset + chunk_size], False, sample_num)
-        res = raytracer.trace_visibility(xyz[offset:offset + chunk_size, None].expand_as(d), d, xyz,
-                                         inverse_covariance, opacity, normal)
-        vis.append(res["visibility"]); dirs.append(d); areas.append(a)
-    return torch.cat(vis, dim=0), torch.cat(dirs, dim=0), torch.cat(areas, dim=0)
+    chunk_size = max(1, P // ((sample_num - 1) // 24 + 1))
+    for offset in range(0, P, chunk_size):
+        end = min(offset + chunk_size, P)
+        d, a = sample_incident_rays(normal[offset:end], False, sample_num)
+        dirs.append(d); areas.append(a)
+        s0, s1 = max(offset, lo), min(end, hi)                  # this rank's part of the chunk
+        if s1 > s0:
+            dd = d[s0 - offset:s1 - offset]
+            res = raytracer.trace_visibility(xyz[s0:s1, None].expand_as(dd), dd, xyz, inverse_covariance, opacity, normal)
+            vis.append(res["visibility"])
+    dirs, areas = torch.cat(dirs, dim=0), torch.cat(areas, dim=0)
+    mine = torch.cat(vis, dim=0) if vis else xyz.new_zeros((0, sample_num, 1))
+    if world == 1:
+        return mine, dirs, areas
+    padded = xyz.new_zeros((per_rank, sample_num, 1))
+    padded[:hi - lo] = mine
+    gathered = xyz.new_empty((world * per_rank, sample_num, 1))
+    tdist.all_gather_into_tensor(gathered, padded, group=group)
+    return gathered[:P].contiguous(), dirs, areas

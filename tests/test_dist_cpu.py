@@ -174,3 +174,94 @@ def test_exchange_aware_backward_host_logic(monkeypatch):
                         (torch.zeros(P, 3), torch.zeros(P, 3), torch.zeros(P, 1), torch.zeros(P, 3), torch.zeros(P, S), torch.zeros(P, 6),
                          torch.zeros(P, M, 3), torch.zeros(P, 3), torch.zeros(P, 4)))
     out[2].sum().backward()
+
+
+def _worker_bake(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from relightable3dgaussian_b200 import raytracer as RT
+
+    class FakeTracer:                       # stand-in for the CUDA LBVH: visibility = a known function of the ray
+        traced = 0
+
+        def __init__(self, *a):
+            pass
+
+        def trace_visibility(self, rays_o, rays_d, *rest):
+            FakeTracer.traced += rays_o.shape[0]
+            return {"visibility": (rays_o[..., :1] * 10.0 + rays_d[..., 2:3]).contiguous()}
+    RT.RayTracer = FakeTracer
+    P, N = 1003, 40                          # odd P: the last rank's slice is shorter; N = 40 -> two chunks
+    g = torch.Generator().manual_seed(9)
+    xyz = torch.randn(P, 3, generator=g)
+    nrm = torch.nn.functional.normalize(torch.randn(P, 3, generator=g), dim=-1)
+    z = torch.zeros(P, 3)
+    vis, dirs, areas = RT.update_visibility(xyz, z, z, z, z[:, 0], nrm, N, shard_group=True)
+    q.put((rank, vis.numpy(), dirs.numpy(), FakeTracer.traced))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_visibility_bake_world2_gloo():
+    """update_visibility(shard_group=...): each rank traces only its slice, one all-gather restores the
+    reference's [P,N,1] tensor on every rank (tracer replaced by a stand-in: no GPU here)."""
+    from relightable3dgaussian_b200 import raytracer as RT
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_bake, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    got = {r: (v, d, n) for r, v, d, n in [q.get(timeout=120) for _ in range(2)]}
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    P, N = 1003, 40
+    g = torch.Generator().manual_seed(9)
+    xyz = torch.randn(P, 3, generator=g)
+    nrm = torch.nn.functional.normalize(torch.randn(P, 3, generator=g), dim=-1)
+    dirs, _ = RT.sample_incident_rays(nrm, False, N)
+    expect = (xyz[:, None, :1].expand(P, N, 1) * 10.0 + dirs[..., 2:3]).numpy()
+    for r in range(2):
+        v, d, traced = got[r]
+        assert v.shape == (P, N, 1) and np.allclose(v, expect, atol=1e-6) and np.allclose(d, dirs.numpy(), atol=1e-6)
+    assert got[0][2] == 502 and got[1][2] == 501          # ceil(1003 / 2) and the rest: nobody traced everything
+
+
+def _worker_stats(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from relightable3dgaussian_b200.dist import allreduce_densification_stats
+    g = torch.Generator().manual_seed(300 + rank)
+    P = 101
+    w, xg, ng = torch.rand(P, 1, generator=g), torch.rand(P, 1, generator=g), torch.rand(P, 1, generator=g)
+    filt = torch.rand(P, generator=g) < 0.6
+    radii = torch.randint(0, 50, (P,), generator=g, dtype=torch.int32)
+    out = allreduce_densification_stats(w, xg, ng, filt, radii)
+    q.put((rank, [t.numpy().copy() for t in out]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_densification_stats_world2_gloo():
+    """Two views of one step: the accumulator increments equal what the reference's per-view loop
+    (gaussian_model.py:931-937, train.py:161-165) adds when it sees the two views one after the other."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_stats, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    got = dict(q.get(timeout=120) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    P = 101
+    acc = dict(w=torch.zeros(P, 1), x=torch.zeros(P, 1), n=torch.zeros(P, 1), d=torch.zeros(P, 1), r=torch.zeros(P, dtype=torch.int32))
+    for rank in range(2):                                   # the reference's sequential accumulation
+        g = torch.Generator().manual_seed(300 + rank)
+        w, xg, ng = torch.rand(P, 1, generator=g), torch.rand(P, 1, generator=g), torch.rand(P, 1, generator=g)
+        filt = torch.rand(P, generator=g) < 0.6
+        radii = torch.randint(0, 50, (P,), generator=g, dtype=torch.int32)
+        acc["w"] += w; acc["x"][filt] += xg[filt]; acc["n"][filt] += ng[filt]; acc["d"][filt] += 1
+        acc["r"][filt] = torch.max(acc["r"][filt], radii[filt])
+    for rank in range(2):
+        w, x, n, d, r = got[rank]
+        assert np.allclose(w, acc["w"].numpy(), atol=1e-6) and np.allclose(x, acc["x"].numpy(), atol=1e-6)
+        assert np.allclose(n, acc["n"].numpy(), atol=1e-6) and np.array_equal(d, acc["d"].numpy()) and np.array_equal(r, acc["r"].numpy())
