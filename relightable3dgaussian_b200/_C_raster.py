@@ -112,6 +112,8 @@ def rasterize_gaussians(background, means3D, features, colors, opacity, scales, 
     imgBuffer = torch.empty((lib.r3dg_raster_img_bytes(W, H),), dtype=torch.uint8, device=dev)
 
     st = _dev_state(dev)
+    if st["capacity"] == 0:
+        _defer = False       # no instance count seen on this device yet: learn it with the synchronous read-back (and retry) once
     capacity = max(st["capacity"], 4 * P + 4096)
     stream = torch.cuda.current_stream(dev)
     slot = st["next"]

@@ -42,7 +42,8 @@ def set_deferred_count(enabled: bool):
     `_C_raster.DeferredCount` (int()-able) that is resolved in backward, after the backward kernels
     have been enqueued, so the loss and the backward follow the forward on the GPU without a host
     round trip in between.  The binning buffer is then sized 1.5x the last count; an overflow
-    raises at resolve time instead of being retried transparently."""
+    raises at resolve time instead of being retried transparently.  The very first forward on a
+    device (no count seen yet) always takes the synchronous path."""
     global _DEFER_COUNT
     _DEFER_COUNT = bool(enabled)
 

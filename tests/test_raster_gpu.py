@@ -374,12 +374,17 @@ def test_deferred_count_option(C):
         assert isinstance(out[0], _C_raster.DeferredCount) and int(out[0]) == ref_out[0]
         assert torch.equal(out[2], ref_out[2]) and torch.equal(out[1], ref_out[1])
         assert rel_l2(npy(g), npy(ref_g)) < 1e-5
-        for st in _C_raster._state.values():
-            st["capacity"] = 0                                  # force a too-small speculative buffer
         sc2, _ = case_inputs(300, 160, 96, 5, view=2, scale_boost=40.0)
         leaf = lambda t: t.cuda()
-        out = GaussianRasterizer(rs)(means3D=leaf(sc2.means3D), means2D=torch.zeros(300, 3).cuda(), opacities=leaf(sc2.opacities),
-                                     shs=leaf(sc2.shs), scales=leaf(sc2.scales), rotations=leaf(sc2.rotations), features=leaf(sc2.features))
+        big = lambda: GaussianRasterizer(rs)(means3D=leaf(sc2.means3D), means2D=torch.zeros(300, 3).cuda(), opacities=leaf(sc2.opacities),
+                                             shs=leaf(sc2.shs), scales=leaf(sc2.scales), rotations=leaf(sc2.rotations), features=leaf(sc2.features))
+        for st in _C_raster._state.values():
+            st["capacity"] = 0                                  # no instance count seen yet on this device:
+        out = big()
+        assert isinstance(out[0], int) and out[0] > 4 * 300 + 4096   # ... the first forward learns it synchronously (and retried)
+        for st in _C_raster._state.values():
+            st["capacity"] = 1                                  # force a too-small speculative buffer
+        out = big()
         with pytest.raises(RuntimeError):
             int(out[0])
     finally:
