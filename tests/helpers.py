@@ -104,3 +104,20 @@ def shading_case(P, N, He, seed):
                 visibility=vis.contiguous(), incident_dirs=dirs.contiguous(), incident_areas=areas.contiguous(),
                 cot_pbr=torch.randn(P, 3, generator=g), cot_diffuse=torch.randn(P, 3, generator=g),
                 cot_specular=torch.randn(P, 3, generator=g))
+
+
+def adam_case():
+    """Seeded optimiser case shared by tests/golden/make_golden_adam.py and the tests: three parameter
+    groups shaped like the reference's (xyz [P,3], f_rest [P,15,3], opacity [P,1]) with its learning
+    rates (arguments/__init__.py), 7 steps of gradients (exact zeros for half of the f_rest rows: never
+    seen Gaussians, eps = 1e-15 decides; an all-zero step for xyz), one lr edit at step 5."""
+    g = torch.Generator().manual_seed(3)
+    shapes, lrs = [(500, 3), (500, 15, 3), (500, 1)], [1.6e-4, 2.5e-3 / 20, 5e-2]
+    params = [torch.randn(s, generator=g).numpy() for s in shapes]
+
+    def grads_for_step(step):
+        gg = torch.Generator().manual_seed(100 + step)
+        gs = [torch.randn(s, generator=gg) * (0.0 if (step == 3 and i == 0) else 1e-3) for i, s in enumerate(shapes)]
+        gs[1][::2] = 0.0
+        return [t.numpy() for t in gs]
+    return params, lrs, grads_for_step, {5: [(0, 1.0e-4)]}

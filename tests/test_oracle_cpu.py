@@ -234,3 +234,23 @@ def test_sh_gradient_factorisation_identity():
     rebuilt = oracle.sh_grad_from_factors(n(sc.means3D), campos, factors, 3, 16, 0.5)
     assert np.abs(dense).max() > 0
     np.testing.assert_allclose(rebuilt, dense, rtol=2e-5, atol=1e-6 * np.abs(dense).max())
+
+
+def test_adam_oracle_matches_committed_torch_fixture():
+    """Same pin as above, against the committed fixture (tests/golden/make_golden_adam.py ran
+    torch.optim.Adam here): travels to boxes regardless of their torch build."""
+    from helpers import adam_case
+    from oracle import oracle_adam
+    g = np.load(os.path.join(GOLDEN, "adam_steps.npz"))
+    params, lrs, grads_for_step, lr_edits = adam_case()
+    st = [(p.copy(), np.zeros_like(p), np.zeros_like(p)) for p in params]
+    lrs = list(lrs)
+    for step in range(1, 8):
+        for gi, lr in lr_edits.get(step, []):
+            lrs[gi] = lr
+        st = [oracle_adam.adam_step(s[0], gr, s[1], s[2], step, lr, eps=1e-15) for s, gr, lr in zip(st, grads_for_step(step), lrs)]
+    for i, s in enumerate(st):
+        assert float(g[f"step{i}"]) == 7.0
+        np.testing.assert_allclose(s[0], g[f"p{i}"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(s[1], g[f"m{i}"], rtol=2e-6, atol=1e-6 * float(np.abs(g[f"m{i}"]).max()))
+        np.testing.assert_allclose(s[2], g[f"v{i}"], rtol=2e-6, atol=1e-18)
