@@ -186,6 +186,43 @@ int r3dg_bvh_trace_opacity(int P, long long num_rays, const int32_t* nodes, cons
                            const float* opacities, const float* normals, int32_t* num_contributes,
                            float* rendered_opacity, void* tmp, size_t tmp_bytes, r3dg_stream_t stream);
 
+/* Replaces `sample_incident_rays(normals, False, N)` of the visibility bake
+ * (scene/gaussian_model.py:20-28 -> utils/graphics_utils.py:9-37 fibonacci_sphere_sampling with
+ * random_rotate=False -> utils/sh_utils.py:36-68 rotation_between_z; ~20 PyTorch kernels and
+ * [P,N,3]-sized intermediates in the reference): dirs f32[P,N,3] unit vectors, areas f32[P,N,1]
+ * = 2*pi (may be NULL).  phase f32[P] (may be NULL) = the caller's torch.rand(P) of
+ * random_rotate=True (is_training): theta_i += phase[g]*2*pi.  Same op-by-op fp32 rounding as
+ * the PyTorch expression. */
+int r3dg_sample_incident_dirs(int P, int N, const float* normals, const float* phase, float* dirs,
+                              float* areas, r3dg_stream_t stream);
+
+/* The visibility bake of `GaussianModel.update_visibility` (scene/gaussian_model.py:312-342) for
+ * the Gaussians of leaf slots [first_slot, first_slot + count) of a built tree (slot = position in
+ * Morton order; 0, P bakes everything) in ONE launch: per Gaussian g and sample i the ray
+ * direction is generated in the kernel exactly as r3dg_sample_incident_dirs does (never read from
+ * HBM), the origin is mean_g + origin_offset * dir (0.05, bvh/__init__.py:63), and the ray is
+ * traced like r3dg_bvh_trace_opacity.  Results are written to row g of the FULL-size outputs
+ * visibility f32[P,N], num_contributes i32[P,N] (may be NULL), dirs f32[P,N,3] and areas
+ * f32[P,N,1] (may be NULL: written once, here); rows of other slots are not touched.
+ * tmp: r3dg_bvh_trace_tmp_bytes(P). */
+int r3dg_bvh_bake_visibility(int P, int first_slot, int count, int N, const int32_t* nodes,
+                             const float* aabbs, const float* means3D, const float* covs3D,
+                             const float* opacities, const float* normals, float origin_offset,
+                             int32_t* num_contributes, float* visibility, float* dirs, float* areas,
+                             void* tmp, size_t tmp_bytes, r3dg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optional fused epilogue of the rasterizer call sites:
+ *     feature / opacity.clamp_min(1e-5) * (num_contrib > 0)
+ * (gaussian_renderer/neilf.py:135-137, render.py:106-108; 3 PyTorch kernels forward, ~6 backward).
+ * feature / out / dL_* are [S,HW] planar, opacity [HW], n_contrib i32[HW].
+ * ------------------------------------------------------------------------------------------ */
+int r3dg_unpremultiply_forward(int S, long long HW, const float* feature, const float* opacity,
+                               const int32_t* n_contrib, float* out, r3dg_stream_t stream);
+int r3dg_unpremultiply_backward(int S, long long HW, const float* feature, const float* opacity,
+                                const int32_t* n_contrib, const float* dL_dout, float* dL_dfeature,
+                                float* dL_dopacity, r3dg_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * BRDF shading: fused `rendering_equation` (gaussian_renderer/neilf.py:339-371) + `GGX_specular`
  * (:374-406) + lat-long environment lookup (scene/direct_light_map.py:70-83) + SH incident light.

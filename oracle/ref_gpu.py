@@ -66,7 +66,7 @@ class RefRasterizer:
         out = dict(color=z(3, H, W), opacity=z(1, H, W), depth=z(1, H, W), feature=z(S, H, W),
                    normal=z(3, H, W), surface_xyz=z(3, H, W), weights=z(P, 1),
                    radii=torch.zeros(P, dtype=torch.int32, device=dev))
-        torch.cuda.synchronize()
+        # no synchronize: the reference launches on the legacy default stream, which is torch's default stream
         R = lib().ref_raster_forward(
             self.ctx, P, S, int(sh_degree), M, _p(bg), W, H, _p(means3D), _p(shs), _p(colors_precomp),
             _p(features), _p(opacities), _p(scales), ctypes.c_float(scale_modifier), _p(rotations),
@@ -122,7 +122,6 @@ class RefRasterizer:
         g = dict(dL_dmeans3D=z(P, 3), dL_dmeans2D=z(P, 3), dL_dfeatures=z(P, S), dL_dcolors=z(P, 3),
                  dL_dconic=z(P, 2, 2), dL_dopacity=z(P, 1), dL_dcov3D=z(P, 6), dL_dsh=z(P, M, 3),
                  dL_dscales=z(P, 3), dL_drotations=z(P, 4))
-        torch.cuda.synchronize()
         rc = lib().ref_raster_backward(
             self.ctx, P, S, int(sh_degree), M, self.R, _p(bg), W, H, _p(means3D), _p(shs),
             _p(features), _p(colors_precomp), _p(scales), ctypes.c_float(scale_modifier),
@@ -211,3 +210,139 @@ def ref_bvh_trace_opacity(nodes, aabbs, rays_o, rays_d, means3D, covs3D, opaciti
     if rc != 0:
         raise RuntimeError("reference trace_bvh_opacity failed")
     return contrib, opa
+
+
+# ----------------------------------------------------------------------------------------------
+# The STOCK code path: the reference's own Python wrappers (git-ignored copies under oracle/_ref/py,
+# made by oracle/build_ref_ext.sh) over either the reference's own pybind modules (oracle/_ref/ext)
+# or this repo's drop-in packages (dropin/) — the latter is how tests/test_dropin_gpu.py proves that
+# the reference's files run unmodified on the B200 kernels.
+# ----------------------------------------------------------------------------------------------
+import importlib.util
+import sys
+
+_REF_PY = os.path.join(_HERE, "_ref", "py")
+_REF_EXT = os.path.join(_HERE, "_ref", "ext")
+_DROPIN = os.path.join(os.path.dirname(_HERE), "dropin")
+_WRAPPERS = {"raster": ("gaussian_renderer/r3dg_rasterization.py", "r3dg_rasterization"),
+             "bvh": ("bvh/__init__.py", "bvh_tracing")}
+_loaded = {}
+
+
+def ext_available(which="raster"):
+    name = _WRAPPERS[which][1]
+    return (os.path.exists(os.path.join(_REF_EXT, name, "_C.so")) and
+            os.path.exists(os.path.join(_REF_PY, _WRAPPERS[which][0])) and torch.cuda.is_available())
+
+
+def wrappers_available(which="raster"):
+    return os.path.exists(os.path.join(_REF_PY, _WRAPPERS[which][0]))
+
+
+def load_reference_wrapper(which, backend):
+    """Import the reference's wrapper file `which` ("raster" | "bvh") BY PATH with its extension package
+    (`r3dg_rasterization` / `bvh_tracing`) resolving to backend "ref" (the reference's own build) or "dropin"
+    (this repo).  Returns the module; both backends can be loaded side by side."""
+    key = (which, backend)
+    if key in _loaded:
+        return _loaded[key]
+    rel, pkg = _WRAPPERS[which]
+    root = _REF_EXT if backend == "ref" else _DROPIN
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == pkg or k.startswith(pkg + ".") or k == "utils" or k.startswith("utils.")}
+    sys.path[:0] = [root, _REF_PY]
+    try:
+        spec = importlib.util.spec_from_file_location(f"_refwrap_{which}_{backend}", os.path.join(_REF_PY, rel))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        origin = os.path.realpath(getattr(mod._C, "__file__", ""))
+        allowed = [os.path.realpath(_REF_EXT)] if backend == "ref" else [os.path.realpath(_DROPIN), os.path.realpath(
+            os.path.join(os.path.dirname(_HERE), "relightable3dgaussian_b200"))]
+        if not any(origin.startswith(a) for a in allowed):
+            raise ImportError(f"{pkg}._C resolved to {origin}, not under {allowed}")
+        mod._C_origin = origin
+    finally:
+        del sys.path[:2]
+        for k in [k for k in sys.modules if k == pkg or k.startswith(pkg + ".") or k == "utils" or k.startswith("utils.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    _loaded[key] = mod
+    return mod
+
+
+class _ShimRasterize(torch.autograd.Function):
+    """Fallback when the reference's own pybind module is not built: its unmodified kernels + rasterizer_impl.cu
+    orchestration behind the raw-pointer shim, with the zero-fills of rasterize_points.cu reproduced."""
+
+    @staticmethod
+    def forward(ctx, ref, means3D, opacities, shs, scales, rotations, features, cam, cd, bg, W, H):
+        kw = dict(means3D=means3D.detach().contiguous(), shs=shs.detach().contiguous(), scales=scales.detach().contiguous(),
+                  rotations=rotations.detach().contiguous(), features=features.detach().contiguous())
+        o = ref.forward(bg=bg, W=W, H=H, tan_fovx=cam.tanfovx, tan_fovy=cam.tanfovy, cx=cam.cx, cy=cam.cy, viewmatrix=cd["view"],
+                        projmatrix=cd["proj"], campos=cd["pos"], opacities=opacities.detach().contiguous(), **kw)
+        ctx.ref, ctx.o, ctx.kw, ctx.cam, ctx.cd, ctx.bg = ref, o, kw, cam, cd, bg
+        n_contrib = ref.intermediate("n_contrib").view(H, W)
+        ctx.mark_non_differentiable(n_contrib)
+        return o["color"], o["opacity"], o["depth"], o["feature"], n_contrib
+
+    @staticmethod
+    def backward(ctx, g_color, g_opacity, g_depth, g_feature, _):
+        z = lambda g, like: torch.zeros_like(like) if g is None else g
+        o = ctx.o
+        g = ctx.ref.backward(o, bg=ctx.bg, tan_fovx=ctx.cam.tanfovx, tan_fovy=ctx.cam.tanfovy, viewmatrix=ctx.cd["view"],
+                             projmatrix=ctx.cd["proj"], campos=ctx.cd["pos"], dL_dcolor=z(g_color, o["color"]),
+                             dL_dopacity=z(g_opacity, o["opacity"]), dL_ddepth=z(g_depth, o["depth"]),
+                             dL_dfeature=z(g_feature, o["feature"]), **ctx.kw)
+        return (None, g["dL_dmeans3D"], g["dL_dopacity"], g["dL_dsh"], g["dL_dscales"], g["dL_drotations"], g["dL_dfeatures"],
+                None, None, None, None, None)
+
+
+def reference_rasterizer():
+    """-> (raster(cam, cd, bg, xyz, opacity, shs, scales, rotations, features) -> dict, description).  Differentiable
+    through torch autograd.  Prefers the stock code path (reference wrapper + reference pybind module)."""
+    if ext_available("raster"):
+        mod = load_reference_wrapper("raster", "ref")
+
+        def raster(cam, cd, bg, xyz, opacity, shs, scales, rotations, features):
+            rs = mod.GaussianRasterizationSettings(
+                image_height=cam.image_height, image_width=cam.image_width, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, cx=cam.cx, cy=cam.cy,
+                bg=bg, scale_modifier=1.0, viewmatrix=cd["view"], projmatrix=cd["proj"], sh_degree=3, campos=cd["pos"], prefiltered=False,
+                backward_geometry=True, computer_pseudo_normal=True, debug=False)
+            means2D = torch.zeros_like(xyz, requires_grad=True)
+            (num_rendered, num_contrib, color, opac, depth, feature, normal, surface_xyz, weights, radii) = mod.GaussianRasterizer(rs)(
+                means3D=xyz, means2D=means2D, shs=shs, colors_precomp=None, opacities=opacity, scales=scales, rotations=rotations,
+                cov3D_precomp=None, features=features)
+            return dict(num_rendered=num_rendered, num_contrib=num_contrib, color=color, opacity=opac, depth=depth, feature=feature,
+                        radii=radii, means2D=means2D)
+        return raster, ("the reference's own rasterizer, stock code path: gaussian_renderer/r3dg_rasterization.py -> r3dg_rasterization._C "
+                        "(rasterize_points.cu + cuda_rasterizer/*.cu built for sm_100 by oracle/build_ref_ext.sh)")
+    ref = RefRasterizer()
+
+    def raster(cam, cd, bg, xyz, opacity, shs, scales, rotations, features):
+        color, opac, depth, feature, n_contrib = _ShimRasterize.apply(ref, xyz, opacity, shs, scales, rotations, features, cam, cd, bg,
+                                                                      cam.image_width, cam.image_height)
+        return dict(num_rendered=ref.R, num_contrib=n_contrib, color=color, opacity=opac, depth=depth, feature=feature, radii=None)
+    return raster, "the reference's unmodified kernels + rasterizer_impl.cu behind the raw-pointer shim (its pybind module is not built)"
+
+
+@torch.no_grad()
+def reference_update_visibility(xyz, scaling, rotation, icov, opacity, normal, sample_num):
+    """scene/gaussian_model.py:312-342 driven exactly like the reference drives it (chunk loop, PyTorch direction
+    sampling, RayTracer.trace_visibility) on the reference's own BVH kernels."""
+    from . import oracle_sampling
+    P = xyz.shape[0]
+    chunk_size = max(1, P // ((sample_num - 1) // 24 + 1))
+    vis, dirs, areas = [], [], []
+    if ext_available("bvh"):
+        mod = load_reference_wrapper("bvh", "ref")
+        rt = mod.RayTracer(xyz, scaling, rotation)
+        kind = "reference RayTracer (bvh/__init__.py) + bvh_tracing._C built for sm_100, PyTorch direction sampling, the reference's chunk loop"
+        trace = lambda o, d: rt.trace_visibility(o, d, xyz, icov, opacity, normal)["visibility"]
+    else:
+        nodes, aabbs, _ = ref_bvh_create(xyz, scaling, rotation)
+        kind = "reference BVH kernels behind the raw-pointer shim, PyTorch direction sampling, the reference's chunk loop"
+        trace = lambda o, d: ref_bvh_trace_opacity(nodes, aabbs, (o + d * 0.05).contiguous(), d, xyz, icov, opacity, normal)[1].unsqueeze(-1)
+    for off in range(0, P, chunk_size):
+        d, a = oracle_sampling.sample_incident_rays(normal[off:off + chunk_size], False, sample_num)
+        vis.append(trace(xyz[off:off + chunk_size, None].expand_as(d), d))
+        dirs.append(d); areas.append(a)
+    return torch.cat(vis, 0), torch.cat(dirs, 0), torch.cat(areas, 0), kind

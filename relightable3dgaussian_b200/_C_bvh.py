@@ -24,8 +24,9 @@ def create_bvh(means3D, scales, rotations, nodes, aabbs):
     morton = torch.zeros((P,), dtype=torch.int64, device=means3D.device)
     tmp = torch.empty((lib.r3dg_bvh_build_tmp_bytes(P),), dtype=torch.uint8, device=means3D.device)
     stream = torch.cuda.current_stream(means3D.device)
-    _lib.check(lib.r3dg_bvh_build(P, nodes.data_ptr(), aabbs.data_ptr(), morton.data_ptr(), tmp.data_ptr(),
-                                  tmp.numel(), stream.cuda_stream), "create_bvh")
+    with torch.cuda.device(means3D.device):
+        _lib.check(lib.r3dg_bvh_build(P, nodes.data_ptr(), aabbs.data_ptr(), morton.data_ptr(), tmp.data_ptr(),
+                                      tmp.numel(), stream.cuda_stream), "create_bvh")
     return nodes, aabbs, morton
 
 
@@ -44,12 +45,13 @@ def _trace(nodes, aabbs, rays_o, rays_per_origin, origin_offset, rays_d, means3D
     means3D, covs3D, opacities, normals = _c(means3D), _c(covs3D), _c(opacities), _c(normals)
     tmp = torch.empty((lib.r3dg_bvh_trace_tmp_bytes(P),), dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
-    _lib.check(lib.r3dg_bvh_trace_opacity(P, num_rays, nodes.data_ptr(), aabbs.data_ptr(), rays_o.data_ptr(),
-                                          int(rays_per_origin), float(origin_offset), rays_d.data_ptr(),
-                                          means3D.data_ptr(), covs3D.data_ptr(), opacities.data_ptr(),
-                                          normals.data_ptr(), num_contributes.data_ptr(),
-                                          rendered_opacity.data_ptr(), tmp.data_ptr(), tmp.numel(),
-                                          stream.cuda_stream), "trace_bvh_opacity")
+    with torch.cuda.device(dev):
+        _lib.check(lib.r3dg_bvh_trace_opacity(P, num_rays, nodes.data_ptr(), aabbs.data_ptr(), rays_o.data_ptr(),
+                                              int(rays_per_origin), float(origin_offset), rays_d.data_ptr(),
+                                              means3D.data_ptr(), covs3D.data_ptr(), opacities.data_ptr(),
+                                              normals.data_ptr(), num_contributes.data_ptr(),
+                                              rendered_opacity.data_ptr(), tmp.data_ptr(), tmp.numel(),
+                                              stream.cuda_stream), "trace_bvh_opacity")
     return num_contributes, rendered_opacity
 
 

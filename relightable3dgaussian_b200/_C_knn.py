@@ -12,6 +12,7 @@ def distCUDA2(points):
     out = torch.full((P,), 0.0, dtype=torch.float32, device=points.device)
     if P > 0:
         tmp = torch.empty((lib.r3dg_knn_tmp_bytes(P),), dtype=torch.uint8, device=points.device)
-        _lib.check(lib.r3dg_knn_dist2(P, pts.data_ptr(), out.data_ptr(), tmp.data_ptr(), tmp.numel(),
-                                      torch.cuda.current_stream(points.device).cuda_stream), "distCUDA2")
+        with torch.cuda.device(points.device):
+            _lib.check(lib.r3dg_knn_dist2(P, pts.data_ptr(), out.data_ptr(), tmp.data_ptr(), tmp.numel(),
+                                          torch.cuda.current_stream(points.device).cuda_stream), "distCUDA2")
     return out

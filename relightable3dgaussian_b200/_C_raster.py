@@ -10,7 +10,9 @@ Differences that are not observable through the reference's Python wrapper
     torch::full / torch::zeros;
   * work is enqueued on torch's current stream (the reference uses the legacy default stream);
   * the binning buffer is sized speculatively from the previous call and the instance count is
-    read back once, after everything has been enqueued — the pipeline itself never synchronises.
+    read back once, after everything has been enqueued — the pipeline itself never synchronises;
+    a missed speculation re-runs the forward (synchronous path: immediately; deferred path: in the
+    autograd backward, before differentiating).
 """
 import ctypes
 
@@ -18,38 +20,52 @@ import torch
 
 from . import _lib
 
-_state = {}          # per-device speculative capacity + pinned readback slots
+_state = {}          # per-device instance-count statistics + pinned readback slots
 _SLOTS = 64
+_LEARN = 8           # forwards per (P, W, H) shape that always take the synchronous read-back (learn the counts)
+_HEADROOM = 4.0      # deferred mode: binning capacity = _HEADROOM x the largest count seen for the shape
 
 
 def _dev_state(device):
     key = device.index if device.index is not None else torch.cuda.current_device()
     st = _state.get(key)
     if st is None:
-        st = {"capacity": 0, "pinned": torch.zeros(_SLOTS, dtype=torch.int32).pin_memory(), "next": 0}
+        st = {"capacity": 0, "pinned": torch.zeros(_SLOTS, dtype=torch.int32).pin_memory(), "next": 0,
+              "shape": None, "seen": 0, "rmax": 0, "pending": None, "overflows": 0}
         _state[key] = st
     return st
 
 
+def _observe(st, rendered, P):
+    """Running statistics of the instance count for the current shape (sizes the next binning buffer)."""
+    st["seen"] += 1
+    st["rmax"] = max(st["rmax"], int(rendered))
+    st["capacity"] = max(int(rendered * 1.25) + 4096, 4 * P + 4096)
+
+
 class DeferredCount:
     """`num_rendered` of a forward whose read-back has not been waited for yet (opt-in, see
-    rasterizer.set_deferred_count).  int() / resolve() waits for the forward's event; an
-    overflow of the speculative binning buffer is reported then (nothing out of bounds was
-    written, but that forward's outputs are invalid)."""
+    rasterizer.set_deferred_count).  int() / resolve() waits for the forward's event.  The binning
+    buffer of a deferred forward is sized _HEADROOM x the largest count any view of this shape has
+    produced (HBM is plentiful on B200: 6 B per instance); should a view still overflow it, nothing
+    out of bounds was written, `overflowed` is set and the autograd backward re-runs the forward
+    with the exact size before differentiating (rasterizer._RasterizeGaussians.backward)."""
 
     def __init__(self, event, slot_view, capacity, state, P):
         self._event, self._slot, self._capacity, self._state, self._P = event, slot_view, capacity, state, P
         self._value = None
+        self.overflowed = False
 
     def resolve(self):
         if self._value is None:
             self._event.synchronize()
             self._value = int(self._slot.item())
-            self._state["capacity"] = max(int(self._value * 1.5) + 4096, 4 * self._P + 4096)
+            _observe(self._state, self._value, self._P)
+            if self._state.get("pending") is self:
+                self._state["pending"] = None
             if self._value > self._capacity:
-                raise RuntimeError(
-                    f"deferred rasterization overflowed its speculative binning buffer ({self._value} instances > "
-                    f"capacity {self._capacity}); the outputs of that forward are invalid — call it again")
+                self.overflowed = True
+                self._state["overflows"] += 1
         return self._value
 
     __int__ = __index__ = resolve
@@ -79,7 +95,7 @@ def _prep(t, name):
 def rasterize_gaussians(background, means3D, features, colors, opacity, scales, rotations,
                         scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
                         cx, cy, image_height, image_width, sh, degree, campos, prefiltered,
-                        computer_pseudo_normal, debug, _defer=False):
+                        computer_pseudo_normal, debug, _defer=False, _min_capacity=None):
     """== RasterizeGaussiansCUDA (rasterize_points.cu:36-141).  Returns the 13-tuple
     (rendered, n_contrib, out_color, out_opacity, out_depth, out_feature, out_normal,
      out_surface_xyz, out_weights, radii, geomBuffer, binningBuffer, imgBuffer)."""
@@ -112,47 +128,64 @@ def rasterize_gaussians(background, means3D, features, colors, opacity, scales, 
     imgBuffer = torch.empty((lib.r3dg_raster_img_bytes(W, H),), dtype=torch.uint8, device=dev)
 
     st = _dev_state(dev)
-    if st["capacity"] == 0:
-        _defer = False       # no instance count seen on this device yet: learn it with the synchronous read-back (and retry) once
-    capacity = max(st["capacity"], 4 * P + 4096)
+    shape = (P, W, H)
+    if st["shape"] != shape:             # new model size / resolution (e.g. after densification): re-learn the counts
+        st.update(shape=shape, seen=0, rmax=0, capacity=0)
+    prev = st["pending"]
+    if prev is not None:                 # a deferred forward whose backward never ran: account for it now
+        prev.resolve()
+        if prev.overflowed:
+            import warnings
+            warnings.warn("a deferred-count forward overflowed its binning buffer and was never differentiated; "
+                          "its images were truncated (use the synchronous path for forwards without backward)")
+    if st["seen"] < _LEARN:
+        _defer = False                   # learn the instance counts of this shape with the synchronous read-back first
+    if _min_capacity is not None:
+        capacity = int(_min_capacity)
+    elif _defer:
+        capacity = max(int(st["rmax"] * _HEADROOM) + 4096, 4 * P + 4096)
+    else:
+        capacity = max(st["capacity"], 4 * P + 4096)
     stream = torch.cuda.current_stream(dev)
     slot = st["next"]
     st["next"] = (slot + 1) % _SLOTS
     pinned = st["pinned"][slot:slot + 1]
-    while True:
-        binningBuffer = torch.empty((lib.r3dg_raster_binning_bytes(capacity),), dtype=torch.uint8,
-                                    device=dev)
-        a = _lib.RasterFwdArgs()
-        a.P, a.S, a.D, a.M, a.W, a.H = P, S, int(degree), M, W, H
-        a.background = _ptr(background); a.means3D = _ptr(means3D); a.shs = _ptr(sh)
-        a.colors_precomp = _ptr(colors); a.features = _ptr(features); a.opacities = _ptr(opacity)
-        a.scales = _ptr(scales); a.rotations = _ptr(rotations); a.cov3D_precomp = _ptr(cov3D_precomp)
-        a.viewmatrix = _ptr(viewmatrix); a.projmatrix = _ptr(projmatrix); a.campos = _ptr(campos)
-        a.scale_modifier = float(scale_modifier); a.tan_fovx = float(tan_fovx)
-        a.tan_fovy = float(tan_fovy); a.cx = float(cx); a.cy = float(cy)
-        a.prefiltered = int(bool(prefiltered)); a.computer_pseudo_normal = int(bool(computer_pseudo_normal))
-        a.debug = int(bool(debug))
-        a.out_color = out_color.data_ptr(); a.out_opacity = out_opacity.data_ptr()
-        a.out_depth = out_depth.data_ptr(); a.out_feature = _ptr(out_feature)
-        a.out_normal = out_normal.data_ptr(); a.out_surface_xyz = out_surface_xyz.data_ptr()
-        a.out_weights = _ptr(out_weights); a.radii = _ptr(radii); a.n_contrib = None
-        a.geom = geomBuffer.data_ptr(); a.geom_bytes = geomBuffer.numel()
-        a.img = imgBuffer.data_ptr(); a.img_bytes = imgBuffer.numel()
-        a.binning = binningBuffer.data_ptr(); a.binning_bytes = binningBuffer.numel()
-        a.num_rendered_host = pinned.data_ptr()
-        _lib.check(lib.r3dg_raster_forward(ctypes.byref(a), stream.cuda_stream), "rasterize_gaussians")
-        if _defer:                    # opt-in: let the host run ahead; the count is resolved later
-            ev = torch.cuda.Event()
-            ev.record(stream)
-            rendered = DeferredCount(ev, pinned, capacity, st, P)
-            break
-        stream.synchronize()          # the one readback: num_rendered is part of the return tuple
-        rendered = int(pinned.item())
-        if rendered <= capacity:
-            break
-        capacity = int(rendered * 1.25) + 4096      # speculation missed: rerun with room to spare
+    with torch.cuda.device(dev):
+        while True:
+            binningBuffer = torch.empty((lib.r3dg_raster_binning_bytes(capacity),), dtype=torch.uint8,
+                                        device=dev)
+            a = _lib.RasterFwdArgs()
+            a.P, a.S, a.D, a.M, a.W, a.H = P, S, int(degree), M, W, H
+            a.background = _ptr(background); a.means3D = _ptr(means3D); a.shs = _ptr(sh)
+            a.colors_precomp = _ptr(colors); a.features = _ptr(features); a.opacities = _ptr(opacity)
+            a.scales = _ptr(scales); a.rotations = _ptr(rotations); a.cov3D_precomp = _ptr(cov3D_precomp)
+            a.viewmatrix = _ptr(viewmatrix); a.projmatrix = _ptr(projmatrix); a.campos = _ptr(campos)
+            a.scale_modifier = float(scale_modifier); a.tan_fovx = float(tan_fovx)
+            a.tan_fovy = float(tan_fovy); a.cx = float(cx); a.cy = float(cy)
+            a.prefiltered = int(bool(prefiltered)); a.computer_pseudo_normal = int(bool(computer_pseudo_normal))
+            a.debug = int(bool(debug))
+            a.out_color = out_color.data_ptr(); a.out_opacity = out_opacity.data_ptr()
+            a.out_depth = out_depth.data_ptr(); a.out_feature = _ptr(out_feature)
+            a.out_normal = out_normal.data_ptr(); a.out_surface_xyz = out_surface_xyz.data_ptr()
+            a.out_weights = _ptr(out_weights); a.radii = _ptr(radii); a.n_contrib = None
+            a.geom = geomBuffer.data_ptr(); a.geom_bytes = geomBuffer.numel()
+            a.img = imgBuffer.data_ptr(); a.img_bytes = imgBuffer.numel()
+            a.binning = binningBuffer.data_ptr(); a.binning_bytes = binningBuffer.numel()
+            a.num_rendered_host = pinned.data_ptr()
+            _lib.check(lib.r3dg_raster_forward(ctypes.byref(a), stream.cuda_stream), "rasterize_gaussians")
+            if _defer:                    # opt-in: let the host run ahead; the count is resolved later
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                rendered = DeferredCount(ev, pinned, capacity, st, P)
+                st["pending"] = rendered
+                break
+            stream.synchronize()          # the one readback: num_rendered is part of the return tuple
+            rendered = int(pinned.item())
+            if rendered <= capacity:
+                break
+            capacity = int(rendered * 1.25) + 4096      # speculation missed: rerun with room to spare
     if not _defer:
-        st["capacity"] = max(int(rendered * 1.25) + 4096, 4 * P + 4096)
+        _observe(st, rendered, P)
     off = lib.r3dg_raster_img_n_contrib_offset(W, H)
     n_contrib = imgBuffer[off:off + 4 * H * W].view(torch.int32).view(H, W)   # view, like the reference
     return (rendered, n_contrib, out_color, out_opacity, out_depth, out_feature, out_normal,
@@ -233,8 +266,9 @@ def rasterize_gaussians_backward(background, means3D, features, radii, colors, s
         a.img = imageBuffer.data_ptr(); a.img_bytes = imageBuffer.numel()
         a.binning = binningBuffer.data_ptr(); a.binning_bytes = binningBuffer.numel()
         stream = torch.cuda.current_stream(dev)
-        _lib.check(lib.r3dg_raster_backward(ctypes.byref(a), stream.cuda_stream),
-                   "rasterize_gaussians_backward")
+        with torch.cuda.device(dev):
+            _lib.check(lib.r3dg_raster_backward(ctypes.byref(a), stream.cuda_stream),
+                       "rasterize_gaussians_backward")
     return (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dfeatures, dL_dcov3D, dL_dsh,
             dL_dscales, dL_drotations)
 
@@ -248,9 +282,10 @@ def mark_visible(means3D, viewmatrix, projmatrix):
         means3D = _prep(means3D, "means3D"); viewmatrix = _prep(viewmatrix, "viewmatrix")
         projmatrix = _prep(projmatrix, "projmatrix")
         stream = torch.cuda.current_stream(means3D.device)
-        _lib.check(lib.r3dg_mark_visible(P, means3D.data_ptr(), viewmatrix.data_ptr(),
-                                         projmatrix.data_ptr(), present.data_ptr(),
-                                         stream.cuda_stream), "mark_visible")
+        with torch.cuda.device(means3D.device):
+            _lib.check(lib.r3dg_mark_visible(P, means3D.data_ptr(), viewmatrix.data_ptr(),
+                                             projmatrix.data_ptr(), present.data_ptr(),
+                                             stream.cuda_stream), "mark_visible")
     return present
 
 
@@ -271,9 +306,10 @@ def debug_intermediate(name, P, S, W, H, geomBuffer, imgBuffer, binningBuffer, n
         return out
     nbytes = out.numel() * out.element_size()
     stream = torch.cuda.current_stream(geomBuffer.device)
-    rc = lib.r3dg_raster_debug_copy(spec[0], P, S, W, H, geomBuffer.data_ptr(), imgBuffer.data_ptr(),
-                                    binningBuffer.data_ptr(), binningBuffer.numel(), out.data_ptr(),
-                                    nbytes, stream.cuda_stream)
+    with torch.cuda.device(geomBuffer.device):
+        rc = lib.r3dg_raster_debug_copy(spec[0], P, S, W, H, geomBuffer.data_ptr(), imgBuffer.data_ptr(),
+                                        binningBuffer.data_ptr(), binningBuffer.numel(), out.data_ptr(),
+                                        nbytes, stream.cuda_stream)
     if rc < 0:
         raise RuntimeError(f"debug_intermediate({name}) failed: {rc}")
     return out

@@ -1,6 +1,6 @@
 // C ABI of libr3dg_b200.so (declared in include/r3dg_b200.h).  Orchestration only: all device
 // work is enqueued on the caller's stream; there is no host synchronisation, no allocation and
-// no global state besides the cached SM count.
+// no global state besides the per-device SM-count cache.
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -10,17 +10,15 @@
 using namespace r3dg;
 
 namespace {
-int g_num_sms = 0;
+int g_num_sms[64] = {0};            // per device (the caller may drive several GPUs from one process)
 int num_sms() {
-    if (g_num_sms == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            g_num_sms = n;
-        else
-            g_num_sms = 148;   // B200
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;   // B200
+    if (g_num_sms[dev] == 0) {
+        int n = 0;
+        g_num_sms[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
     }
-    return g_num_sms;
+    return g_num_sms[dev];
 }
 // ---- optional stage profiler: CUDA events recorded on the launching stream between stages ----
 enum { ST_PROJECT = 0, ST_DEPTH_SORT, ST_BIN_COUNT, ST_BIN_OFFSETS, ST_BIN_SCATTER, ST_COMPOSITE, ST_NORMAL, ST_COMPOSITE_BWD,
@@ -197,6 +195,35 @@ int r3dg_bvh_trace_opacity(int P, long long num_rays, const int32_t* nodes, cons
     return launch_bvh_trace(P, num_rays, nodes, aabbs, rays_o, rays_per_origin, origin_offset, rays_d, means3D, covs3D,
                             opacities, normals, num_contributes, rendered_opacity, tmp, tmp_bytes, num_sms(),
                             (cudaStream_t)stream);
+}
+
+int r3dg_sample_incident_dirs(int P, int N, const float* normals, const float* phase, float* dirs, float* areas, r3dg_stream_t stream) {
+    if (P < 0 || N < 0) return R3DG_ERR_BAD_ARG;
+    g_launches += (P > 0 && N > 0) ? 1 : 0;
+    return launch_sample_dirs(P, N, normals, phase, dirs, areas, num_sms(), (cudaStream_t)stream);
+}
+
+int r3dg_bvh_bake_visibility(int P, int first_slot, int count, int N, const int32_t* nodes, const float* aabbs,
+                             const float* means3D, const float* covs3D, const float* opacities, const float* normals,
+                             float origin_offset, int32_t* num_contributes, float* visibility, float* dirs, float* areas,
+                             void* tmp, size_t tmp_bytes, r3dg_stream_t stream) {
+    if (P < 0 || count < 0 || N < 0) return R3DG_ERR_BAD_ARG;
+    g_launches += (P > 0 && count > 0 && N > 0) ? 2 : 0;
+    return launch_bvh_bake(P, first_slot, count, N, nodes, aabbs, means3D, covs3D, opacities, normals, origin_offset,
+                           num_contributes, visibility, dirs, areas, tmp, tmp_bytes, num_sms(), (cudaStream_t)stream);
+}
+
+int r3dg_unpremultiply_forward(int S, long long HW, const float* feature, const float* opacity, const int32_t* n_contrib,
+                               float* out, r3dg_stream_t stream) {
+    if (S < 0 || HW < 0) return R3DG_ERR_BAD_ARG;
+    g_launches += (S > 0 && HW > 0) ? 1 : 0;
+    return launch_unpremultiply_forward(S, HW, feature, opacity, n_contrib, out, num_sms(), (cudaStream_t)stream);
+}
+int r3dg_unpremultiply_backward(int S, long long HW, const float* feature, const float* opacity, const int32_t* n_contrib,
+                                const float* dL_dout, float* dL_dfeature, float* dL_dopacity, r3dg_stream_t stream) {
+    if (S < 0 || HW < 0) return R3DG_ERR_BAD_ARG;
+    g_launches += HW > 0 ? 1 : 0;
+    return launch_unpremultiply_backward(S, HW, feature, opacity, n_contrib, dL_dout, dL_dfeature, dL_dopacity, num_sms(), (cudaStream_t)stream);
 }
 
 // ---- simple_knn._C.distCUDA2 ----------------------------------------------------------------

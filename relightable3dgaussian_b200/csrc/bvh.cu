@@ -12,7 +12,8 @@
 //    four per-Gaussian arrays at a leaf, from a per-thread local-memory stack.  Here the tree is
 //    re-packed once per trace call into 64 B internal packets {children, both child boxes} and
 //    64 B leaf records {mean, inverse covariance, opacity, normal} stored in Morton order, so one
-//    aligned 4x16 B fetch serves a whole traversal step; stacks live in shared memory; warps are
+//    aligned 4x16 B fetch serves a whole traversal step; the top 20 stack levels live in shared memory
+//    (deeper ones spill to a local array: 10 KB instead of 32 KB per CTA); warps are
 //    persistent and refill finished lanes from a global ray counter (ray-stack compaction), so the
 //    early exit at T < 0.9 does not idle lanes.  Per ray the visiting order (far child pushed
 //    first) is the reference's, hence the product order of (1 - alpha) too.
@@ -288,17 +289,100 @@ __device__ __forceinline__ float ray_box_tmax(float b0, float b1, float b2, floa
     return tmax;
 }
 
+// ---- incident-direction sampling (reference utils/graphics_utils.py:9-37 fibonacci_sphere_sampling with
+// random_rotate=False — the bake always samples deterministically, scene/gaussian_model.py:324 — and
+// utils/sh_utils.py:36-68 rotation_between_z), restated with torch's op-by-op fp32 rounding -------------
+// Canonical sample i of N (the [1,3,N] `z_samples` tensor of the reference): computed per CTA into shared
+// memory by whoever needs it; identical for every Gaussian.
+__device__ __forceinline__ float3 fib_sample(int i, int N) {
+    const float idx = (float)i;
+    // z = (1 - 2*idx/(2N-1)).clamp_min(sin(10 deg));  rad = sqrt(1 - z**2);  theta = delta*idx
+    const float z = fmaxf(sub_(1.0f, div_(mul_(2.0f, idx), (float)(2 * N - 1))), 0.17364817766693033f);
+    const float rad = sqrt_(sub_(1.0f, mul_(z, z)));
+    const float theta = mul_(2.399963229728653f, idx);          // pi * (3 - sqrt(5))
+    return make_float3(mul_(sinf(theta), rad), mul_(cosf(theta), rad), z);
+}
+// R(normal) @ sample, then F.normalize: the rotation taking +z to `normal` (Rodrigues from z; -I when n.z + 1 <= 0).
+// With v = (-n.y, n.x, 0) the reference's nine entries reduce exactly (x + 0 == x, -0 - x == -x in IEEE) to the ones below.
+__device__ __forceinline__ float3 rotate_from_z(float nx, float ny, float nz, float3 s) {
+    float r00, r01, r02, r10, r11, r12, r20, r21, r22;
+    const float zp1 = add_(nz, 1.0f);
+    if (zp1 > 0.0f) {
+        const float v1 = -ny, v2 = nx, c = fmaxf(zp1, 1e-7f);
+        const float v11 = mul_(v1, v1), v22 = mul_(v2, v2), v12 = mul_(v1, v2);
+        r00 = add_(1.0f, div_(-v22, c)); r01 = div_(v12, c);             r02 = v2;
+        r10 = div_(v12, c);             r11 = add_(1.0f, div_(-v11, c)); r12 = -v1;
+        r20 = -v2;                      r21 = v1;                        r22 = add_(1.0f, div_(sub_(-v22, v11), c));
+    } else {
+        r00 = r11 = r22 = -1.0f; r01 = r02 = r10 = r12 = r20 = r21 = 0.0f;
+    }
+    // the [P,3,3] @ [1,3,N] matmul: K = 3 accumulated in order (fp32 FMA chain, as cuBLAS sgemm does)
+    const float x = fma_(r02, s.z, fma_(r01, s.y, mul_(r00, s.x)));
+    const float y = fma_(r12, s.z, fma_(r11, s.y, mul_(r10, s.x)));
+    const float z = fma_(r22, s.z, fma_(r21, s.y, mul_(r20, s.x)));
+    const float nrm = fmaxf(sqrt_(fma_(z, z, fma_(y, y, mul_(x, x)))), 1e-12f);   // F.normalize eps
+    return make_float3(div_(x, nrm), div_(y, nrm), div_(z, nrm));
+}
+
+// phase != nullptr: random_rotate=True — theta_i += phase[g] * 2 * pi with phase = torch.rand(P) drawn by the caller
+__global__ void __launch_bounds__(256) sample_dirs_kernel(int P, int N, const float* __restrict__ normals,
+                                                          const float* __restrict__ phase,
+                                                          float* __restrict__ dirs, float* __restrict__ areas) {
+    extern __shared__ float3 sSample[];
+    for (int i = threadIdx.x; i < N; i += blockDim.x) sSample[i] = fib_sample(i, N);
+    __syncthreads();
+    const long long total = (long long)P * N;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += (long long)gridDim.x * blockDim.x) {
+        const long long g = r / N;
+        const int i = (int)(r - g * N);
+        float3 smp = sSample[i];
+        if (phase) {          // theta = rand * 2 * pi + delta * idx  (graphics_utils.py:24-25)
+            const float rad = sqrt_(sub_(1.0f, mul_(smp.z, smp.z)));
+            const float theta = add_(mul_(mul_(phase[g], 2.0f), 3.141592653589793f), mul_(2.399963229728653f, (float)i));
+            smp.x = mul_(sinf(theta), rad); smp.y = mul_(cosf(theta), rad);
+        }
+        const float3 d = rotate_from_z(normals[3 * g], normals[3 * g + 1], normals[3 * g + 2], smp);
+        dirs[3 * r] = d.x; dirs[3 * r + 1] = d.y; dirs[3 * r + 2] = d.z;
+        if (areas) areas[r] = 6.283185307179586f;                 // ones * 2 * pi
+    }
+}
+
 #define TRACE_THREADS 128
-#define TRACE_STACK 64
+#define TRACE_STACK 64          // total per-ray stack capacity (the reference's local array is 64 too, trace.cuh)
+#define TRACE_STACK_SH 20       // entries kept in shared memory; deeper levels spill to a per-thread local array
+// BAKE = false: explicit rays (rays_o [num_rays / o_group, 3], rays_d [num_rays, 3]) — trace_bvh_opacity.
+// BAKE = true : the visibility bake: ray r = (leaf slot first_slot + r / N, sample r % N); the Gaussian is the
+//   slot's object (Morton order => neighbouring warps walk neighbouring subtrees), the origin its mean, the
+//   direction is generated HERE from its normal (never read from HBM) and written once to `dirs_out` together
+//   with the constant area; results land at the Gaussian's own row g * N + i.
+template <bool BAKE>
 __global__ void __launch_bounds__(TRACE_THREADS) bvh_trace_kernel(int P, long long num_rays, const float4* __restrict__ packets,
                                                                   const float* __restrict__ rays_o, int o_group, float o_offset,
                                                                   const float* __restrict__ rays_d, int32_t* __restrict__ num_contributes,
-                                                                  float* __restrict__ rendered_opacity, unsigned long long* counter) {
-    __shared__ int sStack[TRACE_STACK][TRACE_THREADS];
+                                                                  float* __restrict__ rendered_opacity, unsigned long long* counter,
+                                                                  int N, int first_slot, const int32_t* __restrict__ nodes,
+                                                                  float* __restrict__ dirs_out, float* __restrict__ areas_out) {
+    __shared__ int sStack[TRACE_STACK_SH][TRACE_THREADS];
+    extern __shared__ float3 sSample[];
+    int lStack[TRACE_STACK - TRACE_STACK_SH];
     const int tid = threadIdx.x, lane = tid & 31;
     const int NI = P - 1;
+    if (BAKE) {
+        for (int i = tid; i < N; i += TRACE_THREADS) sSample[i] = fib_sample(i, N);
+        __syncthreads();
+    }
+    auto push = [&](int& sp, int v) {
+        if (sp < TRACE_STACK_SH) sStack[sp][tid] = v;
+        else if (sp < TRACE_STACK) lStack[sp - TRACE_STACK_SH] = v;
+        else return;                                       // deeper than the reference's own stack (it prints and drops too)
+        ++sp;
+    };
+    auto pop = [&](int& sp) {
+        --sp;
+        return sp < TRACE_STACK_SH ? sStack[sp][tid] : lStack[sp - TRACE_STACK_SH];
+    };
     bool has_ray = false, exhausted = false;
-    long long ray = 0;
+    long long ray = 0, out = 0;
     int sp = 0, count = 0;
     float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, T = 1.0f;
     while (true) {
@@ -312,14 +396,29 @@ __global__ void __launch_bounds__(TRACE_THREADS) bvh_trace_kernel(int P, long lo
             if (!has_ray && !exhausted) {
                 ray = (long long)base + __popc(want & ((1u << lane) - 1u));
                 if (ray < num_rays) {
-                    dx = rays_d[3 * ray]; dy = rays_d[3 * ray + 1]; dz = rays_d[3 * ray + 2];
-                    const long long oi = ray / o_group;
-                    ox = rays_o[3 * oi]; oy = rays_o[3 * oi + 1]; oz = rays_o[3 * oi + 2];
+                    if (BAKE) {
+                        const long long slot = ray / N;
+                        const int i = (int)(ray - slot * N);
+                        const float4* q = packets + (size_t)(NI + first_slot + slot) * 4;     // the slot's own leaf record
+                        const float4 q0 = q[0], q2 = q[2], q3 = q[3];
+                        const long long g = nodes[(size_t)(NI + first_slot + slot) * 5 + 3];
+                        const float3 d = rotate_from_z(q2.z, q2.w, q3.x, sSample[i]);
+                        dx = d.x; dy = d.y; dz = d.z;
+                        ox = q0.x; oy = q0.y; oz = q0.z;
+                        out = g * N + i;
+                        if (dirs_out) { dirs_out[3 * out] = dx; dirs_out[3 * out + 1] = dy; dirs_out[3 * out + 2] = dz; }
+                        if (areas_out) areas_out[out] = 6.283185307179586f;
+                    } else {
+                        dx = rays_d[3 * ray]; dy = rays_d[3 * ray + 1]; dz = rays_d[3 * ray + 2];
+                        const long long oi = ray / o_group;
+                        ox = rays_o[3 * oi]; oy = rays_o[3 * oi + 1]; oz = rays_o[3 * oi + 2];
+                        out = ray;
+                    }
                     if (o_offset != 0.0f) {                    // rays_o + rays_d * 0.05 (bvh/__init__.py:63), torch op order
                         ox = add_(ox, mul_(dx, o_offset)); oy = add_(oy, mul_(dy, o_offset)); oz = add_(oz, mul_(dz, o_offset));
                     }
                     has_ray = true; T = 1.0f; count = 0;
-                    sp = 0; sStack[sp++][tid] = NI == 0 ? -1 : 0;      // root (a lone leaf when P == 1)
+                    sp = 0; push(sp, NI == 0 ? -1 : 0);        // root (a lone leaf when P == 1)
                 } else {
                     exhausted = true;
                 }
@@ -329,7 +428,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) bvh_trace_kernel(int P, long lo
         // ---- a bounded burst of traversal steps, then look for idle lanes again -----------------
 #pragma unroll 1
         for (int step = 0; step < 24 && has_ray; ++step) {
-            const int node = sStack[--sp][tid];
+            const int node = pop(sp);
             if (node >= 0) {
                 const float4* p = packets + (size_t)node * 4;
                 const float4 p0 = p[0], p1 = p[1], p2 = p[2], p3 = p[3];
@@ -337,11 +436,11 @@ __global__ void __launch_bounds__(TRACE_THREADS) bvh_trace_kernel(int P, long lo
                 const float lmax = ray_box_tmax(p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, ox, oy, oz, dx, dy, dz);
                 const float rmax = ray_box_tmax(p2.x, p2.y, p2.z, p2.w, p3.x, p3.y, ox, oy, oz, dx, dy, dz);
                 if (lmax > rmax) {                                    // trace.cu:258-272: far child first
-                    if (lmax > 0 && sp < TRACE_STACK) sStack[sp++][tid] = l;
-                    if (rmax > 0 && sp < TRACE_STACK) sStack[sp++][tid] = r;
+                    if (lmax > 0) push(sp, l);
+                    if (rmax > 0) push(sp, r);
                 } else {
-                    if (rmax > 0 && sp < TRACE_STACK) sStack[sp++][tid] = r;
-                    if (lmax > 0 && sp < TRACE_STACK) sStack[sp++][tid] = l;
+                    if (rmax > 0) push(sp, r);
+                    if (lmax > 0) push(sp, l);
                 }
             } else {
                 const float4* p = packets + (size_t)(NI - node - 1) * 4;    // leaf slot = -node - 1
@@ -364,7 +463,8 @@ __global__ void __launch_bounds__(TRACE_THREADS) bvh_trace_kernel(int P, long lo
                             const float alpha = op * __expf(power);
                             T *= 1 - alpha;
                             if (T < 0.9f) {                          // trace.cu:251-254
-                                rendered_opacity[ray] = 0.0f; num_contributes[ray] = 0;
+                                rendered_opacity[out] = 0.0f;
+                                if (num_contributes) num_contributes[out] = 0;
                                 has_ray = false;
                             }
                         }
@@ -372,7 +472,8 @@ __global__ void __launch_bounds__(TRACE_THREADS) bvh_trace_kernel(int P, long lo
                 }
             }
             if (has_ray && sp == 0) {
-                num_contributes[ray] = count; rendered_opacity[ray] = T;
+                if (num_contributes) num_contributes[out] = count;
+                rendered_opacity[out] = T;
                 has_ray = false;
             }
         }
@@ -419,6 +520,11 @@ int launch_bvh_build(int P, int32_t* nodes, float* aabbs, uint64_t* morton, void
     return 0;
 }
 
+static int trace_blocks(long long num_rays, int num_sms) {
+    const long long want = (num_rays + TRACE_THREADS - 1) / TRACE_THREADS;
+    return (int)(want < (long long)num_sms * 16 ? want : (long long)num_sms * 16);
+}
+
 int launch_bvh_trace(int P, long long num_rays, const int32_t* nodes, const float* aabbs, const float* rays_o,
                      int o_group, float o_offset, const float* rays_d, const float* means3D, const float* covs3D,
                      const float* opacities, const float* normals, int32_t* num_contributes, float* rendered_opacity,
@@ -429,10 +535,37 @@ int launch_bvh_trace(int P, long long num_rays, const int32_t* nodes, const floa
     float4* packets = (float4*)((char*)packets_ + 256);
     R3DG_CUDA_TRY(cudaMemsetAsync(counter, 0, 8, stream));
     bvh_pack_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, nodes, aabbs, means3D, covs3D, opacities, normals, packets);
-    const long long want = (num_rays + TRACE_THREADS - 1) / TRACE_THREADS;
-    const int blocks = (int)(want < (long long)num_sms * 12 ? want : (long long)num_sms * 12);
-    bvh_trace_kernel<<<blocks, TRACE_THREADS, 0, stream>>>(P, num_rays, packets, rays_o, o_group, o_offset, rays_d,
-                                                           num_contributes, rendered_opacity, counter);
+    bvh_trace_kernel<false><<<trace_blocks(num_rays, num_sms), TRACE_THREADS, 0, stream>>>(
+        P, num_rays, packets, rays_o, o_group, o_offset, rays_d, num_contributes, rendered_opacity, counter, 1, 0, nodes, nullptr, nullptr);
+    R3DG_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int launch_sample_dirs(int P, int N, const float* normals, const float* phase, float* dirs, float* areas, int num_sms, cudaStream_t stream) {
+    if (P <= 0 || N <= 0) return 0;
+    if ((size_t)N * sizeof(float3) > 48 * 1024) return R3DG_ERR_UNSUPPORTED;          // N <= 4096
+    const long long total = (long long)P * N;
+    const long long want = (total + 255) / 256;
+    const int blocks = (int)(want < (long long)num_sms * 16 ? want : (long long)num_sms * 16);
+    sample_dirs_kernel<<<blocks, 256, (size_t)N * sizeof(float3), stream>>>(P, N, normals, phase, dirs, areas);
+    R3DG_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int launch_bvh_bake(int P, int first_slot, int count, int N, const int32_t* nodes, const float* aabbs, const float* means3D,
+                    const float* covs3D, const float* opacities, const float* normals, float o_offset,
+                    int32_t* num_contributes, float* visibility, float* dirs, float* areas, void* packets_,
+                    size_t packets_bytes, int num_sms, cudaStream_t stream) {
+    if (P <= 0 || count <= 0 || N <= 0) return 0;
+    if (packets_bytes < bvh_packets_bytes(P) || first_slot < 0 || first_slot + count > P) return R3DG_ERR_BAD_ARG;
+    if ((size_t)N * sizeof(float3) > 32 * 1024) return R3DG_ERR_UNSUPPORTED;
+    unsigned long long* counter = (unsigned long long*)packets_;
+    float4* packets = (float4*)((char*)packets_ + 256);
+    R3DG_CUDA_TRY(cudaMemsetAsync(counter, 0, 8, stream));
+    bvh_pack_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, nodes, aabbs, means3D, covs3D, opacities, normals, packets);
+    const long long num_rays = (long long)count * N;
+    bvh_trace_kernel<true><<<trace_blocks(num_rays, num_sms), TRACE_THREADS, (size_t)N * sizeof(float3), stream>>>(
+        P, num_rays, packets, nullptr, 1, o_offset, nullptr, num_contributes, visibility, counter, N, first_slot, nodes, dirs, areas);
     R3DG_CUDA_TRY(cudaGetLastError());
     return 0;
 }

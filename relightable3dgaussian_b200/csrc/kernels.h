@@ -42,6 +42,16 @@ int launch_bvh_trace(int P, long long num_rays, const int32_t* nodes, const floa
                      const float* normals, int32_t* num_contributes, float* rendered_opacity,
                      void* packets, size_t packets_bytes, int num_sms, cudaStream_t stream);
 
+int launch_sample_dirs(int P, int N, const float* normals, const float* phase, float* dirs, float* areas, int num_sms, cudaStream_t stream);
+int launch_bvh_bake(int P, int first_slot, int count, int N, const int32_t* nodes, const float* aabbs, const float* means3D,
+                    const float* covs3D, const float* opacities, const float* normals, float o_offset,
+                    int32_t* num_contributes, float* visibility, float* dirs, float* areas, void* packets,
+                    size_t packets_bytes, int num_sms, cudaStream_t stream);
+int launch_unpremultiply_forward(int S, long long HW, const float* feature, const float* opacity, const int32_t* n_contrib,
+                                 float* out, int num_sms, cudaStream_t stream);
+int launch_unpremultiply_backward(int S, long long HW, const float* feature, const float* opacity, const int32_t* n_contrib,
+                                  const float* g, float* d_feature, float* d_opacity, int num_sms, cudaStream_t stream);
+
 int shade_tune(const char* key, int value, int* previous);
 
 // adam.cu: one launch per <= 16 parameter tensors

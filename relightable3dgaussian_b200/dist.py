@@ -62,8 +62,12 @@ class FactoredGradExchange:
     (12 B per Gaussian and view) and a local kernel that rebuilds mean_v(dL_dsh) — identical on all
     ranks (fixed summation order), equal to the dense all-reduce up to fp32 summation order.
 
-    Usage: `rasterize_gaussians_backward(..., _out=ex.views)`, then
-    `ex.exchange(means3D, campos_of_all_ranks, degree)`; gradients are `ex.grads[name]`.
+    Two ways to use it.  Operator level (the caller owns the per-Gaussian tensors as leaves, e.g.
+    bench.py's resident path): `rasterize_gaussians_backward(..., _out=ex.views)`, then
+    `ex.exchange(means3D, campos_of_all_ranks, degree)`; gradients are `ex.grads[name]`.  Autograd
+    level (`rasterizer.set_grad_exchange`): only the SH factor goes through this object — the dense
+    rest is averaged at the leaf parameters (`LeafGradBucket`), because the maps from the leaves to
+    `features` / `means3D` are view dependent in the reference's render functions.
     `gather_factors()` is pure torch.distributed (runs under gloo in the CPU tests); the rebuild is
     the CUDA kernel (no CPU path)."""
 
@@ -86,7 +90,8 @@ class FactoredGradExchange:
     def gather_factors(self, group=None):
         if self.world > 1:
             # output viewed as the dim-0 concatenation [world*P, 3] (the layout gloo insists on; NCCL accepts both)
-            dist.all_gather_into_tensor(self.gathered.view(self.world * self.P, 3), self.factor, group=group)
+            gather = getattr(dist, "all_gather_into_tensor", None) or dist._all_gather_base      # torch 1.12 (readme.md:26) has only the latter
+            gather(self.gathered.view(self.world * self.P, 3), self.factor, group=group)
         return self.gathered
 
     def rebuild_sh(self, means3D, campos_all, degree):
@@ -98,15 +103,82 @@ class FactoredGradExchange:
         if not means3D.is_cuda:
             raise RuntimeError("FactoredGradExchange.rebuild_sh runs on the GPU only (no CPU path)")
         dev = means3D.device
-        _lib.check(lib.r3dg_sh_grad_from_factors(self.P, int(degree), self.M, self.world, means3D.data_ptr(), campos_all.data_ptr(),
-                                                 self.gathered.data_ptr(), 1.0 / self.world, self.sh.data_ptr(),
-                                                 torch.cuda.current_stream(dev).cuda_stream), "sh_grad_from_factors")
+        with torch.cuda.device(dev):
+            _lib.check(lib.r3dg_sh_grad_from_factors(self.P, int(degree), self.M, self.world, means3D.data_ptr(), campos_all.data_ptr(),
+                                                     self.gathered.data_ptr(), 1.0 / self.world, self.sh.data_ptr(),
+                                                     torch.cuda.current_stream(dev).cuda_stream), "sh_grad_from_factors")
         return self.sh
 
     def exchange(self, means3D, campos_all, degree, group=None):
         self.dense.allreduce_mean(group=group)
         self.gather_factors(group=group)
         return self.rebuild_sh(means3D, campos_all, degree)
+
+
+class LeafGradBucket:
+    """Flat fp32 buffer holding the `.grad` of a list of LEAF parameters as views, so that one
+    collective averages a whole N-view step at the place where averaging is always valid: the leaf
+    parameters, after `loss.backward()` (every view-dependent map between the leaves and the
+    rasterizer inputs — depth channels, brdf_color(viewdirs), viewdirs(means3D) — has been
+    back-propagated by then; gradient paths that bypass the rasterizer, e.g. the environment map or
+    regularisers, are covered too).  Autograd accumulates into the views in place, so no packing copy
+    precedes the collective.  Usage per step: `zero()`, `loss.backward()`, `allreduce_mean()`.
+    Parameters whose gradient is exchanged elsewhere (the SH leaves under `rasterizer.set_grad_exchange`)
+    are simply left out of `params`."""
+
+    def __init__(self, params, device=None):
+        self.params = [p for p in params]
+        device = device if device is not None else self.params[0].device
+        sizes = [p.numel() for p in self.params]
+        self.offsets, off = [], 0
+        for n in sizes:
+            self.offsets.append(off)
+            off += (n + 127) // 128 * 128
+        self.flat = torch.zeros(max(off, 1), dtype=torch.float32, device=device)
+        self.views = [self.flat[o:o + n].view(p.shape) for p, o, n in zip(self.params, self.offsets, sizes)]
+        self.attach()
+
+    def attach(self):
+        """(Re-)bind every parameter's `.grad` to its view (call again after `p.grad = None`)."""
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+    def zero(self):
+        self.flat.zero_()
+        self.attach()
+
+    def bytes(self):
+        return self.flat.numel() * 4
+
+    def allreduce_mean(self, group=None, async_op=False):
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return None
+        for p, v in zip(self.params, self.views):          # a backward that replaced .grad (e.g. set_to_none) is copied in
+            if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+                v.copy_(p.grad)
+                p.grad = v
+        if dist.get_backend(group) == "nccl":
+            return dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group, async_op=async_op)
+        self.flat.mul_(1.0 / dist.get_world_size(group))
+        return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+def average_leaf_grads(params, group=None, skip=()):
+    """One-off form of LeafGradBucket for callers that keep their own `.grad` tensors: averages
+    `p.grad` of every parameter not in `skip` over the ranks (one all-reduce per tensor, in place)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    world = dist.get_world_size(group)
+    skip_ids = {id(p) for p in skip}
+    nccl = dist.get_backend(group) == "nccl"
+    for p in params:
+        if id(p) in skip_ids or p.grad is None:
+            continue
+        if nccl:
+            dist.all_reduce(p.grad, op=dist.ReduceOp.AVG, group=group)
+        else:
+            p.grad.mul_(1.0 / world)
+            dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=group)
 
 
 def allreduce_densification_stats(weights, xyz_grad_norm, normal_grad_norm, update_filter, radii, group=None):

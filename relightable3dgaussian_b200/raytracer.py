@@ -1,69 +1,65 @@
-"""Host-side mirror of the reference's BVH operator surface: `RayTracer` (bvh/__init__.py:28-71),
-`sample_incident_rays` / `fibonacci_sphere_sampling` / `rotation_between_z`
-(scene/gaussian_model.py:20-28, utils/graphics_utils.py:9-37, utils/sh_utils.py:36-68) and the
-visibility bake `update_visibility` (scene/gaussian_model.py:312-342), on the B200 kernels.
+"""Host-side mirror of the reference's BVH operator surface — `RayTracer` (bvh/__init__.py:28-71),
+`sample_incident_rays` / `fibonacci_sphere_sampling` (scene/gaussian_model.py:20-28,
+utils/graphics_utils.py:9-37, utils/sh_utils.py:36-68) and the visibility bake `update_visibility`
+(scene/gaussian_model.py:312-342) — as thin marshalling over the B200 kernels.  No sampling or
+tracing arithmetic lives in this file: directions come from `r3dg_sample_incident_dirs`, the bake
+from `r3dg_bvh_bake_visibility` (directions generated inside the trace kernel, written once).
 
 Differences from the reference that are not observable in the results:
   * the ~60 small PyTorch kernels of RayTracer.__init__ are one fused kernel (same fp32 rounding);
-  * trace_visibility does not materialise `rays_o + 0.05 * rays_d` nor the expanded origins: the
-    trace kernel forms them per ray (same fp32 ops), saving 24 B/ray of HBM traffic.
+  * trace_visibility does not materialise `rays_o + 0.05 * rays_d` nor the expanded origins;
+  * update_visibility is ONE launch over all Gaussians in Morton order instead of the reference's
+    chunk loop (the chunks only bound the size of its [chunk,N,3] PyTorch temporaries); the
+    `[P,N,3]` ray-origin / ray-direction inputs of the reference's trace call never exist.
 """
-import numpy as np
 import torch
-import torch.nn.functional as F
 
 from . import _C_bvh as _C
 from . import _lib
 
 
-def rotation_between_z(vec):
-    """utils/sh_utils.py:36-68 (device-agnostic restatement)."""
-    v1, v2 = -vec[..., 1], vec[..., 0]
-    v3 = torch.zeros_like(v1)
-    v11, v22, v33 = v1 * v1, v2 * v2, v3 * v3
-    v12, v13, v23 = v1 * v2, v1 * v3, v2 * v3
-    cos_p_1 = (vec[..., 2] + 1).clamp_min(1e-7)
-    R = torch.zeros(vec.shape[:-1] + (3, 3), dtype=torch.float32, device=vec.device)
-    R[..., 0, 0] = 1 + (-v33 - v22) / cos_p_1
-    R[..., 0, 1] = -v3 + v12 / cos_p_1
-    R[..., 0, 2] = v2 + v13 / cos_p_1
-    R[..., 1, 0] = v3 + v12 / cos_p_1
-    R[..., 1, 1] = 1 + (-v33 - v11) / cos_p_1
-    R[..., 1, 2] = -v1 + v23 / cos_p_1
-    R[..., 2, 0] = -v2 + v13 / cos_p_1
-    R[..., 2, 1] = v1 + v23 / cos_p_1
-    R[..., 2, 2] = 1 + (-v22 - v11) / cos_p_1
-    return torch.where((vec[..., 2] + 1 > 0)[..., None, None], R,
-                       -torch.eye(3, dtype=torch.float32, device=vec.device).expand_as(R))
+def _f32(t):
+    return t.detach().float().contiguous()
 
 
 def fibonacci_sphere_sampling(normals, sample_num, random_rotate=True):
-    """utils/graphics_utils.py:9-37."""
+    """utils/graphics_utils.py:9-37: (incident_dirs [...,N,3], incident_areas [...,N,1]).  With
+    random_rotate the per-Gaussian phase is drawn here with torch.rand (as the reference does) and
+    applied in the kernel."""
+    lib = _lib.load()
     pre_shape = normals.shape[:-1]
-    if len(pre_shape) > 1:
-        normals = normals.reshape(-1, 3)
-    delta = np.pi * (3.0 - np.sqrt(5.0))
-    idx = torch.arange(sample_num, dtype=torch.float, device=normals.device)[None]
-    z = (1 - 2 * idx / (2 * sample_num - 1)).clamp_min(np.sin(10 / 180 * np.pi))
-    rad = torch.sqrt(1 - z ** 2)
-    theta = delta * idx
-    if random_rotate:
-        theta = torch.rand(*pre_shape, 1, device=normals.device) * 2 * np.pi + theta
-    y = torch.cos(theta) * rad
-    x = torch.sin(theta) * rad
-    z_samples = torch.stack([x, y, z.expand_as(y)], dim=-2)
-    incident_dirs = rotation_between_z(normals) @ z_samples
-    incident_dirs = F.normalize(incident_dirs, dim=-2).transpose(-1, -2)
-    incident_areas = torch.ones_like(incident_dirs)[..., 0:1] * 2 * np.pi
-    if len(pre_shape) > 1:
-        incident_dirs = incident_dirs.reshape(*pre_shape, sample_num, 3)
-        incident_areas = incident_areas.reshape(*pre_shape, sample_num, 1)
-    return incident_dirs, incident_areas
+    n = _f32(normals).reshape(-1, 3)
+    P, N = n.shape[0], int(sample_num)
+    if not n.is_cuda:
+        raise RuntimeError("fibonacci_sphere_sampling runs on the GPU only (no CPU path)")
+    dirs = torch.empty((P, N, 3), dtype=torch.float32, device=n.device)
+    areas = torch.empty((P, N, 1), dtype=torch.float32, device=n.device)
+    phase = torch.rand(P, device=n.device) if random_rotate else None
+    if P > 0 and N > 0:
+        with torch.cuda.device(n.device):
+            _lib.check(lib.r3dg_sample_incident_dirs(P, N, n.data_ptr(), None if phase is None else phase.data_ptr(),
+                                                     dirs.data_ptr(), areas.data_ptr(),
+                                                     torch.cuda.current_stream(n.device).cuda_stream), "sample_incident_dirs")
+    return dirs.reshape(*pre_shape, N, 3), areas.reshape(*pre_shape, N, 1)
 
 
 def sample_incident_rays(normals, is_training=False, sample_num=24):
     """scene/gaussian_model.py:20-28."""
     return fibonacci_sphere_sampling(normals, sample_num, random_rotate=bool(is_training))
+
+
+def inverse_covariance(scaling, rotation, scaling_modifier=1.0):
+    """`GaussianModel.get_inverse_covariance` (scene/gaussian_model.py:257-260): the symmetric 6-vector of
+    L L^T with L = R(q) diag(1 / (s / modifier))  (utils/general_utils.py:66-79,151-160).  Init-time host
+    PyTorch in the reference too (a handful of [P,3,3] ops, once per bake)."""
+    q = torch.nn.functional.normalize(rotation.float(), dim=-1)
+    r, x, y, z = q.unbind(-1)
+    R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+                     2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                     2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], dim=-1).view(-1, 3, 3)
+    L = R * ((1.0 / scaling.float()) * (1.0 / scaling_modifier)).unsqueeze(1)
+    cov = L @ L.transpose(1, 2)
+    return torch.stack([cov[:, 0, 0], cov[:, 0, 1], cov[:, 0, 2], cov[:, 1, 1], cov[:, 1, 2], cov[:, 2, 2]], dim=-1).contiguous()
 
 
 class RayTracer:
@@ -75,10 +71,11 @@ class RayTracer:
         dev = means3D.device
         nodes = torch.empty((2 * P - 1, 5), dtype=torch.int32, device=dev)
         aabbs = torch.empty((2 * P - 1, 6), dtype=torch.float32, device=dev)
-        m, s, r = (t.detach().float().contiguous() for t in (means3D, scales, rotations))
+        m, s, r = _f32(means3D), _f32(scales), _f32(rotations)
         stream = torch.cuda.current_stream(dev)
-        _lib.check(lib.r3dg_bvh_leaf_aabbs(P, m.data_ptr(), s.data_ptr(), r.data_ptr(), nodes.data_ptr(),
-                                           aabbs.data_ptr(), stream.cuda_stream), "RayTracer leaf boxes")
+        with torch.cuda.device(dev):
+            _lib.check(lib.r3dg_bvh_leaf_aabbs(P, m.data_ptr(), s.data_ptr(), r.data_ptr(), nodes.data_ptr(),
+                                               aabbs.data_ptr(), stream.cuda_stream), "RayTracer leaf boxes")
         self.tree, self.aabb, self.morton = _C.create_bvh(m, s, r, nodes, aabbs)
 
     @torch.no_grad()
@@ -91,6 +88,39 @@ class RayTracer:
         cotrib, opa = _C._trace(self.tree, self.aabb, rays_o, group, 0.05, rays_d, means3D, symm_inv, opacity, normals)
         return {"visibility": opa.unsqueeze(-1), "contribute": cotrib.unsqueeze(-1)}
 
+    @torch.no_grad()
+    def bake_visibility(self, means3D, symm_inv, opacity, normals, sample_num, first_slot=0, count=None, out=None,
+                        want_contribute=False, write_dirs=True):
+        """The whole of the reference's bake loop body for leaf slots [first_slot, first_slot + count) in one
+        launch (r3dg_bvh_bake_visibility).  Returns dict(visibility [P,N,1], incident_dirs [P,N,3],
+        incident_areas [P,N,1][, contribute]); rows of Gaussians outside the slot range keep the content of
+        `out` (zero-initialised when not given) — that is what the sharded bake sums over the ranks."""
+        lib = _lib.load()
+        P, N = means3D.shape[0], int(sample_num)
+        dev = means3D.device
+        count = P - first_slot if count is None else count
+        f = dict(dtype=torch.float32, device=dev)
+        if out is None:
+            partial = first_slot != 0 or count != P
+            mk = torch.zeros if partial else torch.empty
+            out = {"visibility": mk((P, N, 1), **f)}
+            if write_dirs:
+                out.update(incident_dirs=mk((P, N, 3), **f), incident_areas=mk((P, N, 1), **f))
+            if want_contribute:
+                out["contribute"] = mk((P, N, 1), dtype=torch.int32, device=dev)
+        m, ci, op, nr = _f32(means3D), _f32(symm_inv), _f32(opacity), _f32(normals)
+        tmp = torch.empty((lib.r3dg_bvh_trace_tmp_bytes(P),), dtype=torch.uint8, device=dev)
+        contrib = out.get("contribute")
+        if P > 0 and N > 0 and count > 0:
+            with torch.cuda.device(dev):
+                _lib.check(lib.r3dg_bvh_bake_visibility(
+                    P, int(first_slot), int(count), N, self.tree.data_ptr(), self.aabb.data_ptr(), m.data_ptr(), ci.data_ptr(),
+                    op.data_ptr(), nr.data_ptr(), 0.05, None if contrib is None else contrib.data_ptr(),
+                    out["visibility"].data_ptr(), out["incident_dirs"].data_ptr() if "incident_dirs" in out else None,
+                    out["incident_areas"].data_ptr() if "incident_areas" in out else None,
+                    tmp.data_ptr(), tmp.numel(), torch.cuda.current_stream(dev).cuda_stream), "bake_visibility")
+        return out
+
 
 @torch.no_grad()
 def update_visibility(xyz, scaling, rotation, inverse_covariance, opacity, normal, sample_num, shard_group=None):
@@ -99,9 +129,11 @@ def update_visibility(xyz, scaling, rotation, inverse_covariance, opacity, norma
 
     `shard_group` (a torch.distributed process group, or True for the default group) shards the one-off
     bake over the ranks: the model is replicated, so every rank builds the same LBVH,
-    traces only its contiguous slice of ceil(P / world) Gaussians and ONE all-gather of the visibility
-    slices follows (directions / areas are deterministic and cheap: computed locally for all P).
-    The reference is single-GPU; without `shard_group` this is exactly its loop."""
+    traces only its contiguous range of ceil(P / world) leaf slots into a zero-initialised full-size
+    visibility tensor, and ONE sum all-reduce restores the complete tensor on every rank (each row is
+    written by exactly one rank); directions / areas are deterministic and cheap, so every rank
+    generates all of them locally (r3dg_sample_incident_dirs) instead of exchanging 16 B per ray.
+    The reference is single-GPU; without `shard_group` this is its loop as one launch."""
     import torch.distributed as tdist
     P = xyz.shape[0]
     world, rank, group = 1, 0, None
@@ -111,23 +143,10 @@ def update_visibility(xyz, scaling, rotation, inverse_covariance, opacity, norma
     raytracer = RayTracer(xyz, scaling, rotation)
     per_rank = -(-P // world)
     lo, hi = min(rank * per_rank, P), min((rank + 1) * per_rank, P)
-    vis, dirs, areas = [], [], []
-    chunk_size = max(1, P // ((sample_num - 1) // 24 + 1))
-    for offset in range(0, P, chunk_size):
-        end = min(offset + chunk_size, P)
-        d, a = sample_incident_rays(normal[offset:end], False, sample_num)
-        dirs.append(d); areas.append(a)
-        s0, s1 = max(offset, lo), min(end, hi)                  # this rank's part of the chunk
-        if s1 > s0:
-            dd = d[s0 - offset:s1 - offset]
-            res = raytracer.trace_visibility(xyz[s0:s1, None].expand_as(dd), dd, xyz, inverse_covariance, opacity, normal)
-            vis.append(res["visibility"])
-    dirs, areas = torch.cat(dirs, dim=0), torch.cat(areas, dim=0)
-    mine = torch.cat(vis, dim=0) if vis else xyz.new_zeros((0, sample_num, 1))
     if world == 1:
-        return mine, dirs, areas
-    padded = xyz.new_zeros((per_rank, sample_num, 1))
-    padded[:hi - lo] = mine
-    gathered = xyz.new_empty((world * per_rank, sample_num, 1))
-    tdist.all_gather_into_tensor(gathered, padded, group=group)
-    return gathered[:P].contiguous(), dirs, areas
+        out = raytracer.bake_visibility(xyz, inverse_covariance, opacity, normal, sample_num)
+        return out["visibility"], out["incident_dirs"], out["incident_areas"]
+    out = raytracer.bake_visibility(xyz, inverse_covariance, opacity, normal, sample_num, first_slot=lo, count=hi - lo, write_dirs=False)
+    tdist.all_reduce(out["visibility"], op=tdist.ReduceOp.SUM, group=group)
+    dirs, areas = sample_incident_rays(normal, False, sample_num)
+    return out["visibility"], dirs, areas

@@ -60,8 +60,9 @@ class _RenderEquation(torch.autograd.Function):
             means = [torch.empty((P, 3), **f) for _ in range(3)] + [torch.empty((P, 1), **f)]
             a.mean_incident_lights, a.mean_local_lights, a.mean_global_lights, a.mean_visibility = [m.data_ptr() for m in means]
         if P > 0:
-            _lib.check(lib.r3dg_render_equation_forward(ctypes.byref(a), torch.cuda.current_stream(dev).cuda_stream),
-                       "rendering_equation")
+            with torch.cuda.device(dev):
+                _lib.check(lib.r3dg_render_equation_forward(ctypes.byref(a), torch.cuda.current_stream(dev).cuda_stream),
+                           "rendering_equation")
         ctx.save_for_backward(*ts)
         ctx.transform = tr
         ctx.mark_non_differentiable(*(means or []))
@@ -87,8 +88,9 @@ class _RenderEquation(torch.autograd.Function):
         a.dL_dpbr, a.dL_ddiffuse_light, a.dL_dspecular = [t.data_ptr() for t in g]
         a.dL_dbase_color, a.dL_droughness, a.dL_dviewdirs = d_base.data_ptr(), d_rough.data_ptr(), d_view.data_ptr()
         a.dL_dincidents, a.dL_denv = d_inc.data_ptr(), d_env.data_ptr()
-        _lib.check(lib.r3dg_render_equation_backward(ctypes.byref(a), torch.cuda.current_stream(dev).cuda_stream),
-                   "rendering_equation backward")
+        with torch.cuda.device(dev):
+            _lib.check(lib.r3dg_render_equation_backward(ctypes.byref(a), torch.cuda.current_stream(dev).cuda_stream),
+                       "rendering_equation backward")
         return d_base, d_rough, d_view, d_inc, d_env, None, None, None, None, None, None
 
 
@@ -151,8 +153,9 @@ def rendering_equation(base_color, roughness, normals, viewdirs, incidents, dire
         a.pbr, a.diffuse_light, a.specular = [t.data_ptr() for t in scratch]
         a.incident_lights, a.local_incident_lights, a.global_incident_lights = [t.data_ptr() for t in outs]
         if P > 0:
-            _lib.check(lib.r3dg_render_equation_forward(ctypes.byref(a), torch.cuda.current_stream(dirs.device).cuda_stream),
-                       "rendering_equation (per-sample lights)")
+            with torch.cuda.device(dirs.device):
+                _lib.check(lib.r3dg_render_equation_forward(ctypes.byref(a), torch.cuda.current_stream(dirs.device).cuda_stream),
+                           "rendering_equation (per-sample lights)")
         return dict(zip(_LazyExtras._LAZY, outs))
 
     extra = _LazyExtras({"incident_dirs": dirs, "incident_visibility": vis, "diffuse_light": diffuse, "specular": specular},

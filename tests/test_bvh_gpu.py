@@ -119,3 +119,49 @@ def test_update_visibility_shapes_and_edge_cases():
     cont, opa = _C_bvh.trace_bvh_opacity(rt.tree, rt.aabb, o.contiguous(), dd, d["means3D"], d["inv_cov"], d["opacity"], d["normals"])
     oc, ov = oracle.bvh_trace_opacity(nodes, aabbs, npy(o), npy(dd), npy(c["means3D"]), npy(c["inv_cov"]), npy(c["opacity"]), npy(c["normals"]))
     assert ((npy(opa) == 0) != (ov == 0)).mean() <= 0.05
+
+
+def test_sampling_kernel_matches_reference_golden():
+    """r3dg_sample_incident_dirs vs tests/golden/sampling.npz (outputs of the reference's own functions)."""
+    from relightable3dgaussian_b200 import raytracer
+    g = np.load(os.path.join(GOLDEN, "sampling.npz"))
+    n = torch.from_numpy(g["normals"]).cuda()
+    for N in (24, 32, 100):
+        d, a = raytracer.sample_incident_rays(n, False, N)
+        assert d.shape == (257, N, 3) and np.array_equal(npy(a), g[f"areas_{N}"])
+        assert np.abs(npy(d) - g[f"dirs_{N}"]).max() <= 5e-7, N          # CPU libm vs CUDA sinf/cosf: <= a few ulp of a unit vector
+        assert np.abs(np.linalg.norm(npy(d), axis=-1) - 1).max() < 1e-6
+    # batched normals keep their leading shape (graphics_utils.py:11-13,32-35)
+    d, a = raytracer.sample_incident_rays(n[:256].reshape(16, 16, 3), False, 24)
+    assert d.shape == (16, 16, 24, 3) and a.shape == (16, 16, 24, 1)
+    assert np.abs(npy(d).reshape(256, 24, 3) - g["dirs_24"][:256]).max() <= 5e-7
+
+
+def test_bake_kernel_equals_sampler_plus_trace_and_cpu_oracle():
+    """r3dg_bvh_bake_visibility (directions generated in the trace kernel, Morton-ordered rays) must equal the two-step
+    path it fuses (r3dg_sample_incident_dirs -> trace_visibility) ray for ray, and the CPU oracle's trace on the same
+    tree up to the T < 0.9 cliff; partial slot ranges touch only their own Gaussians' rows."""
+    from oracle import oracle
+    from relightable3dgaussian_b200 import raytracer
+    c = bvh_case("cube-v1", 6000, 8, 8, 2.0, seed=3)
+    d = {k: v.cuda() for k, v in c.items()}
+    N = 40
+    rt = build_ours(c["means3D"], c["scales"], c["rotations"])
+    full = rt.bake_visibility(d["means3D"], d["inv_cov"], d["opacity"], d["normals"], N, want_contribute=True)
+    dirs, areas = raytracer.sample_incident_rays(d["normals"], False, N)
+    assert torch.equal(full["incident_dirs"], dirs) and torch.equal(full["incident_areas"], areas)
+    two = rt.trace_visibility(d["means3D"][:, None].expand_as(dirs), dirs, d["means3D"], d["inv_cov"], d["opacity"], d["normals"])
+    assert torch.equal(full["visibility"], two["visibility"]) and torch.equal(full["contribute"], two["contribute"])
+    nodes, aabbs, _ = oracle.bvh_build(npy(c["means3D"]), npy(c["scales"]), npy(c["rotations"]))
+    ro = npy(d["means3D"][:, None] + dirs * 0.05).reshape(-1, 3)
+    oc, ov = oracle.bvh_trace_opacity(nodes, aabbs, ro, npy(dirs).reshape(-1, 3), npy(c["means3D"]), npy(c["inv_cov"]),
+                                      npy(c["opacity"]), npy(c["normals"]))
+    flips, err, _ = compare_vis(npy(full["visibility"]).reshape(-1), npy(full["contribute"]).reshape(-1), ov, oc)
+    assert flips <= 2e-3 and err <= 1e-4, (flips, err)
+    # slots [1000, 3500): exactly those Gaussians' rows, nothing else
+    part = rt.bake_visibility(d["means3D"], d["inv_cov"], d["opacity"], d["normals"], N, first_slot=1000, count=2500)
+    P = 6000
+    objs = rt.tree[P - 1 + 1000:P - 1 + 3500, 3].long()
+    mask = torch.zeros(P, dtype=torch.bool, device="cuda"); mask[objs] = True
+    assert torch.equal(part["visibility"][mask], full["visibility"][mask]) and not part["visibility"][~mask].any()
+    assert not part["incident_dirs"][~mask].any() and torch.equal(part["incident_dirs"][mask], dirs[mask])

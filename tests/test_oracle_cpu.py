@@ -254,3 +254,25 @@ def test_adam_oracle_matches_committed_torch_fixture():
         np.testing.assert_allclose(s[0], g[f"p{i}"], rtol=1e-6, atol=1e-7)
         np.testing.assert_allclose(s[1], g[f"m{i}"], rtol=2e-6, atol=1e-6 * float(np.abs(g[f"m{i}"]).max()))
         np.testing.assert_allclose(s[2], g[f"v{i}"], rtol=2e-6, atol=1e-18)
+
+
+def test_sampling_oracle_pinned_to_reference_functions():
+    """oracle/oracle_sampling.py == the reference's own rotation_between_z / fibonacci_sphere_sampling
+    (tests/golden/sampling.npz, generated by executing the reference modules: make_golden_sampling.py)."""
+    from oracle import oracle_sampling as osamp
+    g = np.load(os.path.join(GOLDEN, "sampling.npz"))
+    n = torch.from_numpy(g["normals"])
+    assert np.array_equal(osamp.rotation_between_z(n).numpy(), g["R"])
+    for N in (24, 32, 100):
+        d, a = osamp.fibonacci_sphere_sampling(n, N, random_rotate=False)
+        assert np.array_equal(d.numpy(), g[f"dirs_{N}"]) and np.array_equal(a.numpy(), g[f"areas_{N}"])
+    d, _ = osamp.fibonacci_sphere_sampling(n, 32, random_rotate=True, phase=torch.from_numpy(g["phase"]))
+    assert np.array_equal(d.numpy(), g["dirs_32_random"])
+    # inverse covariance: Sigma^-1 Sigma == I for the restated helper
+    s = torch.rand(50, 3) * 0.5 + 0.1
+    q = torch.nn.functional.normalize(torch.randn(50, 4), dim=-1)
+    ic = osamp.inverse_covariance(s, q)
+    R = osamp.build_rotation(q)
+    cov = R @ torch.diag_embed(s * s) @ R.transpose(1, 2)
+    full = torch.stack([ic[:, 0], ic[:, 1], ic[:, 2], ic[:, 1], ic[:, 3], ic[:, 4], ic[:, 2], ic[:, 4], ic[:, 5]], -1).view(-1, 3, 3)
+    assert torch.allclose(full @ cov, torch.eye(3).expand(50, 3, 3), atol=1e-4)

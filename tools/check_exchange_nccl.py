@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""Multi-GPU check of the factorised gradient exchange on real NCCL (not part of the test suite:
-needs >= 2 GPUs).  Every rank renders its view of one step, then the SAME per-view gradients go
+"""Multi-GPU check of the factorised gradient exchange on real NCCL (tests/test_multigpu_gpu.py launches it
+when the box has >= 2 GPUs).  Every rank renders its view of one step, then the SAME per-view gradients go
 through both exchanges — dense all-reduce (dist.GradBucket) and factorised (dist.FactoredGradExchange)
 — and the results are compared on every rank; both are timed with CUDA events (max over ranks).
 
@@ -82,10 +82,34 @@ def main():
     t = dict(dense_exchange_ms=timed(dense.allreduce_mean), factored_exchange_ms=timed(lambda: fact.exchange(means3D, campos_all, 3)),
              dense_step_ms=timed(lambda: (fwd_bwd(dense.views), dense.allreduce_mean())),
              factored_step_ms=timed(lambda: (fwd_bwd(fact.views), fact.exchange(means3D, campos_all, 3))))
+    # ---- hardware correctness gate: the N-view step's gradients == the mean of N single-view backward
+    # passes of the REFERENCE's own kernels (oracle/_ref), run sequentially on this rank ---------------------------------
+    ref_rel = None
+    from oracle import ref_gpu
+    if ref_gpu.available():
+        ref = ref_gpu.RefRasterizer()
+        acc = None
+        for c in cams:
+            kw = dict(means3D=means3D, shs=shs, scales=scales, rotations=rots, features=feats)
+            cam_kw = dict(viewmatrix=d(c.viewmatrix), projmatrix=d(c.projmatrix), campos=d(c.campos))
+            o = ref.forward(bg=bg, W=W, H=H, tan_fovx=c.tanfovx, tan_fovy=c.tanfovy, cx=c.cx, cy=c.cy, opacities=opac, **cam_kw, **kw)
+            gr = ref.backward(o, bg=bg, tan_fovx=c.tanfovx, tan_fovy=c.tanfovy, dL_dcolor=cot[0], dL_dopacity=cot[1], dL_ddepth=cot[2],
+                              dL_dfeature=cot[3], **cam_kw, **kw)
+            acc = {k: v.double() / world for k, v in gr.items()} if acc is None else {k: acc[k] + v.double() / world for k, v in gr.items()}
+        names = dict(means3D="dL_dmeans3D", features="dL_dfeatures", opacity="dL_dopacity", scales="dL_dscales", rotations="dL_drotations", sh="dL_dsh")
+        ref_rel = {k: float((fact.grads[k].double() - acc[n]).norm() / (acc[n].norm() + 1e-30)) for k, n in names.items()}
+        worst = torch.tensor([max(ref_rel.values())], device=dev)
+        tdist.all_reduce(worst, op=tdist.ReduceOp.MAX)
+        ref_rel["max_over_ranks"] = float(worst.item())
     if rank == 0:
         ok = all(v < 1e-4 for v in rel.values()) and int(lo) == int(hi)      # atomics: run-to-run summation order in the two backwards
+        if ref_rel is not None:
+            ok = ok and ref_rel["max_over_ranks"] < 1e-3
         print(json.dumps(dict(what="exchange check", world=world, P=P, rel_l2_factored_vs_dense=rel, identical_on_all_ranks=int(lo) == int(hi),
-                              dense_bytes=dense.bytes(), factored_bytes_per_rank=fact.bytes(), ok=ok, **t)), flush=True)
+                              dense_bytes=dense.bytes(), factored_bytes_per_rank=fact.bytes(),
+                              rel_l2_vs_mean_of_reference_single_view_backwards=ref_rel, ok=ok, **t)), flush=True)
+        if not ok:
+            sys.exit(1)
     tdist.barrier()
     tdist.destroy_process_group()
 
