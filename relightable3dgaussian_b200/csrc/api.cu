@@ -44,7 +44,7 @@ const char* r3dg_version(void) { return "r3dg_b200 0.1 sm_100a"; }
 
 size_t r3dg_raster_geom_bytes(int P, int S) { return GeomLayout(P < 1 ? 1 : P, S).total; }
 size_t r3dg_raster_img_bytes(int W, int H) { return ImgLayout(W, H).total; }
-size_t r3dg_raster_binning_bytes(long long capacity) { return BinLayout(capacity < 1 ? 1 : capacity).total; }
+size_t r3dg_raster_binning_bytes(long long capacity) { return bin_bytes_for_capacity(capacity < 1 ? 1 : capacity); }
 size_t r3dg_raster_img_n_contrib_offset(int W, int H) { return ImgLayout(W, H).n_contrib; }
 
 int r3dg_raster_forward(const r3dg_raster_fwd_args* a, r3dg_stream_t stream_) {
@@ -78,10 +78,11 @@ int r3dg_raster_forward(const r3dg_raster_fwd_args* a, r3dg_stream_t stream_) {
         for (int i = 1; i <= 4; ++i) prof_mark(true, i, stream);
     }
     if ((rc = launch_tile_order(img + il.ranges, (uint32_t*)(img + il.tile_order), tiles, stream)) != 0) return rc;
+    if (a->P > 0 && (rc = launch_block_masks(a->W, a->H, gl, il, geom, img, bin, bl, stream)) != 0) return rc;
     prof_mark(true, 5, stream);
-    if ((rc = launch_composite_forward(*a, gl, il, (const uint32_t*)(bin + bl.point_list), stream, mark)) != 0) return rc;
+    if ((rc = launch_composite_forward(*a, gl, il, bin, bl, stream, mark)) != 0) return rc;
     prof_mark(true, 7, stream);
-    g_launches += 2 + (a->computer_pseudo_normal ? 1 : 0);
+    g_launches += 2 + (a->P > 0 ? 1 : 0) + (a->computer_pseudo_normal ? 1 : 0);   // tile order, block masks, composite, normals
     if (g_prof.on) g_prof.fwd_calls++;
     if (a->num_rendered_host)
         R3DG_CUDA_TRY(cudaMemcpyAsync(a->num_rendered_host, geom + gl.header, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -106,7 +107,7 @@ int r3dg_raster_backward(const r3dg_raster_bwd_args* a, r3dg_stream_t stream_) {
     char* bin = (char*)a->binning;
     int rc = 0;
     prof_mark(false, 8, stream);
-    if ((rc = launch_composite_backward(*a, gl, il, (const uint32_t*)(bin + bl.point_list), stream)) != 0) return rc;
+    if ((rc = launch_composite_backward(*a, gl, il, bin, bl, stream)) != 0) return rc;
     prof_mark(false, 9, stream);
     if ((rc = launch_projection_backward(*a, gl, stream)) != 0) return rc;
     prof_mark(false, 10, stream);

@@ -145,16 +145,27 @@ struct ImgLayout {
     }
 };
 
-// Binning buffer: the per-tile depth-sorted Gaussian lists (reference binningState.point_list).
+// Binning buffer (capacity-sized, speculative): the per-tile depth-sorted Gaussian lists (reference
+// binningState.point_list) plus one byte per instance for each of
+//   bmask: bit b = 8x4 pixel block b of the instance's tile may be touched by the Gaussian (block_mask_kernel,
+//          the exact-conservative ellipse/rectangle test evaluated ONCE per instance instead of by 8 warps);
+//   cmask: bit b = block b actually composited the instance in the forward pass (some pixel accepted it).  The
+//          backward compositor visits exactly the cmask entries of its block, nothing else.
+// 6 B per instance instead of the reference's 24 B + sort temp.
 struct BinLayout {
-    size_t point_list, total;
+    size_t point_list, bmask, cmask, total;
     long long capacity;
     __host__ __device__ BinLayout(long long cap) : capacity(cap) {
-        point_list = 0;
-        total = align_up((size_t)cap * 4, 256);
+        size_t off = 0;
+        point_list = off; off = align_up(off + (size_t)cap * 4, 256);
+        bmask = off;      off = align_up(off + (size_t)cap, 256);
+        cmask = off;      off = align_up(off + (size_t)cap, 256);
+        total = off;
     }
 };
-inline __host__ long long bin_capacity_for_bytes(size_t bytes) { return (long long)(bytes / 256 * 256 / 4); }
+// largest capacity (a multiple of 64 instances) whose layout fits in `bytes`; r3dg_raster_binning_bytes is its inverse
+inline __host__ long long bin_capacity_for_bytes(size_t bytes) { return bytes < 768 + 384 ? 0 : (long long)((bytes - 768) / 6 / 64 * 64); }
+inline __host__ size_t bin_bytes_for_capacity(long long cap) { return (size_t)((cap + 63) / 64 * 64) * 6 + 768; }
 
 // getHigherMsb (reference rasterizer_impl.cu:35-50): bits needed for tile ids.
 inline __host__ uint32_t higher_msb(uint32_t n) {
@@ -261,6 +272,55 @@ __device__ __forceinline__ bool touch_block(const float4 A, const float4 B, floa
     // slack also absorbs the approximate log/divide above (relative error ~1e-6 of tau <= ~12)
     const float slack = 1.0f + 1e-5f * (ca * um * um + cc * vm * vm + 2.0f * fabsf(cb) * um * vm);
     return !(qmin > tau + slack);
+}
+
+// The same test for all 8 blocks of a tile at once (block b: x offset 8 * (b & 1), y offset 4 * (b >> 1)), with
+// the per-Gaussian part (validity, tau, the two edge slopes) evaluated once.  Bit b of the result == touch_block()
+// of block b: identical arithmetic per block, so the compositors stay exactly as conservative as before.
+__device__ __forceinline__ uint32_t touch_mask8(const float4 A, const float4 B, float TX0, float TY0) {
+    const float gx = A.x, gy = A.y, ca = A.z, cb = A.w, cc = B.x, op = B.y;
+    if (op < 1.0f / 255.0f) return 0u;
+    if (!(ca > 0.0f && cc > 0.0f && ca * cc - cb * cb > 0.0f)) return 0xffu;
+    const float tau = 2.0f * __logf(255.0f * op);
+    if (!(tau >= 0.0f)) return 0xffu;
+    const float rc = __fdividef(-cb, cc), ra = __fdividef(-cb, ca);
+    uint32_t m = 0u;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const float X0 = TX0 + 8.0f * (float)(b & 1), Y0 = TY0 + 4.0f * (float)(b >> 1);
+        const float u0 = gx - (X0 + 7.0f), u1 = gx - X0, v0 = gy - (Y0 + 3.0f), v1 = gy - Y0;
+        bool touch = (u0 <= 0.0f && u1 >= 0.0f && v0 <= 0.0f && v1 >= 0.0f);
+        if (!touch) {
+            auto edge_u = [&](float U) {
+                const float v = fminf(fmaxf(rc * U, v0), v1);
+                return ca * U * U + 2.0f * cb * U * v + cc * v * v;
+            };
+            auto edge_v = [&](float V) {
+                const float u = fminf(fmaxf(ra * V, u0), u1);
+                return ca * u * u + 2.0f * cb * u * V + cc * V * V;
+            };
+            const float qmin = fminf(fminf(edge_u(u0), edge_u(u1)), fminf(edge_v(v0), edge_v(v1)));
+            const float um = fmaxf(fabsf(u0), fabsf(u1)), vm = fmaxf(fabsf(v0), fabsf(v1));
+            const float slack = 1.0f + 1e-5f * (ca * um * um + cc * vm * vm + 2.0f * fabsf(cb) * um * vm);
+            touch = !(qmin > tau + slack);
+        }
+        m |= (touch ? 1u : 0u) << b;
+    }
+    return m;
+}
+
+// ---- warp-level stream compaction over per-instance mask bytes (compositors) ---------------------
+// A warp walks its tile's mask bytes 128 entries at a time (one 4-byte word per lane), keeps the entries whose bit
+// `bit` is set and appends their list positions, in list order, to a small circular queue in shared memory.  The
+// lane-level ranks come from one warp scan of the per-lane popcounts.
+#define R3DG_QCAP 256                      // queue slots per warp (>= 31 + 128 pending entries), power of two
+
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_t& total) {
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    total = __shfl_sync(0xffffffffu, inc, 31);
+    return inc - v;
 }
 
 }  // namespace r3dg

@@ -27,6 +27,8 @@ struct CompositeFwdParams {
     int W, H, gx, S, recf;
     const uint2* ranges;
     const uint32_t* point_list;  // per-tile depth-sorted Gaussian ids (binning.cu)
+    const uint32_t* bmask32;     // per-instance block-touch masks (block_mask_kernel), viewed as words of 4 instances
+    uint32_t* cmask32;           // per-instance contributor masks (zeroed by block_mask_kernel, set here)
     const GeomHeader* header;
     const uint32_t* tile_order;  // CTA -> tile, heaviest tiles first
     const float* rec;
@@ -36,15 +38,39 @@ struct CompositeFwdParams {
     float *out_color, *out_opacity, *out_depth, *out_feature, *out_weights;
 };
 
-// NW = warps per CTA: 8 (one CTA per tile) or 4 (two CTAs per tile).  Warps are autonomous: no
+// One thread per (tile, Gaussian) instance: the 8-bit block-touch mask of the instance and a zeroed contributor byte.
+// CTA per tile (heaviest first); reads 4 B + 32 B (gathered record head), writes 2 B per instance.
+__global__ void __launch_bounds__(256) block_mask_kernel(int gx, int recf, const uint2* __restrict__ ranges,
+                                                         const uint32_t* __restrict__ tile_order,
+                                                         const uint32_t* __restrict__ point_list,
+                                                         const float* __restrict__ rec, uint8_t* __restrict__ bmask,
+                                                         uint8_t* __restrict__ cmask) {
+    const int tile = (int)tile_order[blockIdx.x];
+    const uint2 range = ranges[tile];
+    const float TX0 = (float)((tile % gx) * R3DG_TILE), TY0 = (float)((tile / gx) * R3DG_TILE);
+    const float4* __restrict__ rec4 = reinterpret_cast<const float4*>(rec);
+    const int rec4n = recf >> 2;
+    for (uint32_t i = range.x + threadIdx.x; i < range.y; i += 256) {
+        const uint32_t id = point_list[i];
+        const float4 A = rec4[(size_t)id * rec4n], B = rec4[(size_t)id * rec4n + 1];
+        bmask[i] = (uint8_t)touch_mask8(A, B, TX0, TY0);
+        cmask[i] = 0;
+    }
+}
+
+// NW = warps per CTA (4: two CTAs per tile).  Warps are autonomous: no
 // CTA-wide barrier anywhere; the CTA only exists so that the warps of a tile share L1 lines.
-template <int NG, int NW>
-// occupancy pin for the headline shape (S <= 5 channels): keeps the register allocation at the
-// count that fits one more CTA per SM (ptxas otherwise drifts a few registers above it)
-__global__ void __launch_bounds__(32 * NW, (NG == 2 && NW == 4) ? 9 : 1) composite_fwd_kernel(const CompositeFwdParams p) {
+//
+// Per warp (one 8x4 pixel block): the tile's block-touch mask bytes are streamed 128 instances at a time and the
+// positions whose bit for THIS block is set are compacted into a circular queue (warp scan); batches of 32 queued
+// entries are then fetched (id -> packed record, registers, one batch ahead), staged in the warp's shared-memory slab
+// and composited — every staged entry is one the block may touch, there is no per-entry culling left in the loop.
+template <int NG, int NW, int MINB>
+__global__ void __launch_bounds__(32 * NW, MINB) composite_fwd_kernel(const CompositeFwdParams p) {
     constexpr int RG = 2 + NG;                       // float4 groups per record
-    __shared__ float4 sRec[NW][RG][32];              // this warp's current 32-entry chunk, SoA
-    __shared__ int sId[NW][32];
+    __shared__ float4 sRec[NW][RG][32];              // this warp's current 32-entry batch, SoA
+    __shared__ uint32_t sId[NW][32];
+    __shared__ uint32_t sQ[NW][R3DG_QCAP];           // queued list positions (relative to the tile's range)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int PARTS = 8 / NW;
     const int tile = (int)p.tile_order[blockIdx.x / PARTS];
@@ -55,10 +81,11 @@ __global__ void __launch_bounds__(32 * NW, (NG == 2 && NW == 4) ? 9 : 1) composi
     const bool inside = px < p.W && py < p.H;
     const float pxf = (float)px, pyf = (float)py;
     const uint2 range = p.ranges[tile];
-    const int toDo = (int)(range.y - range.x);
+    const uint32_t lo = range.x, hi = range.y;
     const float4* __restrict__ rec4 = reinterpret_cast<const float4*>(p.rec);
     const int rec4n = p.recf >> 2;
-    const uint32_t* __restrict__ plist = p.point_list + range.x;
+    const uint32_t* __restrict__ plist = p.point_list + lo;
+    uint32_t* q = sQ[warp];
 
     float T = 1.0f, Dp = 0.0f, Op = 0.0f;
     float C[4 * NG];
@@ -67,42 +94,72 @@ __global__ void __launch_bounds__(32 * NW, (NG == 2 && NW == 4) ? 9 : 1) composi
     uint32_t last_contributor = 0;
     bool done = !inside;
 
-    // software pipeline: ids two chunks ahead, records one chunk ahead (registers)
-    uint32_t id_cur = lane < toDo ? plist[lane] : 0u;
+    // ---- mask stream: word w holds instances [4w, 4w+4); lane takes word w_next + lane --------------------
+    const uint32_t w_end = (hi + 3) >> 2;
+    uint32_t w_next = lo >> 2;
+    uint32_t m_nxt = (w_next + lane < w_end) ? p.bmask32[w_next + lane] : 0u;       // prefetched one step ahead
+    int qhead = 0, qcount = 0;
+    auto scan_step = [&]() {
+        const uint32_t w = w_next + lane;
+        uint32_t flags = 0u;
+        if (w < w_end) {
+            flags = (m_nxt >> wb) & 0x01010101u;
+            const uint32_t e0 = w << 2;
+            if (e0 < lo) flags &= 0xffffffffu << (8 * (lo - e0));                   // instances of the previous tile
+            if (e0 + 4 > hi) flags &= 0xffffffffu >> (8 * (e0 + 4 - hi));           // instances of the next tile
+        }
+        w_next += 32;
+        m_nxt = (w_next + lane < w_end) ? p.bmask32[w_next + lane] : 0u;
+        uint32_t total;
+        uint32_t slot = (uint32_t)(qhead + qcount) + warp_excl_scan(__popc(flags), lane, total);
+        const uint32_t rel = (w << 2) - lo;                                          // may wrap for the first word: only flagged bytes are used
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (flags & (1u << (8 * k))) { q[slot & (R3DG_QCAP - 1)] = rel + k; ++slot; }
+        qcount += (int)total;
+    };
+    while (qcount < 64 && w_next < w_end) scan_step();
+    __syncwarp();
+
+    // software pipeline: records of the next batch live in registers while the current one is composited
+    uint32_t id_cur = 0u;
     float4 r[RG];
 #pragma unroll
     for (int g = 0; g < RG; ++g) r[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane < toDo) {
+    if (lane < qcount) {
+        id_cur = plist[q[(qhead + lane) & (R3DG_QCAP - 1)]];
 #pragma unroll
         for (int g = 0; g < RG; ++g) r[g] = rec4[(size_t)id_cur * rec4n + g];
     }
-    uint32_t id_nxt = 32 + lane < toDo ? plist[32 + lane] : 0u;
 
     bool all_done = __all_sync(0xffffffffu, done);
-    for (int base = 0; base < toDo && !all_done; base += 32) {
-        const int n = min(32, toDo - base);
+    while (qcount > 0 && !all_done) {
+        const int n = min(32, qcount);
+        const uint32_t mypos = q[(qhead + lane) & (R3DG_QCAP - 1)];     // valid for lane < n
         __syncwarp();
-        sId[warp][lane] = (int)id_cur;
+        sId[warp][lane] = id_cur;
 #pragma unroll
         for (int g = 0; g < RG; ++g) sRec[warp][g][lane] = r[g];
-        uint32_t word = __ballot_sync(0xffffffffu, lane < n && touch_block(r[0], r[1], (float)bx0, (float)by0));
-        // prefetch: records of the next chunk, ids of the one after
-        id_cur = id_nxt;
-        if (base + 32 + lane < toDo) {
+        const int h0 = qhead;
+        qhead = (qhead + n) & (R3DG_QCAP - 1);
+        qcount -= n;
+        while (qcount < 64 && w_next < w_end) scan_step();
+        __syncwarp();
+        // prefetch: id -> record of the next batch
+        if (lane < qcount) {
+            id_cur = plist[q[(qhead + lane) & (R3DG_QCAP - 1)]];
 #pragma unroll
             for (int g = 0; g < RG; ++g) r[g] = rec4[(size_t)id_cur * rec4n + g];
         }
-        id_nxt = base + 64 + lane < toDo ? plist[base + 64 + lane] : 0u;
-        __syncwarp();
-        while (word) {
-            const int j = __ffs(word) - 1;
-            word &= word - 1;
+        uint32_t cw = 0u;                                               // bit j: entry j was composited by some pixel
+#pragma unroll 1
+        for (int j = 0; j < n; ++j) {
             const float4 a = sRec[warp][0][j];
             const float4 b = sRec[warp][1][j];
             const float dx = sub_(a.x, pxf), dy = sub_(a.y, pyf);
             // power = -0.5f*(ca*dx*dx + cc*dy*dy) - cb*dx*dy  (forward.cu:344) as compiled
-            const float q = fma_(dx, mul_(dx, a.z), mul_(dy, mul_(dy, b.x)));
-            const float power = fma_(q, -0.5f, -mul_(dy, mul_(dx, a.w)));
+            const float qd = fma_(dx, mul_(dx, a.z), mul_(dy, mul_(dy, b.x)));
+            const float power = fma_(qd, -0.5f, -mul_(dy, mul_(dx, a.w)));
             const float alpha = fminf(0.99f, mul_(b.y, expf(power)));
             const float test_T = mul_(T, sub_(1.0f, alpha));
             bool valid = !done && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
@@ -121,14 +178,22 @@ __global__ void __launch_bounds__(32 * NW, (NG == 2 && NW == 4) ? 9 : 1) composi
                 Dp = fma_(w, b.z, Dp);
                 Op = add_(Op, w);
                 T = test_T;
-                last_contributor = (uint32_t)(base + j + 1);      // 1-based position in the tile list
+                last_contributor = q[(h0 + j) & (R3DG_QCAP - 1)] + 1u;      // 1-based position in the tile list
             }
-            // out_weights[id] += sum over the warp's pixels of w: one integer REDUX instead of a
-            // 5-step float shuffle tree (w in [0,1) in 2^-24 fixed point: error <= 1e-6 per warp, far
-            // below the reference's own atomic-order noise on this statistic), one atomic per warp.
-            const int wsum = __reduce_add_sync(0xffffffffu, valid ? __float2int_rn(w * 16777216.0f) : 0);
-            if (lane == 0 && wsum != 0) atomicAdd(&p.out_weights[sId[warp][j]], (float)wsum * (1.0f / 16777216.0f));
+            if (__any_sync(0xffffffffu, valid)) {
+                cw |= 1u << j;
+                // out_weights[id] += sum over the warp's pixels of w: one integer REDUX instead of a 5-step float
+                // shuffle tree (w in [0,1) in 2^-24 fixed point: error <= 1e-6 per warp, far below the reference's own
+                // atomic-order noise on this statistic), one atomic per warp.
+                const int wsum = __reduce_add_sync(0xffffffffu, valid ? __float2int_rn(w * 16777216.0f) : 0);
+                if (lane == 0 && wsum != 0) atomicAdd(&p.out_weights[sId[warp][j]], (float)wsum * (1.0f / 16777216.0f));
+            }
             if (__all_sync(0xffffffffu, done)) { all_done = true; break; }
+        }
+        // contributor bits for the backward pass: one fire-and-forget atomic per composited entry
+        if ((cw >> lane) & 1u) {
+            const uint32_t e = lo + mypos;
+            atomicOr(&p.cmask32[e >> 2], 1u << (8 * (e & 3u) + wb));
         }
     }
     if (inside) {
@@ -195,26 +260,36 @@ __global__ void __launch_bounds__(256) surface_normal_kernel(int W, int H, const
     out_normal[pix] = o0; out_normal[HW + pix] = o1; out_normal[2 * HW + pix] = o2;
 }
 
+// resident CTAs per SM the register allocation is pinned to (ptxas otherwise drifts a few registers above the
+// count that fits one more CTA): by channel groups NG, for the 4-warp CTA (the 8-warp variant is left to ptxas)
+template <int NG> struct FwdOcc { static constexpr int v = NG <= 2 ? 9 : (NG <= 3 ? 8 : (NG <= 5 ? 6 : 4)); };
+
 template <int NG>
-static void launch_fwd_ng(const CompositeFwdParams& p, int tiles, int nw, cudaStream_t stream) {
-    if (nw == 4) composite_fwd_kernel<NG, 4><<<tiles * 2, 128, 0, stream>>>(p);
-    else composite_fwd_kernel<NG, 8><<<tiles, 256, 0, stream>>>(p);
+static void launch_fwd_ng(const CompositeFwdParams& p, int tiles, cudaStream_t stream) {
+    composite_fwd_kernel<NG, 4, FwdOcc<NG>::v><<<tiles * 2, 128, 0, stream>>>(p);      // two 4-warp CTAs per tile
 }
-int composite_nw() {
-    static int nw = 0;
-    if (nw == 0) { const char* e = getenv("R3DG_COMPOSITE_NW"); nw = (e && atoi(e) == 8) ? 8 : 4; }
-    return nw;
+
+int launch_block_masks(int W, int H, const GeomLayout& gl, const ImgLayout& il, char* geom, char* img, char* bin,
+                       const BinLayout& bl, cudaStream_t stream) {
+    const int gx = (W + R3DG_TILE - 1) / R3DG_TILE, gy = (H + R3DG_TILE - 1) / R3DG_TILE;
+    block_mask_kernel<<<gx * gy, 256, 0, stream>>>(gx, gl.recf, (const uint2*)(img + il.ranges), (const uint32_t*)(img + il.tile_order),
+                                                   (const uint32_t*)(bin + bl.point_list), (const float*)(geom + gl.rec),
+                                                   (uint8_t*)(bin + bl.bmask), (uint8_t*)(bin + bl.cmask));
+    R3DG_CUDA_TRY(cudaGetLastError());
+    return 0;
 }
 
 int launch_composite_forward(const r3dg_raster_fwd_args& a, const GeomLayout& gl, const ImgLayout& il,
-                             const uint32_t* point_list, cudaStream_t stream, stage_mark_fn mark) {
+                             char* bin, const BinLayout& bl, cudaStream_t stream, stage_mark_fn mark) {
     char* geom = (char*)a.geom;
     char* img = (char*)a.img;
     CompositeFwdParams p;
     p.W = a.W; p.H = a.H; p.gx = (a.W + R3DG_TILE - 1) / R3DG_TILE; p.S = a.S; p.recf = gl.recf;
     const int gy = (a.H + R3DG_TILE - 1) / R3DG_TILE;
     p.ranges = (const uint2*)(img + il.ranges);
-    p.point_list = point_list; p.header = (const GeomHeader*)(geom + gl.header);
+    p.point_list = (const uint32_t*)(bin + bl.point_list);
+    p.bmask32 = (const uint32_t*)(bin + bl.bmask); p.cmask32 = (uint32_t*)(bin + bl.cmask);
+    p.header = (const GeomHeader*)(geom + gl.header);
     p.tile_order = (const uint32_t*)(img + il.tile_order);
     p.rec = (const float*)(geom + gl.rec);
     p.bg = a.background;
@@ -224,15 +299,15 @@ int launch_composite_forward(const r3dg_raster_fwd_args& a, const GeomLayout& gl
     p.out_feature = a.out_feature; p.out_weights = a.out_weights;
     const int tiles = p.gx * gy;
     switch (num_groups(a.S)) {
-        case 1: launch_fwd_ng<1>(p, tiles, composite_nw(), stream); break;
-        case 2: launch_fwd_ng<2>(p, tiles, composite_nw(), stream); break;
-        case 3: launch_fwd_ng<3>(p, tiles, composite_nw(), stream); break;
-        case 4: launch_fwd_ng<4>(p, tiles, composite_nw(), stream); break;
-        case 5: launch_fwd_ng<5>(p, tiles, composite_nw(), stream); break;
-        case 6: launch_fwd_ng<6>(p, tiles, composite_nw(), stream); break;
-        case 7: launch_fwd_ng<7>(p, tiles, composite_nw(), stream); break;
-        case 8: launch_fwd_ng<8>(p, tiles, composite_nw(), stream); break;
-        case 9: launch_fwd_ng<9>(p, tiles, composite_nw(), stream); break;
+        case 1: launch_fwd_ng<1>(p, tiles, stream); break;
+        case 2: launch_fwd_ng<2>(p, tiles, stream); break;
+        case 3: launch_fwd_ng<3>(p, tiles, stream); break;
+        case 4: launch_fwd_ng<4>(p, tiles, stream); break;
+        case 5: launch_fwd_ng<5>(p, tiles, stream); break;
+        case 6: launch_fwd_ng<6>(p, tiles, stream); break;
+        case 7: launch_fwd_ng<7>(p, tiles, stream); break;
+        case 8: launch_fwd_ng<8>(p, tiles, stream); break;
+        case 9: launch_fwd_ng<9>(p, tiles, stream); break;
         default: return R3DG_ERR_UNSUPPORTED;
     }
     const size_t HW = (size_t)a.H * a.W;

@@ -23,6 +23,7 @@ struct CompositeBwdParams {
     int W, H, gx, S, recf, backward_geometry;
     const uint2* ranges;
     const uint32_t* point_list;  // per-tile depth-sorted Gaussian ids (binning.cu)
+    const uint32_t* cmask32;     // per-instance contributor masks written by the forward compositor
     const GeomHeader* header;
     const uint32_t* tile_order;  // CTA -> tile, heaviest tiles first
     const float* rec;
@@ -55,18 +56,20 @@ __device__ __forceinline__ float reduce_scatter(float (&v)[N], int lane) {
     return r;
 }
 
-template <int NG, int NW>
-// occupancy pin for the headline shape (S <= 5 channels): keeps the register allocation at the
-// count that fits one more CTA per SM (ptxas otherwise drifts a few registers above it; 6 CTAs
-// = 80 registers spills and measured 9% slower)
-__global__ void __launch_bounds__(32 * NW, (NG == 2 && NW == 4) ? 5 : 1) composite_bwd_kernel(const CompositeBwdParams p) {
+// Per warp (one 8x4 pixel block): the forward pass left one contributor bit per (instance, block).  The warp streams
+// its tile's contributor bytes BACK TO FRONT, 128 instances per step, compacts the positions whose bit is set into a
+// circular queue (warp scan) and processes batches of 32 of them: every staged entry is one that some pixel of the
+// block composited in the forward pass — no culling test, no record fetch and no exp() for anything else.
+template <int NG, int NW, int MINB>
+__global__ void __launch_bounds__(32 * NW, MINB) composite_bwd_kernel(const CompositeBwdParams p) {
     constexpr int NC = 4 * NG;              // padded channel count {r,g,b,f...}
     constexpr int V = 8 + NC;               // gradient row width
     constexpr int V0 = V <= 16 ? 16 : 32;   // first butterfly chunk
     constexpr int V1 = V > 32 ? 4 : 0;      // tail chunk (only V == 36)
     constexpr int RG = 2 + NG;
     __shared__ float4 sRec[NW][RG][32];
-    __shared__ int sId[NW][32];
+    __shared__ uint32_t sId[NW][32];
+    __shared__ uint32_t sQ[NW][R3DG_QCAP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int PARTS = 8 / NW;
     const int tile = (int)p.tile_order[blockIdx.x / PARTS];
@@ -77,10 +80,12 @@ __global__ void __launch_bounds__(32 * NW, (NG == 2 && NW == 4) ? 5 : 1) composi
     const bool inside = px < p.W && py < p.H;
     const float pxf = (float)px, pyf = (float)py;
     const uint2 range = p.ranges[tile];
+    const uint32_t lo = range.x;
     const size_t HW = (size_t)p.H * p.W, pix = (size_t)p.W * py + px;
     const float4* __restrict__ rec4 = reinterpret_cast<const float4*>(p.rec);
     const int rec4n = p.recf >> 2;
-    const uint32_t* __restrict__ plist = p.point_list + range.x;
+    const uint32_t* __restrict__ plist = p.point_list + lo;
+    uint32_t* q = sQ[warp];
 
     const float T_final = inside ? p.final_T[pix] : 0.0f;
     float T = T_final;
@@ -90,11 +95,12 @@ __global__ void __launch_bounds__(32 * NW, (NG == 2 && NW == 4) ? 5 : 1) composi
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) total = max(total, __shfl_xor_sync(0xffffffffu, total, o));
     total = min(total, (int)(range.y - range.x));
+    if (total == 0) return;
 
-    float dpix[NC], accum[NC], lastc[NC];
+    float dpix[NC], accum[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-        accum[c] = 0.0f; lastc[c] = 0.0f;
+        accum[c] = 0.0f;
         float g = 0.0f;
         if (inside) {
             if (c < 3) g = p.dL_dpix[c * HW + pix];
@@ -104,50 +110,77 @@ __global__ void __launch_bounds__(32 * NW, (NG == 2 && NW == 4) ? 5 : 1) composi
     }
     const float dpix_d = inside ? p.dL_dpix_d[pix] : 0.0f;
     const float dpix_o = inside ? p.dL_dpix_o[pix] : 0.0f;
-    float accum_d = 0.0f, accum_o = 0.0f, last_alpha = 0.0f, last_depth = 0.0f;
+    float accum_d = 0.0f, accum_o = 0.0f;
     const float bg_dot = p.bg[0] * dpix[0] + p.bg[1] * dpix[1] + p.bg[2] * dpix[2];
     const float ddelx_dx = 0.5f * p.W, ddely_dy = 0.5f * p.H;
     const bool geo = p.backward_geometry != 0;
 
-    // back-to-front: chunk entry `lane` of the chunk starting at `base` is list position
-    // total-1-(base+lane).  Pipeline as in the forward.
-    uint32_t id_cur = lane < total ? plist[total - 1 - lane] : 0u;
+    // ---- contributor-mask stream, descending: word w holds instances [4w, 4w+4); lane takes word w_next - lane -------
+    const uint32_t hi = lo + (uint32_t)total;                 // instances [lo, hi) matter
+    const long long w_low = (long long)(lo >> 2);             // lowest word of the tile
+    long long w_next = (long long)((hi - 1u) >> 2);           // highest word still to scan
+    uint32_t m_nxt = (w_next - lane >= w_low) ? p.cmask32[w_next - lane] : 0u;
+    int qhead = 0, qcount = 0;
+    auto scan_step = [&]() {
+        const long long w = w_next - lane;
+        uint32_t flags = 0u;
+        if (w >= w_low) {
+            flags = (m_nxt >> wb) & 0x01010101u;
+            const uint32_t e0 = (uint32_t)w << 2;
+            if (e0 < lo) flags &= 0xffffffffu << (8 * (lo - e0));
+            if (e0 + 4 > hi) flags &= 0xffffffffu >> (8 * (e0 + 4 - hi));
+        }
+        w_next -= 32;
+        m_nxt = (w_next - lane >= w_low) ? p.cmask32[w_next - lane] : 0u;
+        uint32_t tot;
+        uint32_t slot = (uint32_t)(qhead + qcount) + warp_excl_scan(__popc(flags), lane, tot);
+        const uint32_t rel = ((uint32_t)w << 2) - lo;
+#pragma unroll
+        for (int k = 3; k >= 0; --k)                                              // back to front inside the word too
+            if (flags & (1u << (8 * k))) { q[slot & (R3DG_QCAP - 1)] = rel + k; ++slot; }
+        qcount += (int)tot;
+    };
+    while (qcount < 64 && w_next >= w_low) scan_step();
+    __syncwarp();
+
+    uint32_t id_cur = 0u;
     float4 r[RG];
 #pragma unroll
     for (int g = 0; g < RG; ++g) r[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane < total) {
+    if (lane < qcount) {
+        id_cur = plist[q[(qhead + lane) & (R3DG_QCAP - 1)]];
 #pragma unroll
         for (int g = 0; g < RG; ++g) r[g] = rec4[(size_t)id_cur * rec4n + g];
     }
-    uint32_t id_nxt = 32 + lane < total ? plist[total - 1 - (32 + lane)] : 0u;
 
-    for (int base = 0; base < total; base += 32) {
-        const int n = min(32, total - base);
+    while (qcount > 0) {
+        const int n = min(32, qcount);
         __syncwarp();
-        sId[warp][lane] = (int)id_cur;
+        sId[warp][lane] = id_cur;
 #pragma unroll
         for (int g = 0; g < RG; ++g) sRec[warp][g][lane] = r[g];
-        uint32_t word = __ballot_sync(0xffffffffu, lane < n && touch_block(r[0], r[1], (float)bx0, (float)by0));
-        id_cur = id_nxt;
-        if (base + 32 + lane < total) {
+        const int h0 = qhead;
+        qhead = (qhead + n) & (R3DG_QCAP - 1);
+        qcount -= n;
+        while (qcount < 64 && w_next >= w_low) scan_step();
+        __syncwarp();
+        if (lane < qcount) {
+            id_cur = plist[q[(qhead + lane) & (R3DG_QCAP - 1)]];
 #pragma unroll
             for (int g = 0; g < RG; ++g) r[g] = rec4[(size_t)id_cur * rec4n + g];
         }
-        id_nxt = base + 64 + lane < total ? plist[total - 1 - (base + 64 + lane)] : 0u;
-        __syncwarp();
-        while (word) {
-            const int j = __ffs(word) - 1;
-            word &= word - 1;
-            const int k = total - 1 - (base + j);            // 0-based list position == contributor
+#pragma unroll 1
+        for (int j = 0; j < n; ++j) {
+            const int k = (int)q[(h0 + j) & (R3DG_QCAP - 1)];                    // 0-based list position == contributor
             const float4 a = sRec[warp][0][j];
             const float4 b = sRec[warp][1][j];
             const float dx = sub_(a.x, pxf), dy = sub_(a.y, pyf);
-            const float q = fma_(dx, mul_(dx, a.z), mul_(dy, mul_(dy, b.x)));
-            const float power = fma_(q, -0.5f, -mul_(dy, mul_(dx, a.w)));
+            const float qd = fma_(dx, mul_(dx, a.z), mul_(dy, mul_(dy, b.x)));
+            const float power = fma_(qd, -0.5f, -mul_(dy, mul_(dx, a.w)));
             const float G = expf(power);
             const float alpha = fminf(0.99f, mul_(b.y, G));
+            // the same three tests as the forward pass (identical arithmetic) + "not behind this pixel's last contributor"
             const bool valid = k < last_contributor && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-            if (!__any_sync(0xffffffffu, valid)) continue;
             float v0[V0];
             float v1[V1 > 0 ? V1 : 4];
 #pragma unroll
@@ -165,22 +198,22 @@ __global__ void __launch_bounds__(32 * NW, (NG == 2 && NW == 4) ? 5 : 1) composi
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int c = 4 * g + e;
-                        accum[c] = last_alpha * lastc[c] + (1.0f - last_alpha) * accum[c];
-                        lastc[c] = cc[e];
+                        // accum[c] = colour accumulated BEHIND this entry (backward.cu:541-545).  The reference keeps
+                        // (last_alpha, last_color) and folds them in when the next contributor arrives; folding right
+                        // after use is the same arithmetic on the same values and needs no per-channel `last` registers.
                         if (c < 3 || geo) dL_dalpha += (cc[e] - accum[c]) * dpix[c];
+                        accum[c] = alpha * cc[e] + (1.0f - alpha) * accum[c];
                         const float gv = dchannel_dcolor * dpix[c];
                         if (8 + c < V0) v0[(8 + c) < V0 ? (8 + c) : 0] = gv;
                         else v1[(8 + c - V0) >= 0 && (8 + c - V0) < 4 ? (8 + c - V0) : 0] = gv;
                     }
                 }
                 const float depth = b.z;
-                accum_d = last_alpha * last_depth + (1.0f - last_alpha) * accum_d;
-                last_depth = depth;
                 dL_dalpha += (depth - accum_d) * dpix_d;
-                accum_o = last_alpha + (1.0f - last_alpha) * accum_o;
+                accum_d = alpha * depth + (1.0f - alpha) * accum_d;
                 dL_dalpha += (1.0f - accum_o) * dpix_o;
+                accum_o = alpha + (1.0f - alpha) * accum_o;
                 dL_dalpha *= T;
-                last_alpha = alpha;
                 dL_dalpha += (-T_final / (1.0f - alpha)) * bg_dot;
                 const float dL_dG = b.y * dL_dalpha;
                 const float gdx = G * dx, gdy = G * dy;
@@ -210,15 +243,14 @@ __global__ void __launch_bounds__(32 * NW, (NG == 2 && NW == 4) ? 5 : 1) composi
     }
 }
 
-int composite_nw();
+template <int NG> struct BwdOcc { static constexpr int v = NG <= 2 ? 6 : (NG <= 3 ? 5 : (NG <= 5 ? 4 : 3)); };
 template <int NG>
 static void launch_bwd_ng(const CompositeBwdParams& p, int tiles, cudaStream_t stream) {
-    if (composite_nw() == 4) composite_bwd_kernel<NG, 4><<<tiles * 2, 128, 0, stream>>>(p);
-    else composite_bwd_kernel<NG, 8><<<tiles, 256, 0, stream>>>(p);
+    composite_bwd_kernel<NG, 4, BwdOcc<NG>::v><<<tiles * 2, 128, 0, stream>>>(p);      // two 4-warp CTAs per tile
 }
 
 int launch_composite_backward(const r3dg_raster_bwd_args& a, const GeomLayout& gl, const ImgLayout& il,
-                              const uint32_t* point_list, cudaStream_t stream) {
+                              char* bin, const BinLayout& bl, cudaStream_t stream) {
     char* geom = (char*)a.geom;
     char* img = (char*)a.img;
     CompositeBwdParams p;
@@ -226,7 +258,8 @@ int launch_composite_backward(const r3dg_raster_bwd_args& a, const GeomLayout& g
     p.backward_geometry = a.backward_geometry;
     const int gy = (a.H + R3DG_TILE - 1) / R3DG_TILE;
     p.ranges = (const uint2*)(img + il.ranges);
-    p.point_list = point_list; p.header = (const GeomHeader*)(geom + gl.header);
+    p.point_list = (const uint32_t*)(bin + bl.point_list); p.cmask32 = (const uint32_t*)(bin + bl.cmask);
+    p.header = (const GeomHeader*)(geom + gl.header);
     p.tile_order = (const uint32_t*)(img + il.tile_order);
     p.rec = (const float*)(geom + gl.rec);
     p.bg = a.background;

@@ -21,11 +21,13 @@ int launch_binning(int P, int W, int H, char* geom, const GeomLayout& gl, char* 
                    char* bin, const BinLayout& bl, int num_sms, cudaStream_t stream, stage_mark_fn mark);
 int launch_rebuild_keys(int T, const void* ranges, const uint32_t* point_list, const float* rec, int recf,
                         long long limit, uint64_t* keys, cudaStream_t stream);
+int launch_block_masks(int W, int H, const GeomLayout& gl, const ImgLayout& il, char* geom, char* img, char* bin,
+                       const BinLayout& bl, cudaStream_t stream);
 int launch_composite_forward(const r3dg_raster_fwd_args& a, const GeomLayout& gl,
-                             const ImgLayout& il, const uint32_t* point_list,
+                             const ImgLayout& il, char* bin, const BinLayout& bl,
                              cudaStream_t stream, stage_mark_fn mark);
 int launch_composite_backward(const r3dg_raster_bwd_args& a, const GeomLayout& gl,
-                              const ImgLayout& il, const uint32_t* point_list,
+                              const ImgLayout& il, char* bin, const BinLayout& bl,
                               cudaStream_t stream);
 int launch_projection_backward(const r3dg_raster_bwd_args& a, const GeomLayout& gl,
                                cudaStream_t stream);

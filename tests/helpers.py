@@ -77,7 +77,7 @@ def bvh_case(recipe, P, n_src, N, boost, seed=3):
     """Seeded BVH / visibility case: P Gaussians, rays from the first n_src of them along N
     Fibonacci directions around the FLIPPED normal (so that they run through the scene),
     origins pre-offset by 0.05 d like bvh/__init__.py:63."""
-    from relightable3dgaussian_b200.raytracer import fibonacci_sphere_sampling
+    from oracle.oracle_sampling import fibonacci_sphere_sampling
     sc = synth.make_scene(P, recipe, seed, 0)
     scales = sc.scales * boost
     normals = sc.normals
@@ -90,7 +90,7 @@ def bvh_case(recipe, P, n_src, N, boost, seed=3):
 def shading_case(P, N, He, seed):
     """Seeded inputs of `rendering_equation` (neilf.py:339): activated material parameters, SH
     incident light, raw env map (softplus applied by the light object), baked visibility / dirs."""
-    from relightable3dgaussian_b200.raytracer import fibonacci_sphere_sampling
+    from oracle.oracle_sampling import fibonacci_sphere_sampling
     g = torch.Generator().manual_seed(500 + seed)
     n = torch.nn.functional.normalize(torch.randn(P, 3, generator=g), dim=-1)
     dirs, areas = fibonacci_sphere_sampling(n, N, random_rotate=False)
