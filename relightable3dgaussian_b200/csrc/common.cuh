@@ -89,7 +89,7 @@ inline __host__ size_t geom_grad_pad() {
 }
 
 struct GeomLayout {
-    size_t header, rec, tiles_touched, rects, clamped, scan_state, sort, grad, total;
+    size_t header, rec, tiles_touched, rects, brects, clamped, scan_state, sort, grad, total;
     int P, S, recf;
     __host__ GeomLayout(int P_, int S_) : P(P_), S(S_) {
         recf = rec_floats(S_);
@@ -98,6 +98,7 @@ struct GeomLayout {
         rec = off;           off = align_up(off + (size_t)P_ * recf * 4, 256);
         tiles_touched = off; off = align_up(off + (size_t)P_ * 4, 256);
         rects = off;         off = align_up(off + (size_t)P_ * 8, 256);         // packed tile rectangles
+        brects = off;        off = align_up(off + (size_t)P_ * 8, 256);         // packed block rectangles (block_rect())
         clamped = off;       off = align_up(off + (size_t)P_, 256);
         scan_state = off;    off = align_up(off + ((size_t)P_ / R3DG_SCAN_ITEMS + 2) * 4, 256);
         sort = off;          off = align_up(off + SortLayout(P_).total, 256);   // depth sort of the Gaussians
@@ -188,6 +189,42 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+// ---- TMA-unit bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier (SYNCS) -------------------
+// One instruction moves a contiguous, 16-byte aligned slab global -> shared with no register staging and no
+// per-thread address arithmetic; completion is signalled by transaction bytes on a shared-memory mbarrier.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global bulk store (UBLKCP.G.S): the issuing thread commits and waits until the source may be reused
+__device__ __forceinline__ void bulk_copy_s2g(void* gmem_dst, const void* smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 // Asynchronous, coalesced copy of a CTA's [nvalid][rowf] float slab into the TRANSPOSED shared slab
 // s[k * ld + t] (element k of row t): every warp instruction moves 32 consecutive floats (128 B of
 // global memory) to 32 different banks.  nthreads = blockDim.x.
@@ -272,6 +309,29 @@ __device__ __forceinline__ bool touch_block(const float4 A, const float4 B, floa
     // slack also absorbs the approximate log/divide above (relative error ~1e-6 of tau <= ~12)
     const float slack = 1.0f + 1e-5f * (ca * um * um + cc * vm * vm + 2.0f * fabsf(cb) * um * vm);
     return !(qmin > tau + slack);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Conservative footprint of a Gaussian in units of the compositors' pixel blocks (8 px wide, 4 px high): the
+// axis-aligned bounding box of the ellipse {q <= tau_b} around the projected centre, where every pixel that can pass
+// the reference's alpha >= 1/255 test (q <= tau = 2 ln(255 o), evaluated in fp32) lies.  tau_b = 1.02 tau + 0.25
+// absorbs the fp32 evaluation error of the per-pixel quadratic for conics with trace^2/det <= 6000 (error <=
+// 2.4e-7 * 1.5 * trace^2/det * q); worse-conditioned, non-positive-definite or NaN conics get the full range.
+// Packed {bx0 | bx1 << 16, by0 | by1 << 16}, inclusive block column / row indices; empty (bx0 > bx1) when the
+// opacity is below 1/255.  This is only a PRE-filter (block_mask_kernel): the compositor still applies the exact
+// ellipse / rectangle test to what passes, and the exact per-pixel tests to what passes that.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint2 block_rect(float gx, float gy, float ca, float cb, float cc, float op) {
+    if (op < 1.0f / 255.0f) return make_uint2(1u, 0u);                       // bx0 = 1 > bx1 = 0: touches nothing
+    const float det = ca * cc - cb * cb, tr = ca + cc;
+    const float tau = 2.0f * __logf(255.0f * op);
+    if (!(ca > 0.0f && cc > 0.0f && det > 0.0f && tr * tr <= 6000.0f * det && tau >= 0.0f)) return make_uint2(0xffff0000u, 0xffff0000u);
+    const float tb = 1.02f * tau + 0.25f;
+    const float hx = sqrtf(tb * cc / det) * 1.0001f + 0.01f, hy = sqrtf(tb * ca / det) * 1.0001f + 0.01f;
+    auto blk = [](float v, float inv) { return (uint32_t)fminf(fmaxf(floorf(v * inv), 0.0f), 65535.0f); };
+    // a box entirely left of / above the image maps to an empty range (pixels have coordinates >= 0)
+    if (gx + hx < 0.0f || gy + hy < 0.0f) return make_uint2(1u, 0u);
+    return make_uint2(blk(gx - hx, 0.125f) | (blk(gx + hx, 0.125f) << 16), blk(gy - hy, 0.25f) | (blk(gy + hy, 0.25f) << 16));
 }
 
 // The same test for all 8 blocks of a tile at once (block b: x offset 8 * (b & 1), y offset 4 * (b >> 1)), with

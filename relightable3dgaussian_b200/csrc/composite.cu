@@ -38,22 +38,30 @@ struct CompositeFwdParams {
     float *out_color, *out_opacity, *out_depth, *out_feature, *out_weights;
 };
 
-// One thread per (tile, Gaussian) instance: the 8-bit block-touch mask of the instance and a zeroed contributor byte.
-// CTA per tile (heaviest first); reads 4 B + 32 B (gathered record head), writes 2 B per instance.
-__global__ void __launch_bounds__(256) block_mask_kernel(int gx, int recf, const uint2* __restrict__ ranges,
+// One thread per (tile, Gaussian) instance: the 8-bit block pre-filter mask of the instance (bit b = block b of the
+// tile intersects the Gaussian's conservative block rectangle, projection.cu / block_rect()) and a zeroed contributor
+// byte.  CTA per tile (heaviest first); reads 4 B + a gathered 8 B, writes 2 B per instance.
+__global__ void __launch_bounds__(256) block_mask_kernel(int gx, const uint2* __restrict__ ranges,
                                                          const uint32_t* __restrict__ tile_order,
                                                          const uint32_t* __restrict__ point_list,
-                                                         const float* __restrict__ rec, uint8_t* __restrict__ bmask,
+                                                         const uint2* __restrict__ brects, uint8_t* __restrict__ bmask,
                                                          uint8_t* __restrict__ cmask) {
     const int tile = (int)tile_order[blockIdx.x];
     const uint2 range = ranges[tile];
-    const float TX0 = (float)((tile % gx) * R3DG_TILE), TY0 = (float)((tile / gx) * R3DG_TILE);
-    const float4* __restrict__ rec4 = reinterpret_cast<const float4*>(rec);
-    const int rec4n = recf >> 2;
+    const uint32_t c0 = 2u * (uint32_t)(tile % gx), r0 = 4u * (uint32_t)(tile / gx);   // first block column / row of the tile
     for (uint32_t i = range.x + threadIdx.x; i < range.y; i += 256) {
-        const uint32_t id = point_list[i];
-        const float4 A = rec4[(size_t)id * rec4n], B = rec4[(size_t)id * rec4n + 1];
-        bmask[i] = (uint8_t)touch_mask8(A, B, TX0, TY0);
+        const uint2 br = brects[point_list[i]];
+        const uint32_t bx0 = br.x & 0xffffu, bx1 = br.x >> 16, by0 = br.y & 0xffffu, by1 = br.y >> 16;
+        uint32_t cols = 0u, rows = 0u;
+        if (bx0 <= c0 && c0 <= bx1) cols |= 1u;
+        if (bx0 <= c0 + 1u && c0 + 1u <= bx1) cols |= 2u;
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k)
+            if (by0 <= r0 + k && r0 + k <= by1) rows |= 1u << k;
+        // block b = (row b >> 1, column b & 1): spread the row bits to even positions, combine with the column bits
+        const uint32_t spread = (rows & 1u) | ((rows & 2u) << 1) | ((rows & 4u) << 2) | ((rows & 8u) << 3);
+        const uint32_t m = ((cols & 1u) ? spread : 0u) | ((cols & 2u) ? (spread << 1) : 0u);
+        bmask[i] = (uint8_t)m;
         cmask[i] = 0;
     }
 }
@@ -61,10 +69,11 @@ __global__ void __launch_bounds__(256) block_mask_kernel(int gx, int recf, const
 // NW = warps per CTA (4: two CTAs per tile).  Warps are autonomous: no
 // CTA-wide barrier anywhere; the CTA only exists so that the warps of a tile share L1 lines.
 //
-// Per warp (one 8x4 pixel block): the tile's block-touch mask bytes are streamed 128 instances at a time and the
+// Per warp (one 8x4 pixel block): the tile's block pre-filter mask bytes are streamed 128 instances at a time and the
 // positions whose bit for THIS block is set are compacted into a circular queue (warp scan); batches of 32 queued
-// entries are then fetched (id -> packed record, registers, one batch ahead), staged in the warp's shared-memory slab
-// and composited — every staged entry is one the block may touch, there is no per-entry culling left in the loop.
+// entries are then fetched (id -> packed record, registers, one batch ahead) and staged in the warp's shared-memory
+// slab.  Each lane applies the exact-conservative ellipse / rectangle test to ITS OWN staged entry (one evaluation per
+// entry instead of one per (entry, warp-iteration)); a ballot yields the bitmap of entries worth compositing.
 template <int NG, int NW, int MINB>
 __global__ void __launch_bounds__(32 * NW, MINB) composite_fwd_kernel(const CompositeFwdParams p) {
     constexpr int RG = 2 + NG;                       // float4 groups per record
@@ -140,6 +149,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_fwd_kernel(const Comp
         sId[warp][lane] = id_cur;
 #pragma unroll
         for (int g = 0; g < RG; ++g) sRec[warp][g][lane] = r[g];
+        uint32_t word = __ballot_sync(0xffffffffu, lane < n && touch_block(r[0], r[1], (float)bx0, (float)by0));
         const int h0 = qhead;
         qhead = (qhead + n) & (R3DG_QCAP - 1);
         qcount -= n;
@@ -152,8 +162,10 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_fwd_kernel(const Comp
             for (int g = 0; g < RG; ++g) r[g] = rec4[(size_t)id_cur * rec4n + g];
         }
         uint32_t cw = 0u;                                               // bit j: entry j was composited by some pixel
-#pragma unroll 1
-        for (int j = 0; j < n; ++j) {
+        int last_j = -1;                                                // this pixel's last accepted entry of the batch
+        while (word) {
+            const int j = __ffs(word) - 1;
+            word &= word - 1;
             const float4 a = sRec[warp][0][j];
             const float4 b = sRec[warp][1][j];
             const float dx = sub_(a.x, pxf), dy = sub_(a.y, pyf);
@@ -178,7 +190,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_fwd_kernel(const Comp
                 Dp = fma_(w, b.z, Dp);
                 Op = add_(Op, w);
                 T = test_T;
-                last_contributor = q[(h0 + j) & (R3DG_QCAP - 1)] + 1u;      // 1-based position in the tile list
+                last_j = j;
             }
             if (__any_sync(0xffffffffu, valid)) {
                 cw |= 1u << j;
@@ -190,6 +202,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_fwd_kernel(const Comp
             }
             if (__all_sync(0xffffffffu, done)) { all_done = true; break; }
         }
+        if (last_j >= 0) last_contributor = q[(h0 + last_j) & (R3DG_QCAP - 1)] + 1u;     // 1-based position in the tile list
         // contributor bits for the backward pass: one fire-and-forget atomic per composited entry
         if ((cw >> lane) & 1u) {
             const uint32_t e = lo + mypos;
@@ -272,8 +285,8 @@ static void launch_fwd_ng(const CompositeFwdParams& p, int tiles, cudaStream_t s
 int launch_block_masks(int W, int H, const GeomLayout& gl, const ImgLayout& il, char* geom, char* img, char* bin,
                        const BinLayout& bl, cudaStream_t stream) {
     const int gx = (W + R3DG_TILE - 1) / R3DG_TILE, gy = (H + R3DG_TILE - 1) / R3DG_TILE;
-    block_mask_kernel<<<gx * gy, 256, 0, stream>>>(gx, gl.recf, (const uint2*)(img + il.ranges), (const uint32_t*)(img + il.tile_order),
-                                                   (const uint32_t*)(bin + bl.point_list), (const float*)(geom + gl.rec),
+    block_mask_kernel<<<gx * gy, 256, 0, stream>>>(gx, (const uint2*)(img + il.ranges), (const uint32_t*)(img + il.tile_order),
+                                                   (const uint32_t*)(bin + bl.point_list), (const uint2*)(geom + gl.brects),
                                                    (uint8_t*)(bin + bl.bmask), (uint8_t*)(bin + bl.cmask));
     R3DG_CUDA_TRY(cudaGetLastError());
     return 0;

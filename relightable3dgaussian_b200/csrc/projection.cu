@@ -60,7 +60,8 @@ __device__ __forceinline__ void cov3d_from_scale_rot(const float* __restrict__ s
 
 // SH -> RGB (forward.cu:20-71).  sh rows are [M][3] floats.
 // `sh` points at coefficient 0 / channel 0 of this Gaussian; consecutive floats of its [M][3] row
-// are `stride` apart (1 in global memory, PROJ_THREADS+1 in the transposed shared-memory slab).
+// are `stride` apart (1 in global memory, PROJ_THREADS+1 in the transposed shared-memory slab);
+// stride 0 = contiguous, 16-byte aligned row read with vector loads (row-major slab of the bulk-copy path).
 __device__ __forceinline__ void sh_to_rgb(int deg, float px, float py, float pz,
                                           const float* __restrict__ campos,
                                           const float* __restrict__ sh, int stride, float* rgb,
@@ -89,13 +90,33 @@ __device__ __forceinline__ void sh_to_rgb(int deg, float px, float py, float pz,
     }
     const int n = (deg + 1) * (deg + 1);
     float res[3];
+    if (stride == 0) {
+        // row-major slab row (TMA bulk copy path): 16-byte vector reads, each consumed immediately.  Element
+        // i = 3k + c adds w[k] * sh[k][c] to channel c in the same k order as below (same fma chain per channel).
+        const float4* __restrict__ r4 = reinterpret_cast<const float4*>(sh);
+        res[0] = res[1] = res[2] = 0.0f;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) res[c] = w[0] * sh[c * stride];
+        for (int i4 = 0; i4 < 12; ++i4) {
+            if (4 * i4 < 3 * n) {
+                const float4 v4 = r4[i4];
+                const float v[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
-    for (int k = 1; k < 16; ++k) {
-        if (k < n) {
+                for (int e = 0; e < 4; ++e) {
+                    const int i = 4 * i4 + e, k = i / 3, c = i - 3 * k;
+                    if (k == 0) res[c] = w[0] * v[e];
+                    else if (k < n) res[c] = fmaf(w[k], v[e], res[c]);
+                }
+            }
+        }
+    } else {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) res[c] = fmaf(w[k], sh[(3 * k + c) * stride], res[c]);
+        for (int c = 0; c < 3; ++c) res[c] = w[0] * sh[c * stride];
+#pragma unroll
+        for (int k = 1; k < 16; ++k) {
+            if (k < n) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) res[c] = fmaf(w[k], sh[(3 * k + c) * stride], res[c]);
+            }
         }
     }
     clamped_bits = 0;
@@ -121,6 +142,7 @@ struct ProjParams {
     GeomHeader* header;
     uint32_t *sort_keys, *sort_vals;      // depth-sort input (radix_sort.cu)
     uint2* rects;                         // packed tile rectangles (binning.cu)
+    uint2* brects;                        // packed block rectangles (compositor pre-filter, common.cuh block_rect)
 };
 
 #define PROJ_THREADS 128
@@ -165,18 +187,30 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjParams 
             alive = false;
         }
     }
-    // SH rows ([M][3] floats, 192 B at M=16 = 3/4 of the kernel's input bytes) are staged through a
-    // transposed shared slab.  The copy is asynchronous (LDGSTS) and is issued as soon as the depth
-    // cull is known, so that it overlaps the covariance / projection math below; blocks whose
-    // Gaussians are all behind the camera skip it.
-    bool slab_loaded = false;
+    // SH rows ([M][3] floats, 192 B at M=16 = 3/4 of the kernel's input bytes) are staged in shared memory.  The
+    // CTA's rows are ONE contiguous 24 KB slab, so a single TMA-unit bulk copy (cp.async.bulk -> UBLKCP) moves it
+    // with no per-thread instructions and signals an mbarrier; it is issued as soon as the depth cull is known and
+    // overlaps the covariance / projection math below.  Blocks whose Gaussians are all behind the camera skip it.
+    // (Rows that are not a multiple of 16 B — SH degree 0 / 2 — or a ragged, unaligned tail fall back to 4-byte
+    // LDGSTS copies into a transposed slab.)
+    __shared__ __align__(8) uint64_t sBar;
+    bool slab_loaded = false, slab_bulk = false;
+    const int rowf = 3 * p.M;
     if (p.colors_precomp == nullptr) {
+        const int block_base = blockIdx.x * PROJ_THREADS;
+        const int nvalid = min(PROJ_THREADS, p.P - block_base);
+        const float* src = p.shs + (size_t)block_base * rowf;
+        const unsigned bytes = (unsigned)nvalid * (unsigned)rowf * 4u;
+        slab_bulk = (rowf & 3) == 0 && (bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+        if (threadIdx.x == 0 && slab_bulk) { mbar_init(&sBar, 1); fence_proxy_async_smem(); }
         slab_loaded = __syncthreads_or(alive) != 0;
         if (slab_loaded) {
-            const int rowf = 3 * p.M, block_base = blockIdx.x * PROJ_THREADS;
-            load_rows_transposed_async(sSH, PROJ_THREADS + 1, p.shs + (size_t)block_base * rowf,
-                                       min(PROJ_THREADS, p.P - block_base), rowf, PROJ_THREADS);
-            cp_async_commit();
+            if (slab_bulk) {
+                if (threadIdx.x == 0) { mbar_arrive_expect_tx(&sBar, bytes); bulk_copy_g2s(sSH, src, bytes, &sBar); }
+            } else {
+                load_rows_transposed_async(sSH, PROJ_THREADS + 1, src, nvalid, rowf, PROJ_THREADS);
+                cp_async_commit();
+            }
         }
     }
     float pix_x = 0.f, pix_y = 0.f, con_a = 0.f, con_b = 0.f, con_c = 0.f;
@@ -240,12 +274,22 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjParams 
     float rgb[3] = {0.f, 0.f, 0.f};
     if (p.colors_precomp == nullptr) {
         if (slab_loaded) {
-            cp_async_wait_all();
-            __syncthreads();
-            if (alive) {
-                unsigned cl = 0;
-                sh_to_rgb(p.D, px, py, pz, sCam, sSH + threadIdx.x, PROJ_THREADS + 1, rgb, cl);
-                p.clamped[idx] = (uint8_t)cl;
+            if (slab_bulk) {
+                mbar_wait(&sBar, 0);                       // all transaction bytes of the slab have landed
+                if (alive) {
+                    // row-major slab: this thread's row as 16-byte vectors (LDS.128: 4 consecutive rows span all banks)
+                    unsigned cl = 0;
+                    sh_to_rgb(p.D, px, py, pz, sCam, sSH + (size_t)threadIdx.x * rowf, 0, rgb, cl);
+                    p.clamped[idx] = (uint8_t)cl;
+                }
+            } else {
+                cp_async_wait_all();
+                __syncthreads();
+                if (alive) {
+                    unsigned cl = 0;
+                    sh_to_rgb(p.D, px, py, pz, sCam, sSH + threadIdx.x, PROJ_THREADS + 1, rgb, cl);
+                    p.clamped[idx] = (uint8_t)cl;
+                }
             }
         }
     } else if (alive) {
@@ -263,6 +307,7 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjParams 
                              : make_uint2(0u, 0u);
     }
     if (!alive) return;
+    p.brects[idx] = block_rect(pix_x, pix_y, con_a, con_b, con_c, p.opacities[idx]);
     float4* rec = reinterpret_cast<float4*>(p.rec + (size_t)idx * p.recf);
     rec[0] = make_float4(pix_x, pix_y, con_a, con_b);
     rec[1] = make_float4(con_c, p.opacities[idx], tz, __int_as_float(my_radius));
@@ -416,7 +461,7 @@ int launch_projection(const r3dg_raster_fwd_args& a, const GeomLayout& gl, cudaS
     const SortLayout sl(a.P);
     p.sort_keys = (uint32_t*)(geom + gl.sort + sl.keys_a);
     p.sort_vals = (uint32_t*)(geom + gl.sort + sl.vals_a);
-    p.rects = (uint2*)(geom + gl.rects);
+    p.rects = (uint2*)(geom + gl.rects); p.brects = (uint2*)(geom + gl.brects);
     const size_t sh_smem = a.shs ? (size_t)3 * a.M * (PROJ_THREADS + 1) * sizeof(float) : 0;
     project_kernel<<<(a.P + PROJ_THREADS - 1) / PROJ_THREADS, PROJ_THREADS, sh_smem, stream>>>(p);
     R3DG_CUDA_TRY(cudaGetLastError());

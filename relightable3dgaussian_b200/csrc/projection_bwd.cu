@@ -52,11 +52,20 @@ __device__ __forceinline__ void cov3d_plain(const float* s3, float mod, const fl
 #define PROJ_THREADS 128
 #define SLAB_LD (PROJ_THREADS + 1)
 __global__ void __launch_bounds__(PROJ_THREADS, 5) projection_bwd_kernel(const ProjBwdParams p) {
-    // SH rows (192 B at M=16) travel through a transposed shared slab s[k * SLAB_LD + t]: the
-    // block reads its [128][3M] slab of shs with coalesced 16B vectors, every thread turns its
-    // column into dL/dsh in place, and the slab is written back coalesced (zeros for culled rows).
-    extern __shared__ float sSH[];
+    // SH rows (192 B at M=16) travel through shared memory: the CTA's [128][3M] slab of shs is ONE contiguous
+    // 24 KB block, fetched by a single TMA-unit bulk copy (cp.async.bulk, mbarrier-signalled) into a row-major
+    // slab; every thread turns its row into dL/dsh in place (16-byte vector accesses) and ONE bulk store writes the
+    // slab back (zeros for culled rows).  Rows that are not 16-byte multiples (SH degree 0 / 2) or ragged / unaligned
+    // tails use the transposed slab s[k * SLAB_LD + t] with 4-byte LDGSTS copies and a coalesced write-back loop.
+    extern __shared__ __align__(16) float sSH[];
     __shared__ float sV[16], sPr[16], sCam[3];
+    __shared__ __align__(8) uint64_t sBar;
+    const int rowf_ = 3 * p.M, base_ = blockIdx.x * PROJ_THREADS;
+    const unsigned slab_bytes = (unsigned)min(PROJ_THREADS, p.P - base_) * (unsigned)rowf_ * 4u;
+    const bool bulk = p.shs && (rowf_ & 3) == 0 && (slab_bytes & 15u) == 0 &&
+                      (reinterpret_cast<uintptr_t>(p.shs + (size_t)base_ * rowf_) & 15) == 0 &&
+                      (!p.dL_dsh || (reinterpret_cast<uintptr_t>(p.dL_dsh + (size_t)base_ * rowf_) & 15) == 0);
+    if (threadIdx.x == 0 && bulk) { mbar_init(&sBar, 1); fence_proxy_async_smem(); }
     if (threadIdx.x < 16) { sV[threadIdx.x] = p.viewmatrix[threadIdx.x]; sPr[threadIdx.x] = p.projmatrix[threadIdx.x]; }
     if (threadIdx.x < 3) sCam[threadIdx.x] = p.campos[threadIdx.x];
     __syncthreads();
@@ -81,9 +90,13 @@ __global__ void __launch_bounds__(PROJ_THREADS, 5) projection_bwd_kernel(const P
         }
         if (p.shs) cl = p.clamped[idx];
     }
-    if (p.shs) {     // asynchronous (LDGSTS) transposed copy, overlapped with the covariance chain below
-        load_rows_transposed_async(sSH, SLAB_LD, p.shs + (size_t)block_base * rowf, nvalid, rowf, PROJ_THREADS);
-        cp_async_commit();
+    if (p.shs) {     // asynchronous copy of the slab, overlapped with the covariance chain below
+        if (bulk) {
+            if (threadIdx.x == 0) { mbar_arrive_expect_tx(&sBar, slab_bytes); bulk_copy_g2s(sSH, p.shs + (size_t)block_base * rowf, slab_bytes, &sBar); }
+        } else {
+            load_rows_transposed_async(sSH, SLAB_LD, p.shs + (size_t)block_base * rowf, nvalid, rowf, PROJ_THREADS);
+            cp_async_commit();
+        }
     }
     const float* V = sV;
     const float* proj = sPr;
@@ -223,7 +236,10 @@ __global__ void __launch_bounds__(PROJ_THREADS, 5) projection_bwd_kernel(const P
         }
     }
     // the SH slab was requested asynchronously at the top; it is first needed here
-    if (p.shs) { cp_async_wait_all(); __syncthreads(); }
+    if (p.shs) {
+        if (bulk) mbar_wait(&sBar, 0);
+        else { cp_async_wait_all(); __syncthreads(); }
+    }
     if (visible) {
         // ---- SH backward (backward.cu:20-139) -------------------------------------------------
         if (p.shs) {
@@ -270,6 +286,31 @@ __global__ void __launch_bounds__(PROJ_THREADS, 5) projection_bwd_kernel(const P
             }
             const int ncoef = (p.D + 1) * (p.D + 1);
             float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+            if (bulk) {
+                // row-major slab: 4 coefficients (12 floats = three 16-byte vectors) at a time, read, used, overwritten
+                float4* row4 = reinterpret_cast<float4*>(sSH + (size_t)threadIdx.x * rowf);
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb) {
+                    if (4 * kb < p.M) {
+                        float v[12];
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) { const float4 t4 = row4[3 * kb + i]; v[4 * i] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w; }
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const int k = 4 * kb + kk;
+                            const bool act = k < ncoef;
+                            const float s0 = act ? v[3 * kk] : 0.f, s1 = act ? v[3 * kk + 1] : 0.f, s2 = act ? v[3 * kk + 2] : 0.f;
+                            const float dotc = s0 * dRGB[0] + s1 * dRGB[1] + s2 * dRGB[2];
+                            ddx += wx[k] * dotc; ddy += wy[k] * dotc; ddz += wz[k] * dotc;
+                            v[3 * kk] = act ? w[k] * dRGB[0] : 0.f; v[3 * kk + 1] = act ? w[k] * dRGB[1] : 0.f; v[3 * kk + 2] = act ? w[k] * dRGB[2] : 0.f;
+                        }
+                        if (p.dL_dsh) {
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) row4[3 * kb + i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        }
+                    }
+                }
+            } else {
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 if (k < p.M) {
@@ -285,6 +326,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, 5) projection_bwd_kernel(const P
                     }
                 }
             }
+            }
             // dnormvdv (auxiliary.h:105-116)
             const float sum2 = dox * dox + doy * doy + doz * doz;
             const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
@@ -293,23 +335,36 @@ __global__ void __launch_bounds__(PROJ_THREADS, 5) projection_bwd_kernel(const P
             dmean3[2] += (-dox * doz * ddx - doy * doz * ddy + (sum2 - doz * doz) * ddz) * invsum32;
         }
     } else if (p.shs && p.dL_dsh) {
-        for (int k = 0; k < rowf; ++k) sSH[k * SLAB_LD + threadIdx.x] = 0.f;
-    }
-    if (p.shs && p.dL_dsh) {                        // coalesced write-back of the dL/dsh slab
-        __syncthreads();
-        const int total = nvalid * rowf;
-        float* dst = p.dL_dsh + (size_t)block_base * rowf;
-        if ((rowf & 3) == 0) {
-            float4* dst4 = reinterpret_cast<float4*>(dst);
-            for (int i4 = threadIdx.x; i4 < total / 4; i4 += PROJ_THREADS) {
-                const int i = 4 * i4, t = i / rowf, k = i - t * rowf;
-                dst4[i4] = make_float4(sSH[(k + 0) * SLAB_LD + t], sSH[(k + 1) * SLAB_LD + t],
-                                       sSH[(k + 2) * SLAB_LD + t], sSH[(k + 3) * SLAB_LD + t]);
+        if (bulk) {
+            if ((int)threadIdx.x < nvalid) {
+                float4* row4 = reinterpret_cast<float4*>(sSH + (size_t)threadIdx.x * rowf);
+                for (int i = 0; i < rowf / 4; ++i) row4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         } else {
-            for (int i = threadIdx.x; i < total; i += PROJ_THREADS) {
-                const int t = i / rowf, k = i - t * rowf;
-                dst[i] = sSH[k * SLAB_LD + t];
+            for (int k = 0; k < rowf; ++k) sSH[k * SLAB_LD + threadIdx.x] = 0.f;
+        }
+    }
+    if (p.shs && p.dL_dsh) {                        // write-back of the dL/dsh slab
+        float* dst = p.dL_dsh + (size_t)block_base * rowf;
+        if (bulk) {
+            fence_proxy_async_smem();               // this thread's generic-proxy stores -> visible to the bulk-copy engine
+            __syncthreads();
+            if (threadIdx.x == 0) { bulk_copy_s2g(dst, sSH, slab_bytes); bulk_wait_read_all(); }
+        } else {
+            __syncthreads();
+            const int total = nvalid * rowf;
+            if ((rowf & 3) == 0) {
+                float4* dst4 = reinterpret_cast<float4*>(dst);
+                for (int i4 = threadIdx.x; i4 < total / 4; i4 += PROJ_THREADS) {
+                    const int i = 4 * i4, t = i / rowf, k = i - t * rowf;
+                    dst4[i4] = make_float4(sSH[(k + 0) * SLAB_LD + t], sSH[(k + 1) * SLAB_LD + t],
+                                           sSH[(k + 2) * SLAB_LD + t], sSH[(k + 3) * SLAB_LD + t]);
+                }
+            } else {
+                for (int i = threadIdx.x; i < total; i += PROJ_THREADS) {
+                    const int t = i / rowf, k = i - t * rowf;
+                    dst[i] = sSH[k * SLAB_LD + t];
+                }
             }
         }
     }

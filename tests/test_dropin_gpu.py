@@ -35,6 +35,9 @@ def _render_through_wrapper(mod, sc, cam, S, bg, cots):
     out = rast(means3D=xyz, means2D=means2D, shs=shs, colors_precomp=None, opacities=opac, scales=scales, rotations=rots,
                cov3D_precomp=None, features=feats)
     (num_rendered, num_contrib, color, opacity, depth, feature, normal, surface_xyz, weights, radii) = out
+    # the reference returns num_contrib as a NON-OWNING from_blob view of imgBuffer (rasterize_points.cu:136-139): it dangles
+    # once autograd frees the saved buffers, so it is copied before backward
+    num_contrib = num_contrib.clone()
     loss = sum((o * d(c)).sum() for o, c in zip((color, opacity, depth, feature), cots))
     loss.backward()
     torch.cuda.synchronize()

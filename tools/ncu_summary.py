@@ -42,7 +42,7 @@ def main():
     src = list(csv.reader(io.StringIO(run([rep, "--page", "source", "--csv"]))))
     h = src[1]
     iS, iN, iE = h.index("Source"), h.index("# Samples"), h.index("Instructions Executed")
-    data = src[2:]
+    data = [r for r in src[2:] if len(r) > max(iS, iN, iE) and r[iE].strip().lstrip('-').isdigit() and r[iN].strip().isdigit()]
     segs, cur = [], None
     for k, r in enumerate(data):
         e, s = int(r[iE]), int(r[iN])
