@@ -157,8 +157,18 @@ def bench_ours(args, cfg, rank, local, world):
     E = torch.Tensor([])
     # exchange step (N > 1): dense = one all-reduce of all per-Gaussian gradients (256 MB); factored = all-reduce
     # of the dense rest (64 MB) + all-gather of the rank-1 SH-gradient factors (12 MB per rank) + local rebuild
-    factored = world > 1 and args.exchange == "factored"
-    bucket = rdist.FactoredGradExchange(P, S, M, dev) if factored else rdist.GradBucket(P, S, M, dev)
+    factored = world > 1 and args.exchange in ("factored", "p2p", "auto")
+    bucket, exchange_kind = None, "dense"
+    if world > 1 and args.exchange in ("p2p", "auto"):
+        try:                                             # one-kernel NVLink exchange; needs symmetric memory on this box
+            bucket, exchange_kind = rdist.P2PGradExchange(P, S, M, dev), "p2p"
+        except Exception as e:
+            if args.exchange == "p2p":
+                raise
+            print(f"[bench] P2P exchange unavailable ({type(e).__name__}: {e}); using the NCCL factored exchange", file=sys.stderr)
+    if bucket is None:
+        bucket = rdist.FactoredGradExchange(P, S, M, dev) if factored else rdist.GradBucket(P, S, M, dev)
+        exchange_kind = "factored" if factored else "dense"
     campos_tab = {}
 
     def campos_all(i):      # camera centres of the views the ranks render in step i, rank order
@@ -290,7 +300,7 @@ def bench_ours(args, cfg, rank, local, world):
                 tdist.all_reduce(p_.grad, op=tdist.ReduceOp.AVG)
         loss_host[i % 64:i % 64 + 1].copy_(loss.detach().reshape(1), non_blocking=True)
 
-    leaf_bucket = rdist.LeafGradBucket([params[k] for k in (0, 1, 3, 4, 5)], dev) if factored else None
+    leaf_bucket = rdist.LeafGradBucket([params[k] for k in (0, 1, 3, 4, 5)], dev, symmetric=exchange_kind == "p2p") if factored else None
     e_steps = max(3, args.steps // 2)
     # (1) the path an UNCHANGED caller of the reference surface gets: synchronous instance count (one host wait per forward,
     #     like the reference's own cudaMemcpy at rasterizer_impl.cu:291).  Its warm-up also teaches the deferred path the counts.
@@ -322,9 +332,14 @@ def bench_ours(args, cfg, rank, local, world):
             "dtype": "f32", "data": "synthetic",
             "config": workload_config(cfg, R),
             "arm": {"impl": "relightable3dgaussian_b200 (libr3dg_b200.so through the C ABI)", "P_visible": Pv,
-                    "parallelism": (f"view-parallel x{world}, per step 1 NCCL all-reduce of {bucket.dense.bytes() / 1e6:.0f} MB dense grads + 1 all-gather of "
-                                    f"{bucket.factor.numel() * 4 / 1e6:.0f} MB SH-gradient factors per rank + local rebuild" if factored else
-                                    f"view-parallel x{world}, 1 NCCL all-reduce of {bucket.bytes() / 1e6:.0f} MB grads/step") if world > 1 else "single GPU"},
+                    "exchange": exchange_kind if world > 1 else None,
+                    "parallelism": ("single GPU" if world == 1 else
+                                    f"view-parallel x{world}, per step ONE kernel over NVLink peer memory: SH gradient rebuilt from the peers' {bucket.factor.numel() * 4 / 1e6:.0f} MB "
+                                    f"factor buffers (P2P loads) + in-switch (multimem{'' if bucket.multicast else ' unavailable: peer load/store'}) all-reduce of {bucket.n_dense * 4 / 1e6:.0f} MB dense grads, "
+                                    "two symmetric-memory barriers, no NCCL collective" if exchange_kind == "p2p" else
+                                    f"view-parallel x{world}, per step 1 NCCL all-reduce of {bucket.dense.bytes() / 1e6:.0f} MB dense grads + 1 all-gather of "
+                                    f"{bucket.factor.numel() * 4 / 1e6:.0f} MB SH-gradient factors per rank + local rebuild" if exchange_kind == "factored" else
+                                    f"view-parallel x{world}, 1 NCCL all-reduce of {bucket.bytes() / 1e6:.0f} MB grads/step")},
             "e2e": {"value": e2e_value, "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e_steps, "ms_per_step": ms_sync / e_steps,
                     "what": "GaussianRasterizer module exactly as an unchanged caller of the reference surface uses it (synchronous instance count) + autograd + L1 loss; "
@@ -469,7 +484,7 @@ def main():
                          "configs #4 (1 GPU: 1.5M / 1600x1200) / #5 (N GPUs: 2M / 1920x1080), printed with \"workload\": \"stage2\"")
     ap.add_argument("--ref-shim", action="store_true", help="reference arm: force the raw-pointer shim instead of the stock wrapper + pybind module")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="factored", choices=["dense", "factored"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "factored", "dense"],
                     help="N > 1: gradient exchange per step (DESIGN.md section 5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -144,9 +144,23 @@ def run_ours(args, cfg, rank, local, world):
 
     # ---- multi-GPU: SH factor inside backward, everything else averaged at the leaves ---------------
     exchange = bucket = None
+    exchange_kind = None
     if world > 1:
-        exchange = rdist.FactoredGradExchange(P, S2, 16, dev)
-        bucket = rdist.LeafGradBucket([m[k] for k in m if k not in ("f_dc", "f_rest")], dev)
+        leaves = [m[k] for k in m if k not in ("f_dc", "f_rest")]
+        if args.exchange in ("p2p", "auto"):
+            try:                                             # one-kernel NVLink exchange (symmetric memory + NVLS)
+                exchange = rdist.P2PGradExchange(P, S2, 16, dev)
+                bucket = rdist.LeafGradBucket(leaves, dev, symmetric=True)
+                exchange_kind = "p2p"
+            except Exception as e:
+                if args.exchange == "p2p":
+                    raise
+                print(f"[bench] P2P exchange unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
+                exchange = bucket = None
+        if exchange is None:
+            exchange = rdist.FactoredGradExchange(P, S2, 16, dev)
+            bucket = rdist.LeafGradBucket(leaves, dev)
+            exchange_kind = "factored"
     gt_dev = [torch.empty(3, H, W, device=dev) for _ in range(2)]
     loss_host = torch.zeros(64).pin_memory()
     ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -247,8 +261,10 @@ def run_ours(args, cfg, rank, local, world):
         "config": {"workload": f"stage-2 neilf training step (BASELINE config #{'5' if world > 1 else '4'} shape): shading N={N} -> 16-channel pack -> raster fwd -> "
                                f"un-premultiply + L1 -> backward -> FusedAdam; {cfg['recipe']} seed {cfg['seed']}, P={P}, {W}x{H}, {cfg['views']}-camera ring",
                    "P": P, "W": W, "H": H, "S": S2, "N": N, "num_rendered": R, "P_visible": Pv,
-                   "parallelism": "single GPU" if world == 1 else f"view-parallel x{world}: SH-gradient factors all-gathered inside backward, all other leaf gradients "
-                                  f"in one {bucket.bytes() / 1e6:.0f} MB NCCL all-reduce after backward; bake sharded over ranks",
+                   "parallelism": "single GPU" if world == 1 else (
+                       f"view-parallel x{world} ({exchange_kind}): SH gradient rebuilt inside backward from the ranks' factors "
+                       f"({'P2P loads over NVLink' if exchange_kind == 'p2p' else 'NCCL all-gather'}), all other leaf gradients averaged in one "
+                       f"{bucket.bytes() / 1e6:.0f} MB {'NVLS multimem kernel' if exchange_kind == 'p2p' else 'NCCL all-reduce'} after backward; bake sharded over ranks"),
                    "l2": "inputs larger than L2 (P x N x 20 B baked tensors + 236 B/Gaussian parameters vs 126 MB)"},
         "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "what": "the step IS the public-API path (rendering_equation + GaussianRasterizer mirrors + autograd + FusedAdam); the per-step H2D of the "

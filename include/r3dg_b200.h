@@ -136,6 +136,29 @@ int r3dg_sh_grad_from_factors(int P, int D, int M, int num_views, const float* m
                               const float* campos, const float* factors, float scale,
                               float* dL_dsh, r3dg_stream_t stream);
 
+/* The same exchange as ONE kernel over NVLink peer memory (no NCCL call): the per-view factors and the dense
+ * per-Gaussian gradient section live in symmetric buffers mapped into every rank (the caller allocates and
+ * rendezvouses them, e.g. torch.distributed._symmetric_memory).  The launch
+ *   (a) rebuilds dL_dsh as r3dg_sh_grad_from_factors does, loading view v's 12 B per Gaussian straight from rank v's
+ *       buffer (coalesced P2P loads: the transfer overlaps the outer-product math), scale = 1/world;
+ *   (b) replaces the section dense[rank][0..n_dense) on EVERY rank by its mean over the ranks: rank r reduces slice r
+ *       with `multimem.ld_reduce` through the NVSwitch multicast mapping `dense_multicast` (in-switch reduction) and
+ *       writes it back to all ranks with `multimem.st`; with dense_multicast == NULL it falls back to peer loads/stores.
+ * The caller must order it between two cross-rank barriers (all ranks' backward kernels done before; all ranks'
+ * exchange kernels done before anyone reads the dense section or overwrites a factor buffer).  n_dense: floats,
+ * a multiple of 4, 16-byte aligned sections.  world <= 64. */
+typedef struct r3dg_exchange_args {
+    int P, D, M, world, rank;
+    const float* means3D;          /* [P,3] (replicated) */
+    const float* campos;           /* [world,3] camera centres of the ranks' views */
+    const float* factors[64];      /* [v]: rank v's [P,3] factor buffer (peer pointer; [rank] is local) */
+    float* dL_dsh;                 /* [P,M,3] local output */
+    long long n_dense;             /* 0: no dense job */
+    float* dense[64];              /* [v]: rank v's dense section (peer pointer) */
+    float* dense_multicast;        /* multicast address of the section or NULL */
+} r3dg_exchange_args;
+int r3dg_exchange_p2p(const r3dg_exchange_args* args, r3dg_stream_t stream);
+
 /* Replaces Rasterizer::markVisible (rasterizer_impl.cu:141-153) == `_C.mark_visible`
  * (rasterize_points.cu:237-256).  present: uint8/bool [P]. */
 int r3dg_mark_visible(int P, const float* means3D, const float* viewmatrix,

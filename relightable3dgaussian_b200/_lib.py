@@ -57,6 +57,12 @@ class ShadeArgs(ctypes.Structure):
                                  "dL_droughness", "dL_dviewdirs", "dL_dincidents", "dL_denv")])
 
 
+class ExchangeArgs(ctypes.Structure):
+    _fields_ = ([(n, c_int) for n in ("P", "D", "M", "world", "rank")] +
+                [("means3D", c_void_p), ("campos", c_void_p), ("factors", c_void_p * 64), ("dL_dsh", c_void_p),
+                 ("n_dense", c_ll), ("dense", c_void_p * 64), ("dense_multicast", c_void_p)])
+
+
 class AdamTensor(ctypes.Structure):
     _fields_ = ([(n, c_void_p) for n in ("param", "grad", "exp_avg", "exp_avg_sq")] +
                 [("n", c_ll), ("step", c_ll)] +
@@ -73,6 +79,7 @@ SYMBOLS = [
     ("r3dg_raster_forward", c_int, [ctypes.POINTER(RasterFwdArgs), c_void_p]),
     ("r3dg_raster_backward", c_int, [ctypes.POINTER(RasterBwdArgs), c_void_p]),
     ("r3dg_sh_grad_from_factors", c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
+    ("r3dg_exchange_p2p", c_int, [ctypes.POINTER(ExchangeArgs), c_void_p]),
     ("r3dg_mark_visible", c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("r3dg_bvh_build_tmp_bytes", c_size_t, [c_int]),
     ("r3dg_bvh_trace_tmp_bytes", c_size_t, [c_int]),

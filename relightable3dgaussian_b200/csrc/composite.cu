@@ -71,9 +71,9 @@ __global__ void __launch_bounds__(256) block_mask_kernel(int gx, const uint2* __
 //
 // Per warp (one 8x4 pixel block): the tile's block pre-filter mask bytes are streamed 128 instances at a time and the
 // positions whose bit for THIS block is set are compacted into a circular queue (warp scan); batches of 32 queued
-// entries are then fetched (id -> packed record, registers, one batch ahead) and staged in the warp's shared-memory
-// slab.  Each lane applies the exact-conservative ellipse / rectangle test to ITS OWN staged entry (one evaluation per
-// entry instead of one per (entry, warp-iteration)); a ballot yields the bitmap of entries worth compositing.
+// entries are then fetched (id -> packed record, registers, one batch ahead), staged in the warp's shared-memory slab
+// and composited.  (Measured, profiles/r02_ncu_composite_fwd.md: the block-rectangle pre-filter passes only 4% more
+// entries than the exact ellipse / rectangle test of round 1, so no second test is applied.)
 template <int NG, int NW, int MINB>
 __global__ void __launch_bounds__(32 * NW, MINB) composite_fwd_kernel(const CompositeFwdParams p) {
     constexpr int RG = 2 + NG;                       // float4 groups per record
@@ -149,7 +149,6 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_fwd_kernel(const Comp
         sId[warp][lane] = id_cur;
 #pragma unroll
         for (int g = 0; g < RG; ++g) sRec[warp][g][lane] = r[g];
-        uint32_t word = __ballot_sync(0xffffffffu, lane < n && touch_block(r[0], r[1], (float)bx0, (float)by0));
         const int h0 = qhead;
         qhead = (qhead + n) & (R3DG_QCAP - 1);
         qcount -= n;
@@ -163,9 +162,9 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_fwd_kernel(const Comp
         }
         uint32_t cw = 0u;                                               // bit j: entry j was composited by some pixel
         int last_j = -1;                                                // this pixel's last accepted entry of the batch
-        while (word) {
-            const int j = __ffs(word) - 1;
-            word &= word - 1;
+        int my_wsum = 0;                                                // lane j keeps the warp's weight sum of entry j
+#pragma unroll 1
+        for (int j = 0; j < n; ++j) {
             const float4 a = sRec[warp][0][j];
             const float4 b = sRec[warp][1][j];
             const float dx = sub_(a.x, pxf), dy = sub_(a.y, pyf);
@@ -194,15 +193,16 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_fwd_kernel(const Comp
             }
             if (__any_sync(0xffffffffu, valid)) {
                 cw |= 1u << j;
-                // out_weights[id] += sum over the warp's pixels of w: one integer REDUX instead of a 5-step float
-                // shuffle tree (w in [0,1) in 2^-24 fixed point: error <= 1e-6 per warp, far below the reference's own
-                // atomic-order noise on this statistic), one atomic per warp.
+                // sum over the warp's pixels of w for out_weights: one integer REDUX instead of a 5-step float shuffle tree
+                // (w in [0,1) in 2^-24 fixed point: error <= 1e-6 per warp, far below the reference's own atomic-order
+                // noise on this statistic); lane j keeps entry j's sum, ONE atomic instruction per batch adds them
                 const int wsum = __reduce_add_sync(0xffffffffu, valid ? __float2int_rn(w * 16777216.0f) : 0);
-                if (lane == 0 && wsum != 0) atomicAdd(&p.out_weights[sId[warp][j]], (float)wsum * (1.0f / 16777216.0f));
+                if (lane == j) my_wsum = wsum;
             }
             if (__all_sync(0xffffffffu, done)) { all_done = true; break; }
         }
         if (last_j >= 0) last_contributor = q[(h0 + last_j) & (R3DG_QCAP - 1)] + 1u;     // 1-based position in the tile list
+        if (my_wsum != 0) atomicAdd(&p.out_weights[sId[warp][lane]], (float)my_wsum * (1.0f / 16777216.0f));
         // contributor bits for the backward pass: one fire-and-forget atomic per composited entry
         if ((cw >> lane) & 1u) {
             const uint32_t e = lo + mypos;
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(256) surface_normal_kernel(int W, int H, const
 
 // resident CTAs per SM the register allocation is pinned to (ptxas otherwise drifts a few registers above the
 // count that fits one more CTA): by channel groups NG, for the 4-warp CTA (the 8-warp variant is left to ptxas)
-template <int NG> struct FwdOcc { static constexpr int v = NG <= 2 ? 9 : (NG <= 3 ? 8 : (NG <= 5 ? 6 : 4)); };
+template <int NG> struct FwdOcc { static constexpr int v = NG <= 2 ? 8 : (NG <= 3 ? 7 : (NG <= 5 ? 5 : 4)); };
 
 template <int NG>
 static void launch_fwd_ng(const CompositeFwdParams& p, int tiles, cudaStream_t stream) {

@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_bwd_kernel(const Comp
     while (qcount > 0) {
         const int n = min(32, qcount);
         __syncwarp();
-        sId[warp][lane] = id_cur;
+        sId[warp][lane] = id_cur * (uint32_t)p.recf;                   // element offset of the Gaussian's gradient row
 #pragma unroll
         for (int g = 0; g < RG; ++g) sRec[warp][g][lane] = r[g];
         const int h0 = qhead;
@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_bwd_kernel(const Comp
             // branch-free: every lane runs the arithmetic, lanes that did not composite this entry contribute zeros and
             // keep their state (some lane always did — that is what the contributor bit says)
             const float gate = valid ? 1.0f : 0.0f;
-            const float inv = __frcp_rn(1.0f - alpha);                  // 1 - alpha >= 0.01
+            float inv;                                                   // 1 / (1 - alpha), 1 - alpha in [0.01, 1]: one MUFU
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.0f - alpha));
             const float Tn = T * inv;                                   // T before this entry (backward.cu:533)
             const float dchannel_dcolor = gate * alpha * Tn;
             float v0[V0];
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_bwd_kernel(const Comp
             v0[4] = -0.5f * gdx * dx * dL_dG;
             v0[5] = -0.5f * gdx * dy * dL_dG;
             v0[6] = -0.5f * gdy * dy * dL_dG;
-            float* grow = p.grad + (size_t)sId[warp][j] * p.recf;
+            float* grow = p.grad + sId[warp][j];
             const float r0 = reduce_scatter<V0>(v0, lane);
             {
                 constexpr int SH = V0 == 32 ? 0 : 1;            // lanes per component - 1 (log2)

@@ -25,9 +25,16 @@ namespace r3dg {
 
 struct ShxParams {
     int P, D, M, num_views;
-    const float *means3D, *campos, *factors;
+    const float *means3D, *campos;
+    const float* factors[SHX_MAX_VIEWS];       // view v's [P,3] factor rows: local memory (all-gathered) or PEER memory
     float scale;
     float* dL_dsh;
+    // optional second job of the same launch: in-place mean over the ranks of a flat fp32 section that exists at the
+    // same offset in every rank's symmetric buffer (the dense per-Gaussian gradients)
+    int rank, sh_blocks;
+    long long n_dense4;                         // float4 elements of the section (0: no dense job)
+    float* dense_peers[SHX_MAX_VIEWS];          // the section on every rank (peer pointers; [rank] is local)
+    float* dense_mc;                            // multicast (NVLS) address of the section, or nullptr
 };
 
 __device__ __forceinline__ void shx_basis(int D, float x, float y, float z, float* w) {
@@ -52,9 +59,43 @@ __device__ __forceinline__ void shx_basis(int D, float x, float y, float z, floa
     }
 }
 
+// ---- NVLink all-reduce (mean) of a flat section, fused into the exchange launch -------------------------------------
+// Rank r owns the r-th slice.  With a multicast mapping (NVSwitch NVLS) one `multimem.ld_reduce` pulls the 16 bytes
+// from every GPU and adds them INSIDE the switch, one `multimem.st` writes the mean back into every GPU's copy: each
+// link carries every byte once per direction.  Without multicast the slice is summed with peer loads (in rank order)
+// and broadcast with peer stores.  The caller brackets the launch with cross-rank barriers.
+__device__ __forceinline__ void dense_mean_slice(const ShxParams& p, int block, int nblocks) {
+    const long long per = (p.n_dense4 + p.num_views - 1) / p.num_views;
+    const long long lo = min((long long)p.rank * per, p.n_dense4), hi = min(lo + per, p.n_dense4);
+    const float s = p.scale;
+    for (long long i = lo + (long long)block * SHX_THREADS + threadIdx.x; i < hi; i += (long long)nblocks * SHX_THREADS) {
+        float4 v;
+        if (p.dense_mc) {
+            float4* a = reinterpret_cast<float4*>(p.dense_mc) + i;
+            asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a) : "memory");
+            v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+        } else {
+            v = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < p.num_views; ++r) {
+                const float4 t = reinterpret_cast<const float4*>(p.dense_peers[r])[i];
+                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+            }
+            v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+            for (int r = 0; r < p.num_views; ++r) reinterpret_cast<float4*>(p.dense_peers[r])[i] = v;
+        }
+    }
+    __threadfence_system();
+}
+
 __global__ void __launch_bounds__(SHX_THREADS) sh_from_factors_kernel(const ShxParams p) {
     extern __shared__ float sOut[];                       // [3M][SHX_LD]
     __shared__ float sCam[3 * SHX_MAX_VIEWS];
+    if ((int)blockIdx.x >= p.sh_blocks) {                 // the dense-mean job rides in the same launch
+        dense_mean_slice(p, (int)blockIdx.x - p.sh_blocks, (int)gridDim.x - p.sh_blocks);
+        return;
+    }
     for (int i = threadIdx.x; i < 3 * p.num_views; i += SHX_THREADS) sCam[i] = p.campos[i];
     __syncthreads();
     const int block_base = blockIdx.x * SHX_THREADS;
@@ -67,7 +108,7 @@ __global__ void __launch_bounds__(SHX_THREADS) sh_from_factors_kernel(const ShxP
 #pragma unroll
         for (int q = 0; q < 48; ++q) acc[q] = 0.f;
         for (int v = 0; v < p.num_views; ++v) {
-            const float* f = p.factors + ((size_t)v * p.P + idx) * 3;
+            const float* f = p.factors[v] + (size_t)idx * 3;       // peer memory in the P2P exchange: a coalesced 12 B/thread NVLink read
             const float f0 = f[0], f1 = f[1], f2 = f[2];
             if (f0 == 0.f && f1 == 0.f && f2 == 0.f) continue;      // culled in this view (or fully clamped): contributes exact zeros
             const float dox = mx - sCam[3 * v], doy = my - sCam[3 * v + 1], doz = mz - sCam[3 * v + 2];
@@ -112,20 +153,45 @@ extern "C" {
 
 unsigned long long r3dg_shx_launches = 0;      // folded into r3dg_launch_count (api.cu)
 
+static int launch_shx(ShxParams& p, int dense_blocks, cudaStream_t stream) {
+    const size_t smem = (size_t)3 * p.M * SHX_LD * sizeof(float);
+    p.sh_blocks = (p.P + SHX_THREADS - 1) / SHX_THREADS;
+    sh_from_factors_kernel<<<p.sh_blocks + dense_blocks, SHX_THREADS, smem, stream>>>(p);
+    R3DG_CUDA_TRY(cudaGetLastError());
+    ++r3dg_shx_launches;
+    return 0;
+}
+
 int r3dg_sh_grad_from_factors(int P, int D, int M, int num_views, const float* means3D, const float* campos,
                               const float* factors, float scale, float* dL_dsh, r3dg_stream_t stream) {
     if (P < 0 || D < 0 || D > 3 || M < 1 || M > 16 || (D + 1) * (D + 1) > M || num_views < 1) return R3DG_ERR_BAD_ARG;
     if (num_views > SHX_MAX_VIEWS) return R3DG_ERR_UNSUPPORTED;
     if (P == 0) return 0;
     if (!means3D || !campos || !factors || !dL_dsh) return R3DG_ERR_BAD_ARG;
-    ShxParams p;
+    ShxParams p = {};
     p.P = P; p.D = D; p.M = M; p.num_views = num_views;
-    p.means3D = means3D; p.campos = campos; p.factors = factors; p.scale = scale; p.dL_dsh = dL_dsh;
-    const size_t smem = (size_t)3 * M * SHX_LD * sizeof(float);
-    sh_from_factors_kernel<<<(P + SHX_THREADS - 1) / SHX_THREADS, SHX_THREADS, smem, (cudaStream_t)stream>>>(p);
-    R3DG_CUDA_TRY(cudaGetLastError());
-    ++r3dg_shx_launches;
-    return 0;
+    p.means3D = means3D; p.campos = campos; p.scale = scale; p.dL_dsh = dL_dsh;
+    for (int v = 0; v < num_views; ++v) p.factors[v] = factors + (size_t)v * P * 3;
+    return launch_shx(p, 0, (cudaStream_t)stream);
+}
+
+int r3dg_exchange_p2p(const r3dg_exchange_args* a, r3dg_stream_t stream) {
+    if (!a || a->P < 0 || a->D < 0 || a->D > 3 || a->M < 1 || a->M > 16 || (a->D + 1) * (a->D + 1) > a->M) return R3DG_ERR_BAD_ARG;
+    if (a->world < 1 || a->world > SHX_MAX_VIEWS || a->rank < 0 || a->rank >= a->world) return R3DG_ERR_BAD_ARG;
+    if (a->n_dense < 0 || (a->n_dense & 3)) return R3DG_ERR_BAD_ARG;
+    if (a->P == 0 && a->n_dense == 0) return 0;
+    ShxParams p = {};
+    p.P = a->P; p.D = a->D; p.M = a->M; p.num_views = a->world; p.rank = a->rank;
+    p.means3D = a->means3D; p.campos = a->campos; p.scale = 1.0f / (float)a->world; p.dL_dsh = a->dL_dsh;
+    for (int v = 0; v < a->world; ++v) {
+        p.factors[v] = a->factors[v]; p.dense_peers[v] = a->dense[v];
+        if (a->P > 0 && !a->factors[v]) return R3DG_ERR_BAD_ARG;
+        if (a->n_dense > 0 && !a->dense[v]) return R3DG_ERR_BAD_ARG;
+    }
+    p.n_dense4 = a->n_dense / 4; p.dense_mc = a->dense_multicast;
+    // enough CTAs to keep the NVLink pipes full; the SH rebuild blocks run beside them
+    const int dense_blocks = a->n_dense > 0 ? 1184 : 0;
+    return launch_shx(p, dense_blocks, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -115,6 +115,95 @@ class FactoredGradExchange:
         return self.rebuild_sh(means3D, campos_all, degree)
 
 
+class P2PGradExchange:
+    """The exchange step as ONE kernel over NVLink peer memory — no NCCL collective on the data path
+    (csrc/sh_exchange.cu: r3dg_exchange_p2p).  The per-view SH-gradient factors [P,3] and the dense per-Gaussian
+    gradient section (means3D, features, opacity, scales, rotations) live in ONE symmetric buffer that
+    `torch.distributed._symmetric_memory` maps into every rank (allocation / rendezvous / barriers only — the
+    arithmetic and the transfers are ours).  Per step, after this rank's backward wrote into `views`:
+
+        barrier -> [ one launch: rebuild mean_v(dL_dsh_v) with view v's factors loaded straight from rank v's
+                     buffer (P2P loads overlapping the outer-product math)  +  in-switch NVLS all-reduce
+                     (multimem.ld_reduce / multimem.st) of the dense section, slice r by rank r ] -> barrier
+
+    Same interface as FactoredGradExchange (`views`, `grads`, `exchange()`); equal results up to fp32 summation
+    order.  Raises at construction when symmetric memory cannot be set up (callers fall back to the NCCL classes)."""
+
+    def __init__(self, P, S, M, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.P, self.S, self.M = P, S, M
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        shapes = OrderedDict(means3D=(P, 3), features=(P, S), opacity=(P, 1), scales=(P, 3), rotations=(P, 4), sh_factor=(P, 3))
+        sizes = [int(torch.Size(s).numel()) for s in shapes.values()]
+        offs, off = [], 0
+        for n in sizes:
+            offs.append(off)
+            off += (n + 127) // 128 * 128
+        self.n_dense = offs[-1]                                   # the factor section comes last: everything before it is averaged
+        self.flat = symm_mem.empty(max(off, 128), dtype=torch.float32, device=device)
+        self.flat.zero_()
+        self.hdl = symm_mem.rendezvous(self.flat, self.group)
+        self.views = OrderedDict((name, self.flat[o:o + n].view(shape)) for (name, shape), o, n in zip(shapes.items(), offs, sizes))
+        self.factor = self.views["sh_factor"]
+        self.factor_off = offs[-1]
+        self.sh = torch.zeros((P, M, 3), dtype=torch.float32, device=device)
+        self.grads = OrderedDict((k, v) for k, v in self.views.items() if k != "sh_factor")
+        self.grads["sh"] = self.sh
+        self.multicast = int(self.hdl.multicast_ptr) if getattr(self.hdl, "multicast_ptr", 0) else 0
+        self.peer_ptrs = [int(x) for x in self.hdl.buffer_ptrs]
+
+    def bytes(self):
+        """Bytes of this rank's buffer that other ranks read in one step."""
+        return (self.n_dense + self.P * 3) * 4
+
+    def exchange(self, means3D, campos_all, degree, dense=True):
+        from . import _lib
+        import ctypes
+        lib = _lib.load()
+        assert campos_all.shape == (self.world, 3) and campos_all.is_contiguous() and campos_all.dtype == torch.float32
+        assert means3D.is_contiguous() and means3D.dtype == torch.float32 and means3D.shape == (self.P, 3)
+        dev = means3D.device
+        a = _lib.ExchangeArgs()
+        a.P, a.D, a.M, a.world, a.rank = self.P, int(degree), self.M, self.world, self.rank
+        a.means3D, a.campos, a.dL_dsh = means3D.data_ptr(), campos_all.data_ptr(), self.sh.data_ptr()
+        for v in range(self.world):
+            a.factors[v] = self.peer_ptrs[v] + 4 * self.factor_off
+            a.dense[v] = self.peer_ptrs[v]
+        a.n_dense = self.n_dense if dense else 0
+        a.dense_multicast = self.multicast if self.multicast else None
+        self.hdl.barrier(channel=0)                    # every rank's backward has written its factors / dense rows
+        with torch.cuda.device(dev):
+            _lib.check(lib.r3dg_exchange_p2p(ctypes.byref(a), torch.cuda.current_stream(dev).cuda_stream), "exchange_p2p")
+        self.hdl.barrier(channel=1)                    # every rank is done reading / writing everyone's buffers
+        return self.sh
+
+    # the two calls rasterizer.set_grad_exchange makes inside backward (SH only; the leaves are averaged separately)
+    def gather_factors(self, group=None):
+        return None                                    # nothing to gather: the rebuild reads the peers' buffers directly
+
+    def rebuild_sh(self, means3D, campos_all, degree):
+        return self.exchange(means3D, campos_all, degree, dense=False)
+
+
+def _nvls_mean_inplace(flat, hdl, world, rank, multicast, peer_ptrs):
+    """In-place mean over the ranks of a symmetric flat fp32 buffer: barrier, one r3dg_exchange_p2p launch (dense job
+    only), barrier."""
+    from . import _lib
+    import ctypes
+    a = _lib.ExchangeArgs()
+    a.P, a.D, a.M, a.world, a.rank = 0, 0, 1, world, rank
+    n = flat.numel() // 4 * 4
+    for v in range(world):
+        a.dense[v] = peer_ptrs[v]
+    a.n_dense = n
+    a.dense_multicast = multicast if multicast else None
+    hdl.barrier(channel=0)
+    with torch.cuda.device(flat.device):
+        _lib.check(_lib.load().r3dg_exchange_p2p(ctypes.byref(a), torch.cuda.current_stream(flat.device).cuda_stream), "nvls mean")
+    hdl.barrier(channel=1)
+
+
 class LeafGradBucket:
     """Flat fp32 buffer holding the `.grad` of a list of LEAF parameters as views, so that one
     collective averages a whole N-view step at the place where averaging is always valid: the leaf
@@ -126,7 +215,7 @@ class LeafGradBucket:
     Parameters whose gradient is exchanged elsewhere (the SH leaves under `rasterizer.set_grad_exchange`)
     are simply left out of `params`."""
 
-    def __init__(self, params, device=None):
+    def __init__(self, params, device=None, symmetric=False, group=None):
         self.params = [p for p in params]
         device = device if device is not None else self.params[0].device
         sizes = [p.numel() for p in self.params]
@@ -134,7 +223,18 @@ class LeafGradBucket:
         for n in sizes:
             self.offsets.append(off)
             off += (n + 127) // 128 * 128
-        self.flat = torch.zeros(max(off, 1), dtype=torch.float32, device=device)
+        self.hdl = None
+        if symmetric:                       # NVLink path: the buffer is mapped into every rank, the mean is one NVLS kernel
+            import torch.distributed._symmetric_memory as symm_mem
+            group = group if group is not None else dist.group.WORLD
+            self.flat = symm_mem.empty(max(off, 128), dtype=torch.float32, device=device)
+            self.flat.zero_()
+            self.hdl = symm_mem.rendezvous(self.flat, group)
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+            self.multicast = int(self.hdl.multicast_ptr) if getattr(self.hdl, "multicast_ptr", 0) else 0
+            self.peer_ptrs = [int(x) for x in self.hdl.buffer_ptrs]
+        else:
+            self.flat = torch.zeros(max(off, 1), dtype=torch.float32, device=device)
         self.views = [self.flat[o:o + n].view(p.shape) for p, o, n in zip(self.params, self.offsets, sizes)]
         self.attach()
 
@@ -157,6 +257,8 @@ class LeafGradBucket:
             if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
                 v.copy_(p.grad)
                 p.grad = v
+        if self.hdl is not None:
+            return _nvls_mean_inplace(self.flat, self.hdl, self.world, self.rank, self.multicast, self.peer_ptrs)
         if dist.get_backend(group) == "nccl":
             return dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group, async_op=async_op)
         self.flat.mul_(1.0 / dist.get_world_size(group))

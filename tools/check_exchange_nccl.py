@@ -78,10 +78,30 @@ def main():
     chk = fact.sh.view(torch.int32).sum(dtype=torch.int64).reshape(1)
     lo, hi = chk.clone(), chk.clone()
     tdist.all_reduce(lo, op=tdist.ReduceOp.MIN); tdist.all_reduce(hi, op=tdist.ReduceOp.MAX)
+    # ---- the same gradients through the ONE-kernel NVLink exchange (peer loads + NVLS all-reduce) ----------------------
+    p2p_rel, p2p_info = None, "unavailable"
+    try:
+        p2p = rdist.P2PGradExchange(P, S, M, dev)
+        p2p_info = dict(multicast=bool(p2p.multicast))
+    except Exception as e:                                # no symmetric memory on this box / torch build
+        p2p, p2p_info = None, f"unavailable: {type(e).__name__}: {e}"
+    if p2p is not None:
+        fwd_bwd(p2p.views); p2p.exchange(means3D, campos_all, 3)
+        torch.cuda.synchronize()
+        p2p_rel = {k: float((p2p.grads[k].double() - dense.views[k].double()).norm() / (dense.views[k].double().norm() + 1e-30))
+                   for k in ("means3D", "features", "opacity", "scales", "rotations", "sh")}
+        c2 = torch.stack([p2p.sh.view(torch.int32).sum(dtype=torch.int64), p2p.flat[:p2p.n_dense].view(torch.int32).sum(dtype=torch.int64)])
+        lo2, hi2 = c2.clone(), c2.clone()
+        tdist.all_reduce(lo2, op=tdist.ReduceOp.MIN); tdist.all_reduce(hi2, op=tdist.ReduceOp.MAX)
+        p2p_info["identical_on_all_ranks"] = bool((lo2 == hi2).all())
     # ---- timing: exchange only, and the whole step -----------------------------------------------
     t = dict(dense_exchange_ms=timed(dense.allreduce_mean), factored_exchange_ms=timed(lambda: fact.exchange(means3D, campos_all, 3)),
              dense_step_ms=timed(lambda: (fwd_bwd(dense.views), dense.allreduce_mean())),
              factored_step_ms=timed(lambda: (fwd_bwd(fact.views), fact.exchange(means3D, campos_all, 3))))
+    if p2p is not None:
+        t.update(p2p_exchange_ms=timed(lambda: p2p.exchange(means3D, campos_all, 3)),
+                 p2p_step_ms=timed(lambda: (fwd_bwd(p2p.views), p2p.exchange(means3D, campos_all, 3))))
+    t["single_gpu_step_ms"] = timed(lambda: fwd_bwd(dense.views))
     # ---- hardware correctness gate: the N-view step's gradients == the mean of N single-view backward
     # passes of the REFERENCE's own kernels (oracle/_ref), run sequentially on this rank ---------------------------------
     ref_rel = None
@@ -105,9 +125,11 @@ def main():
         ok = all(v < 1e-4 for v in rel.values()) and int(lo) == int(hi)      # atomics: run-to-run summation order in the two backwards
         if ref_rel is not None:
             ok = ok and ref_rel["max_over_ranks"] < 1e-3
+        if p2p_rel is not None:
+            ok = ok and all(v < 1e-4 for v in p2p_rel.values()) and p2p_info["identical_on_all_ranks"]
         print(json.dumps(dict(what="exchange check", world=world, P=P, rel_l2_factored_vs_dense=rel, identical_on_all_ranks=int(lo) == int(hi),
                               dense_bytes=dense.bytes(), factored_bytes_per_rank=fact.bytes(),
-                              rel_l2_vs_mean_of_reference_single_view_backwards=ref_rel, ok=ok, **t)), flush=True)
+                              rel_l2_vs_mean_of_reference_single_view_backwards=ref_rel, rel_l2_p2p_vs_dense=p2p_rel, p2p=p2p_info, ok=ok, **t)), flush=True)
         if not ok:
             sys.exit(1)
     tdist.barrier()
