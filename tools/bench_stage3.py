@@ -14,7 +14,7 @@ import torch.nn.functional as F
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-from helpers import inverse_covariance, shading_case  # noqa: E402
+from helpers import shading_case  # noqa: E402
 from relightable3dgaussian_b200 import raytracer, shading, synth  # noqa: E402
 from oracle import oracle_shading as osh, ref_gpu  # noqa: E402
 
@@ -31,29 +31,26 @@ def timeit(fn, n=3, warm=1):
     return e0.elapsed_time(e1) / n
 
 
-def bvh(P, N):
-    sc = synth.make_scene(P, "shell-v1", 0, 0)
+def bvh(P, N, recipe="shell-v1", ref=True):
+    """LBVH build + the visibility bake (one launch, in-kernel direction sampling) vs the reference's own kernels driven
+    like scene/gaussian_model.py:312-342.  `cube-v1` (random normals inside a cube) exercises the T < 0.9 early exit;
+    `shell-v1` (outward normals on a sphere) never blocks, every ray walks the tree to the end."""
+    sc = synth.make_scene(P, recipe, 0, 0)
     d = lambda t: t.cuda()
     xyz, s, r, op, nrm = d(sc.means3D), d(sc.scales), d(sc.rotations), d(sc.opacities[:, 0].contiguous()), d(sc.normals)
-    icov = inverse_covariance(s, r)
+    icov = raytracer.inverse_covariance(s, r)
     t_build = timeit(lambda: raytracer.RayTracer(xyz, s, r))
+    rt = raytracer.RayTracer(xyz, s, r)
+    t_trace = timeit(lambda: rt.bake_visibility(xyz, icov, op, nrm, N), n=3)
     t_bake = timeit(lambda: raytracer.update_visibility(xyz, s, r, icov, op, nrm, N), n=2)
-    out = dict(what="bvh", P=P, N=N, rays=P * N, ours_build_ms=t_build, ours_bake_ms=t_bake,
-               ours_Mrays_per_s=P * N / t_bake / 1e3)
-    if ref_gpu.bvh_available():
-        t_rbuild = timeit(lambda: ref_gpu.ref_bvh_create(xyz, s, r))
-        nodes, aabbs, _ = ref_gpu.ref_bvh_create(xyz, s, r)
-
-        def ref_bake():
-            chunk = max(1, P // ((N - 1) // 24 + 1))
-            for off in range(0, P, chunk):
-                dirs, _ = raytracer.sample_incident_rays(nrm[off:off + chunk], False, N)
-                ro = xyz[off:off + chunk, None].expand_as(dirs) + dirs * 0.05          # bvh/__init__.py:63
-                ref_gpu.ref_bvh_trace_opacity(nodes, aabbs, ro.contiguous(), dirs, xyz, icov, op, nrm)
-        t_rbake = timeit(ref_bake, n=2)
-        vis_o, _, _ = raytracer.update_visibility(xyz, s, r, icov, op, nrm, N)
-        out.update(ref_build_ms=t_rbuild, ref_bake_ms=t_rbake, bake_speedup=t_rbake / t_bake, build_speedup=t_rbuild / t_build,
-                   blocked_fraction=float((vis_o == 0).float().mean()))
+    vis_o = raytracer.update_visibility(xyz, s, r, icov, op, nrm, N)[0]
+    out = dict(what="bvh", recipe=recipe, P=P, N=N, rays=P * N, ours_build_ms=t_build, ours_trace_ms=t_trace, ours_bake_ms=t_bake,
+               ours_Mrays_per_s=P * N / t_trace / 1e3, blocked_fraction=float((vis_o == 0).float().mean()))
+    if ref and ref_gpu.bvh_available():
+        t_rbake = timeit(lambda: ref_gpu.reference_update_visibility(xyz, s, r, icov, op, nrm, N), n=1, warm=1)
+        rvis = ref_gpu.reference_update_visibility(xyz, s, r, icov, op, nrm, N)[0]
+        flip = float(((vis_o == 0) != (rvis == 0)).float().mean())
+        out.update(ref_bake_ms=t_rbake, ref_Mrays_per_s=P * N / t_rbake / 1e3, bake_speedup=t_rbake / t_bake, flip_rate_vs_reference=flip)
     print(json.dumps(out), flush=True)
 
 
@@ -147,6 +144,10 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["bvh", "shade", "kernels", "adam"]
     if "bvh" in which:
         bvh(300_000, 64)
+        bvh(300_000, 64, "cube-v1")
+        bvh(1_500_000, 32, "cube-v1")
+    if "bvh_fast" in which:                       # ncu target: one configuration, no reference
+        bvh(300_000, 64, "cube-v1", ref=False)
     if "shade" in which:
         shade(300_000, 64)
         shade(1_000_000, 32)
