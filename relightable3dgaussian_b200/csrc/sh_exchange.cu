@@ -107,17 +107,33 @@ __global__ void __launch_bounds__(SHX_THREADS) sh_from_factors_kernel(const ShxP
         float acc[48];
 #pragma unroll
         for (int q = 0; q < 48; ++q) acc[q] = 0.f;
-        for (int v = 0; v < p.num_views; ++v) {
-            const float* f = p.factors[v] + (size_t)idx * 3;       // peer memory in the P2P exchange: a coalesced 12 B/thread NVLink read
-            const float f0 = f[0], f1 = f[1], f2 = f[2];
-            if (f0 == 0.f && f1 == 0.f && f2 == 0.f) continue;      // culled in this view (or fully clamped): contributes exact zeros
-            const float dox = mx - sCam[3 * v], doy = my - sCam[3 * v + 1], doz = mz - sCam[3 * v + 2];
-            const float len = sqrtf(dox * dox + doy * doy + doz * doz);
-            float w[16];
-            shx_basis(p.D, dox / len, doy / len, doz / len, w);
+        // factors of 8 views at a time: all (peer) loads are issued before any is used, so their NVLink latencies overlap
+        for (int v0 = 0; v0 < p.num_views; v0 += 8) {
+            float f[8][3];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                acc[3 * k] += w[k] * f0; acc[3 * k + 1] += w[k] * f1; acc[3 * k + 2] += w[k] * f2;
+            for (int u = 0; u < 8; ++u) {
+                f[u][0] = f[u][1] = f[u][2] = 0.f;
+                if (v0 + u < p.num_views) {
+                    const float* src = p.factors[v0 + u] + (size_t)idx * 3;       // peer memory in the P2P exchange: coalesced 12 B/thread NVLink reads
+                    f[u][0] = src[0]; f[u][1] = src[1]; f[u][2] = src[2];
+                }
+            }
+#pragma unroll 1
+            for (int u = 0; u < 8; ++u) {
+                const int v = v0 + u;
+                float f0 = f[0][0], f1 = f[0][1], f2 = f[0][2];
+#pragma unroll
+                for (int t = 1; t < 8; ++t)
+                    if (u == t) { f0 = f[t][0]; f1 = f[t][1]; f2 = f[t][2]; }       // register select (no local-memory indexing)
+                if (v >= p.num_views || (f0 == 0.f && f1 == 0.f && f2 == 0.f)) continue;   // culled in this view (or fully clamped): exact zeros
+                const float dox = mx - sCam[3 * v], doy = my - sCam[3 * v + 1], doz = mz - sCam[3 * v + 2];
+                const float len = sqrtf(dox * dox + doy * doy + doz * doz);
+                float w[16];
+                shx_basis(p.D, dox / len, doy / len, doz / len, w);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    acc[3 * k] += w[k] * f0; acc[3 * k + 1] += w[k] * f1; acc[3 * k + 2] += w[k] * f2;
+                }
             }
         }
         float* col = sOut + threadIdx.x;

@@ -99,6 +99,12 @@ def main():
              dense_step_ms=timed(lambda: (fwd_bwd(dense.views), dense.allreduce_mean())),
              factored_step_ms=timed(lambda: (fwd_bwd(fact.views), fact.exchange(means3D, campos_all, 3))))
     if p2p is not None:
+        from relightable3dgaussian_b200.dist import _nvls_mean_inplace
+        t.update(p2p_barrier_pair_ms=timed(lambda: (p2p.hdl.barrier(channel=0), p2p.hdl.barrier(channel=1))),
+                 p2p_sh_only_ms=timed(lambda: p2p.exchange(means3D, campos_all, 3, dense=False)),
+                 p2p_dense_only_ms=timed(lambda: _nvls_mean_inplace(p2p.flat[:p2p.n_dense], p2p.hdl, p2p.world, p2p.rank, p2p.multicast, p2p.peer_ptrs)),
+                 nccl_allreduce_dense_rest_ms=timed(fact.dense.allreduce_mean), nccl_allgather_factors_ms=timed(fact.gather_factors),
+                 local_rebuild_ms=timed(lambda: fact.rebuild_sh(means3D, campos_all, 3)))
         t.update(p2p_exchange_ms=timed(lambda: p2p.exchange(means3D, campos_all, 3)),
                  p2p_step_ms=timed(lambda: (fwd_bwd(p2p.views), p2p.exchange(means3D, campos_all, 3))))
     t["single_gpu_step_ms"] = timed(lambda: fwd_bwd(dense.views))
