@@ -247,6 +247,27 @@ int r3dg_unpremultiply_backward(int S, long long HW, const float* feature, const
                                 float* dL_dopacity, r3dg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Densification surgery: stable compaction of the rows of MANY per-Gaussian tensors
+ * by one keep-mask.  Replaces the ~40 `tensor[mask]` boolean-index launches of
+ * `_prune_optimizer` / `prune_points` / `densify_and_prune` (scene/gaussian_model.py:682-729,890-929):
+ *   r3dg_compact_scan  : exclusive prefix sum of keep[P] into tmp, number of kept rows -> *count_host
+ *                        (pinned host int or NULL; copied asynchronously on `stream`);
+ *   r3dg_compact_rows  : dst_k[offset(i)] = src_k[i] for every kept row i of every tensor k, one launch
+ *                        per <= 32 tensors.  row_bytes: a multiple of 4; dst must hold count rows.
+ * ------------------------------------------------------------------------------------------ */
+#define R3DG_COMPACT_MAX 32
+typedef struct r3dg_compact_tensor {
+    const void* src;               /* [P, row_bytes] */
+    void* dst;                     /* [count, row_bytes] */
+    long long row_bytes;
+} r3dg_compact_tensor;
+size_t r3dg_compact_tmp_bytes(int P);
+int r3dg_compact_scan(int P, const uint8_t* keep, void* tmp, size_t tmp_bytes, int* count_host,
+                      r3dg_stream_t stream);
+int r3dg_compact_rows(int P, int num_tensors, const r3dg_compact_tensor* tensors, const uint8_t* keep,
+                      const void* tmp, r3dg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * BRDF shading: fused `rendering_equation` (gaussian_renderer/neilf.py:339-371) + `GGX_specular`
  * (:374-406) + lat-long environment lookup (scene/direct_light_map.py:70-83) + SH incident light.
  * The reference has no extension boundary here (pure PyTorch; its render_equation.cu is dead,

@@ -63,6 +63,10 @@ class ExchangeArgs(ctypes.Structure):
                  ("n_dense", c_ll), ("dense", c_void_p * 64), ("dense_multicast", c_void_p)])
 
 
+class CompactTensor(ctypes.Structure):
+    _fields_ = [("src", c_void_p), ("dst", c_void_p), ("row_bytes", c_ll)]
+
+
 class AdamTensor(ctypes.Structure):
     _fields_ = ([(n, c_void_p) for n in ("param", "grad", "exp_avg", "exp_avg_sq")] +
                 [("n", c_ll), ("step", c_ll)] +
@@ -95,6 +99,9 @@ SYMBOLS = [
     ("r3dg_unpremultiply_backward", c_int, [c_int, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("r3dg_render_equation_forward", c_int, [ctypes.POINTER(ShadeArgs), c_void_p]),
     ("r3dg_render_equation_backward", c_int, [ctypes.POINTER(ShadeArgs), c_void_p]),
+    ("r3dg_compact_tmp_bytes", c_size_t, [c_int]),
+    ("r3dg_compact_scan", c_int, [c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    ("r3dg_compact_rows", c_int, [c_int, c_int, ctypes.POINTER(CompactTensor), c_void_p, c_void_p, c_void_p]),
     ("r3dg_knn_tmp_bytes", c_size_t, [c_int]),
     ("r3dg_knn_dist2", c_int, [c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     ("r3dg_adam_step", c_int, [c_int, ctypes.POINTER(AdamTensor), c_void_p]),

@@ -227,6 +227,19 @@ int r3dg_unpremultiply_backward(int S, long long HW, const float* feature, const
     return launch_unpremultiply_backward(S, HW, feature, opacity, n_contrib, dL_dout, dL_dfeature, dL_dopacity, num_sms(), (cudaStream_t)stream);
 }
 
+size_t r3dg_compact_tmp_bytes(int P) { return compact_tmp_bytes(P < 0 ? 0 : P); }
+int r3dg_compact_scan(int P, const uint8_t* keep, void* tmp, size_t tmp_bytes, int* count_host, r3dg_stream_t stream) {
+    if (P < 0 || !tmp) return R3DG_ERR_BAD_ARG;
+    g_launches += P > 0 ? 3 : 1;
+    return launch_compact_scan(P, keep, tmp, tmp_bytes, count_host, (cudaStream_t)stream);
+}
+int r3dg_compact_rows(int P, int num_tensors, const r3dg_compact_tensor* tensors, const uint8_t* keep, const void* tmp,
+                      r3dg_stream_t stream) {
+    if (P < 0 || num_tensors < 0 || (num_tensors > 0 && !tensors)) return R3DG_ERR_BAD_ARG;
+    g_launches += (P > 0 && num_tensors > 0) ? (num_tensors + R3DG_COMPACT_MAX - 1) / R3DG_COMPACT_MAX : 0;
+    return launch_compact_rows(P, num_tensors, tensors, keep, tmp, num_sms(), (cudaStream_t)stream);
+}
+
 // ---- simple_knn._C.distCUDA2 ----------------------------------------------------------------
 size_t r3dg_knn_tmp_bytes(int P) { return knn_tmp_bytes(P); }
 int r3dg_knn_dist2(int P, const float* points, float* mean_dist2, void* tmp, size_t tmp_bytes, r3dg_stream_t stream) {

@@ -59,6 +59,11 @@ int shade_tune(const char* key, int value, int* previous);
 // adam.cu: one launch per <= 16 parameter tensors
 int launch_adam(int num, const r3dg_adam_tensor* tensors, cudaStream_t stream, int* launches);
 
+size_t compact_tmp_bytes(int P);
+int launch_compact_scan(int P, const uint8_t* keep, void* tmp, size_t tmp_bytes, int* count_host, cudaStream_t stream);
+int launch_compact_rows(int P, int num, const r3dg_compact_tensor* tensors, const uint8_t* keep, const void* tmp,
+                        int num_sms, cudaStream_t stream);
+
 size_t knn_tmp_bytes(int P);
 int launch_knn(int P, const float* points, float* out, void* tmp, size_t tmp_bytes, int num_sms, cudaStream_t stream);
 

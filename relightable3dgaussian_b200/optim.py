@@ -104,3 +104,92 @@ def uninstall():
     if _torch_adam is not None:
         torch.optim.Adam = _torch_adam
         _torch_adam = None
+
+
+# ---------------------------------------------------------------------------------------------
+# Densification surgery (SURVEY.md §8(f)3): the reference's `_prune_optimizer` / `prune_points`
+# (scene/gaussian_model.py:682-729) apply one boolean mask to every per-Gaussian tensor, one
+# `tensor[mask]` launch chain each.  `compact_rows` does the whole set with one scan of the mask and
+# one gather launch (r3dg_compact_scan / r3dg_compact_rows).
+# ---------------------------------------------------------------------------------------------
+_compact_pinned = None
+
+
+def compact_rows(tensors, keep):
+    """[t[keep] for t in tensors] for tensors that share dim 0 (fp32 / int32 / any dtype whose row is a
+    multiple of 4 bytes; other rows fall back to boolean indexing).  One host read-back of the kept
+    count — boolean indexing has the same one."""
+    import ctypes
+    global _compact_pinned
+    lib = _lib.load()
+    keep = keep.reshape(-1)
+    P = keep.shape[0]
+    dev = keep.device
+    if not keep.is_cuda:
+        raise RuntimeError("compact_rows runs on the GPU only (no CPU path)")
+    k8 = keep.to(torch.uint8).contiguous() if keep.dtype != torch.uint8 else keep.contiguous()
+    if keep.dtype == torch.bool:
+        k8 = keep.contiguous().view(torch.uint8)
+    tmp = torch.empty((lib.r3dg_compact_tmp_bytes(P),), dtype=torch.uint8, device=dev)
+    if _compact_pinned is None:
+        _compact_pinned = torch.zeros(1, dtype=torch.int32).pin_memory()
+    stream = torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.r3dg_compact_scan(P, k8.data_ptr(), tmp.data_ptr(), tmp.numel(), _compact_pinned.data_ptr(), stream.cuda_stream),
+                   "compact_scan")
+        stream.synchronize()
+        count = int(_compact_pinned.item())
+        outs, descs, hold = [], [], []
+        for t in tensors:
+            assert t.shape[0] == P, "all tensors must share dim 0 with the mask"
+            row_bytes = (t.numel() // max(P, 1)) * t.element_size() if P > 0 else 0
+            if P == 0 or row_bytes % 4 != 0 or not t.is_cuda:
+                outs.append(t[keep.bool()])
+                continue
+            src = t.detach().contiguous()
+            dst = torch.empty((count,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+            hold.append(src)
+            d = _lib.CompactTensor()
+            d.src, d.dst, d.row_bytes = src.data_ptr(), dst.data_ptr(), row_bytes
+            descs.append(d)
+            outs.append(dst)
+        if descs and count > 0:
+            arr = (_lib.CompactTensor * len(descs))(*descs)
+            _lib.check(lib.r3dg_compact_rows(P, len(descs), arr, k8.data_ptr(), tmp.data_ptr(), stream.cuda_stream), "compact_rows")
+    return outs
+
+
+def prune_optimizer(optimizer, keep, extra=()):
+    """`GaussianModel._prune_optimizer(mask)` (scene/gaussian_model.py:682-700) for every per-Gaussian group at
+    once: parameters and both Adam moments of all groups whose parameter has `keep.shape[0]` rows (+ any `extra`
+    per-Gaussian tensors, e.g. xyz_gradient_accum / denom / max_radii2D of prune_points :702-729) are compacted by ONE
+    launch.  Returns ({group name: new nn.Parameter}, [compacted extras]); optimizer state is re-keyed like the reference."""
+    P = keep.reshape(-1).shape[0]
+    groups = [g for g in optimizer.param_groups if len(g["params"]) == 1 and g["params"][0].dim() > 0 and g["params"][0].shape[0] == P]
+    work, slots = [], []
+    for g in groups:
+        p = g["params"][0]
+        st = optimizer.state.get(p, None)
+        work.append(p.data); slots.append((g, "param"))
+        if st is not None and "exp_avg" in st:
+            work.append(st["exp_avg"]); slots.append((g, "exp_avg"))
+            work.append(st["exp_avg_sq"]); slots.append((g, "exp_avg_sq"))
+    n_model = len(work)
+    work += list(extra)
+    outs = compact_rows(work, keep)
+    new = {}
+    per_group = {}
+    for (g, kind), t in zip(slots, outs[:n_model]):
+        per_group.setdefault(id(g), {"g": g})[kind] = t
+    for rec in per_group.values():
+        g = rec["g"]
+        old = g["params"][0]
+        st = optimizer.state.pop(old, None)
+        newp = torch.nn.Parameter(rec["param"].requires_grad_(True))
+        g["params"][0] = newp
+        if st is not None:
+            if "exp_avg" in rec:
+                st["exp_avg"], st["exp_avg_sq"] = rec["exp_avg"], rec["exp_avg_sq"]
+            optimizer.state[newp] = st
+        new[g.get("name", str(len(new)))] = newp
+    return new, outs[n_model:]

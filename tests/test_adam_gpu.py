@@ -130,3 +130,43 @@ def test_rejects_what_it_does_not_implement_and_skips_missing_grads():
     ref = r.detach().clone().requires_grad_(True); ref.grad = r.grad.clone()
     FusedAdam([r], lr=1e-2).step(); torch.optim.Adam([ref], lr=1e-2).step()
     np.testing.assert_allclose(npy(r), npy(ref), rtol=1e-6, atol=2e-7)
+
+
+def test_fused_compaction_matches_boolean_indexing():
+    """§8(f)3: compact_rows / prune_optimizer == the reference's `tensor[mask]` chain (gaussian_model.py:682-729)."""
+    from relightable3dgaussian_b200 import optim as O
+    g = torch.Generator().manual_seed(0)
+    for P in (1, 7, 2048, 2049, 100_003):
+        keep = (torch.rand(P, generator=g) < 0.6).cuda()
+        shapes = [(3,), (1,), (15, 3), (4,), ()]
+        ts = [torch.randn((P,) + s, generator=g).cuda() for s in shapes] + [torch.randint(0, 100, (P,), generator=g, dtype=torch.int32).cuda()]
+        outs = O.compact_rows(ts, keep)
+        for t, o in zip(ts, outs):
+            assert torch.equal(o, t[keep]), (P, t.shape)
+    # all kept / none kept
+    t = torch.randn(1000, 3).cuda()
+    assert torch.equal(O.compact_rows([t], torch.ones(1000, dtype=torch.bool).cuda())[0], t)
+    assert O.compact_rows([t], torch.zeros(1000, dtype=torch.bool).cuda())[0].shape == (0, 3)
+    # optimiser surgery: same parameters / moments as the reference's per-group loop, FusedAdam keeps stepping
+    P = 5000
+    names = ["xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation"]
+    shapes = [(3,), (1, 3), (15, 3), (1,), (3,), (4,)]
+    params = [torch.nn.Parameter(torch.randn((P,) + s, generator=g).cuda()) for s in shapes]
+    env = torch.nn.Parameter(torch.randn(1, 16, 32, 3).cuda())               # not per-Gaussian: must be left alone
+    opt = O.FusedAdam([{"params": [p], "lr": 1e-3, "name": n} for p, n in zip(params, names)] + [{"params": [env], "lr": 1e-2, "name": "env"}], lr=0.0, eps=1e-15)
+    for p in params + [env]:
+        p.grad = torch.randn_like(p)
+    opt.step()
+    keep = (torch.rand(P, generator=g) < 0.5).cuda()
+    expect = {n: (p.data[keep].clone(), opt.state[p]["exp_avg"][keep].clone(), opt.state[p]["exp_avg_sq"][keep].clone()) for p, n in zip(params, names)}
+    accum = torch.rand(P, 1).cuda()
+    new, extras = O.prune_optimizer(opt, keep, extra=[accum])
+    assert set(new) == set(names) and torch.equal(extras[0], accum[keep])
+    for n in names:
+        p = new[n]
+        assert isinstance(p, torch.nn.Parameter) and torch.equal(p.data, expect[n][0])
+        assert torch.equal(opt.state[p]["exp_avg"], expect[n][1]) and torch.equal(opt.state[p]["exp_avg_sq"], expect[n][2])
+    assert opt.param_groups[-1]["params"][0] is env and env in opt.state
+    for p in list(new.values()) + [env]:
+        p.grad = torch.randn_like(p)
+    opt.step()                                                                  # state shapes are consistent
