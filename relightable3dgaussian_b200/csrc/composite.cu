@@ -18,6 +18,7 @@
 //  * per-pixel arithmetic keeps the association of the reference binary, so n_contrib and the
 //    images are bit-identical to it for identical lists.
 #include <cstdlib>
+#include <cstring>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -74,10 +75,18 @@ __global__ void __launch_bounds__(256) block_mask_kernel(int gx, const uint2* __
 // entries are then fetched (id -> packed record, registers, one batch ahead), staged in the warp's shared-memory slab
 // and composited.  (Measured, profiles/r02_ncu_composite_fwd.md: the block-rectangle pre-filter passes only 4% more
 // entries than the exact ellipse / rectangle test of round 1, so no second test is applied.)
-template <int NG, int NW, int MINB>
+//
+// BULK = false: the next batch's records are prefetched into registers (r[RG]) and stored to a SoA slab.
+// BULK = true : the TMA-unit experiment north_star asks for — every lane issues ONE 1-D bulk copy (cp.async.bulk, SASS
+//   UBLKCP) of its entry's record (recf * 4 bytes, 16-byte aligned) straight into a double-buffered AoS slab; the
+//   warp's mbarrier counts the transaction bytes.  No prefetch registers (12-28 fewer live registers), no staging
+//   stores.  Selected with r3dg_tune("composite_bulk", 1); measured result in profiles/r02_composite_bulk_staging.md.
+template <int NG, int NW, int MINB, bool BULK>
 __global__ void __launch_bounds__(32 * NW, MINB) composite_fwd_kernel(const CompositeFwdParams p) {
     constexpr int RG = 2 + NG;                       // float4 groups per record
-    __shared__ float4 sRec[NW][RG][32];              // this warp's current 32-entry batch, SoA
+    __shared__ __align__(16) float4 sRec[BULK ? 1 : NW][BULK ? 1 : RG][BULK ? 1 : 32];   // this warp's current 32-entry batch, SoA
+    __shared__ __align__(16) float4 sRecB[BULK ? NW : 1][BULK ? 2 : 1][BULK ? 32 : 1][BULK ? RG : 1];   // BULK: [stage][entry][group]
+    __shared__ __align__(8) uint64_t sBar[NW][2];
     __shared__ uint32_t sId[NW][32];
     __shared__ uint32_t sQ[NW][R3DG_QCAP];           // queued list positions (relative to the tile's range)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -130,15 +139,33 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_fwd_kernel(const Comp
     while (qcount < 64 && w_next < w_end) scan_step();
     __syncwarp();
 
-    // software pipeline: records of the next batch live in registers while the current one is composited
+    // software pipeline: records of the next batch are in flight (registers, or bulk copies into the other slab stage)
+    // while the current one is composited
     uint32_t id_cur = 0u;
-    float4 r[RG];
+    float4 r[BULK ? 1 : RG];
+    int stage = 0;
+    unsigned phase0 = 0u, phase1 = 0u;
+    const unsigned rec_bytes = (unsigned)p.recf * 4u;
+    auto issue_bulk = [&](int s_, int nb, uint32_t id) {        // lanes < nb: one bulk copy each into stage s_
+        fence_proxy_async_smem();                               // earlier generic reads of that stage are done (WAR)
+        __syncwarp();
+        if (lane == 0) mbar_arrive_expect_tx(&sBar[warp][s_], (unsigned)nb * rec_bytes);
+        __syncwarp();
+        if (lane < nb) bulk_copy_g2s(&sRecB[warp][s_][lane][0], p.rec + (size_t)id * p.recf, rec_bytes, &sBar[warp][s_]);
+    };
+    if (BULK) {
+        if (lane == 0) { mbar_init(&sBar[warp][0], 1); mbar_init(&sBar[warp][1], 1); fence_proxy_async_smem(); }
+        __syncwarp();
+        if (lane < qcount) id_cur = plist[q[(qhead + lane) & (R3DG_QCAP - 1)]];
+        if (qcount > 0) issue_bulk(0, min(32, qcount), id_cur);
+    } else {
 #pragma unroll
-    for (int g = 0; g < RG; ++g) r[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane < qcount) {
-        id_cur = plist[q[(qhead + lane) & (R3DG_QCAP - 1)]];
+        for (int g = 0; g < RG; ++g) r[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < qcount) {
+            id_cur = plist[q[(qhead + lane) & (R3DG_QCAP - 1)]];
 #pragma unroll
-        for (int g = 0; g < RG; ++g) r[g] = rec4[(size_t)id_cur * rec4n + g];
+            for (int g = 0; g < RG; ++g) r[g] = rec4[(size_t)id_cur * rec4n + g];
+        }
     }
 
     bool all_done = __all_sync(0xffffffffu, done);
@@ -147,16 +174,22 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_fwd_kernel(const Comp
         const uint32_t mypos = q[(qhead + lane) & (R3DG_QCAP - 1)];     // valid for lane < n
         __syncwarp();
         sId[warp][lane] = id_cur;
+        if (!BULK) {
 #pragma unroll
-        for (int g = 0; g < RG; ++g) sRec[warp][g][lane] = r[g];
+            for (int g = 0; g < RG; ++g) sRec[warp][g][lane] = r[g];
+        }
         const int h0 = qhead;
         qhead = (qhead + n) & (R3DG_QCAP - 1);
         qcount -= n;
         while (qcount < 64 && w_next < w_end) scan_step();
         __syncwarp();
         // prefetch: id -> record of the next batch
-        if (lane < qcount) {
-            id_cur = plist[q[(qhead + lane) & (R3DG_QCAP - 1)]];
+        if (lane < qcount) id_cur = plist[q[(qhead + lane) & (R3DG_QCAP - 1)]];
+        if (BULK) {
+            if (qcount > 0) issue_bulk(stage ^ 1, min(32, qcount), id_cur);
+            mbar_wait(&sBar[warp][stage], stage ? phase1 : phase0);      // the current batch has landed
+            if (stage) phase1 ^= 1u; else phase0 ^= 1u;
+        } else if (lane < qcount) {
 #pragma unroll
             for (int g = 0; g < RG; ++g) r[g] = rec4[(size_t)id_cur * rec4n + g];
         }
@@ -165,8 +198,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_fwd_kernel(const Comp
         int my_wsum = 0;                                                // lane j keeps the warp's weight sum of entry j
 #pragma unroll 1
         for (int j = 0; j < n; ++j) {
-            const float4 a = sRec[warp][0][j];
-            const float4 b = sRec[warp][1][j];
+            const float4 a = BULK ? sRecB[warp][stage][j][0] : sRec[warp][0][j];
+            const float4 b = BULK ? sRecB[warp][stage][j][1] : sRec[warp][1][j];
             const float dx = sub_(a.x, pxf), dy = sub_(a.y, pyf);
             // power = -0.5f*(ca*dx*dx + cc*dy*dy) - cb*dx*dy  (forward.cu:344) as compiled
             const float qd = fma_(dx, mul_(dx, a.z), mul_(dy, mul_(dy, b.x)));
@@ -180,7 +213,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_fwd_kernel(const Comp
                 w = mul_(T, alpha);
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
-                    const float4 c = sRec[warp][2 + g][j];
+                    const float4 c = BULK ? sRecB[warp][stage][j][2 + g] : sRec[warp][2 + g][j];
                     C[4 * g + 0] = fma_(w, c.x, C[4 * g + 0]);
                     C[4 * g + 1] = fma_(w, c.y, C[4 * g + 1]);
                     C[4 * g + 2] = fma_(w, c.z, C[4 * g + 2]);
@@ -203,6 +236,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_fwd_kernel(const Comp
         }
         if (last_j >= 0) last_contributor = q[(h0 + last_j) & (R3DG_QCAP - 1)] + 1u;     // 1-based position in the tile list
         if (my_wsum != 0) atomicAdd(&p.out_weights[sId[warp][lane]], (float)my_wsum * (1.0f / 16777216.0f));
+        stage ^= 1;
         // contributor bits for the backward pass: one fire-and-forget atomic per composited entry
         if ((cw >> lane) & 1u) {
             const uint32_t e = lo + mypos;
@@ -277,9 +311,21 @@ __global__ void __launch_bounds__(256) surface_normal_kernel(int W, int H, const
 // count that fits one more CTA): by channel groups NG, for the 4-warp CTA (the 8-warp variant is left to ptxas)
 template <int NG> struct FwdOcc { static constexpr int v = NG <= 2 ? 8 : (NG <= 3 ? 7 : (NG <= 5 ? 5 : 4)); };
 
+int g_composite_bulk = -1;      // r3dg_tune("composite_bulk"): 1 = TMA bulk-copy record staging in the forward compositor
+int composite_tune(const char* key, int value, int* previous) {
+    if (strcmp(key, "composite_bulk") != 0) return R3DG_ERR_BAD_ARG;
+    if (g_composite_bulk < 0) { const char* e = getenv("R3DG_COMPOSITE_BULK"); g_composite_bulk = (e && atoi(e) == 1) ? 1 : 0; }
+    if (previous) *previous = g_composite_bulk;
+    if (value != 0 && value != 1) return R3DG_ERR_BAD_ARG;
+    g_composite_bulk = value;
+    return 0;
+}
 template <int NG>
 static void launch_fwd_ng(const CompositeFwdParams& p, int tiles, cudaStream_t stream) {
-    composite_fwd_kernel<NG, 4, FwdOcc<NG>::v><<<tiles * 2, 128, 0, stream>>>(p);      // two 4-warp CTAs per tile
+    if (g_composite_bulk < 0) { const char* e = getenv("R3DG_COMPOSITE_BULK"); g_composite_bulk = (e && atoi(e) == 1) ? 1 : 0; }
+    // two 4-warp CTAs per tile
+    if (g_composite_bulk == 1 && NG <= 6) composite_fwd_kernel<NG <= 6 ? NG : 1, 4, FwdOcc<NG>::v, true><<<tiles * 2, 128, 0, stream>>>(p);
+    else composite_fwd_kernel<NG, 4, FwdOcc<NG>::v, false><<<tiles * 2, 128, 0, stream>>>(p);
 }
 
 int launch_block_masks(int W, int H, const GeomLayout& gl, const ImgLayout& il, char* geom, char* img, char* bin,

@@ -55,6 +55,7 @@ int launch_unpremultiply_backward(int S, long long HW, const float* feature, con
                                   const float* g, float* d_feature, float* d_opacity, int num_sms, cudaStream_t stream);
 
 int shade_tune(const char* key, int value, int* previous);
+int composite_tune(const char* key, int value, int* previous);
 
 // adam.cu: one launch per <= 16 parameter tensors
 int launch_adam(int num, const r3dg_adam_tensor* tensors, cudaStream_t stream, int* launches);

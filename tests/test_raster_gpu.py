@@ -411,3 +411,32 @@ def test_deferred_count_option(C):
         assert isinstance(out[0], int) and out[0] > 4 * 300 + 4096
     finally:
         rasterizer.set_deferred_count(False)
+
+
+def test_bulk_copy_record_staging_variant_is_bit_identical(C):
+    """r3dg_tune("composite_bulk", 1): the forward compositor stages its records with per-lane TMA bulk copies
+    (cp.async.bulk + mbarrier) instead of the register prefetch — same arithmetic, so identical images and counters."""
+    from relightable3dgaussian_b200 import _lib
+    for path in RASTER_CASES[:2]:
+        g = np.load(path)
+        kw, (P, W, H, S, R) = golden_kwargs(g)
+        a = run_ours(C, **kw)
+        prev = _lib.tune("composite_bulk", 1)
+        try:
+            b = run_ours(C, **kw)
+        finally:
+            _lib.tune("composite_bulk", prev)
+        for n in ("color", "opacity", "depth", "feature", "n_contrib", "normal"):
+            assert torch.equal(a[n], b[n]), n
+        assert (a["weights"] - b["weights"]).abs().max().item() < 1e-5
+    sc, cam = case_inputs(300_000, 800, 800, 16, view=1)
+    kw = oracle_kwargs(sc, cam, torch.tensor([0.0, 0.5, 1.0]))
+    extra = dict(shs=npy(sc.shs), scales=npy(sc.scales), rotations=npy(sc.rotations), features=npy(sc.features))
+    a = run_ours(C, **kw, **extra)
+    prev = _lib.tune("composite_bulk", 1)
+    try:
+        b = run_ours(C, **kw, **extra)
+    finally:
+        _lib.tune("composite_bulk", prev)
+    for n in ("color", "feature", "n_contrib"):
+        assert torch.equal(a[n], b[n]), n
