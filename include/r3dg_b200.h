@@ -75,6 +75,11 @@ typedef struct r3dg_raster_fwd_args {
      * num_rendered > capacity means the binning buffer was too small: outputs are invalid and
      * the call must be repeated with a larger buffer (nothing out of bounds is ever written). */
     int* num_rendered_host;
+    /* optional cudaEvent_t: recorded on `stream` right after the copy into num_rendered_host has been enqueued, which
+     * happens as soon as the instance count exists on the device (after the binning offsets, ~1/4 into the forward) —
+     * a host that waits on this event instead of the stream gets the count while the compositor is still running and
+     * can already enqueue what follows the forward.  NULL: not used. */
+    void* count_ready_event;
 } r3dg_raster_fwd_args;
 
 /* Replaces CudaRasterizer::Rasterizer::forward (rasterizer.h:34-65, rasterizer_impl.cu:199-380)

@@ -172,14 +172,20 @@ def rasterize_gaussians(background, means3D, features, colors, opacity, scales, 
             a.img = imgBuffer.data_ptr(); a.img_bytes = imgBuffer.numel()
             a.binning = binningBuffer.data_ptr(); a.binning_bytes = binningBuffer.numel()
             a.num_rendered_host = pinned.data_ptr()
+            # recorded by the library right after the count's D2H copy — a quarter into the forward, not at its end
+            ev = torch.cuda.Event()
+            ev.record(stream)             # (creates the underlying cudaEvent_t; re-recorded inside the call)
+            a.count_ready_event = ev.cuda_event
             _lib.check(lib.r3dg_raster_forward(ctypes.byref(a), stream.cuda_stream), "rasterize_gaussians")
             if _defer:                    # opt-in: let the host run ahead; the count is resolved later
-                ev = torch.cuda.Event()
-                ev.record(stream)
                 rendered = DeferredCount(ev, pinned, capacity, st, P)
                 st["pending"] = rendered
                 break
-            stream.synchronize()          # the one readback: num_rendered is part of the return tuple
+            if debug:
+                stream.synchronize()
+            else:
+                ev.synchronize()          # the one readback: num_rendered is part of the return tuple.  The host resumes
+                                          # while the compositor still runs and can enqueue the loss / backward behind it
             rendered = int(pinned.item())
             if rendered <= capacity:
                 break

@@ -26,7 +26,7 @@ class RasterFwdArgs(ctypes.Structure):
                                  "out_normal", "out_surface_xyz", "out_weights", "radii",
                                  "n_contrib")] +
         [("geom", c_void_p), ("geom_bytes", c_size_t), ("img", c_void_p), ("img_bytes", c_size_t),
-         ("binning", c_void_p), ("binning_bytes", c_size_t), ("num_rendered_host", c_void_p)])
+         ("binning", c_void_p), ("binning_bytes", c_size_t), ("num_rendered_host", c_void_p), ("count_ready_event", c_void_p)])
 
 
 class RasterBwdArgs(ctypes.Structure):

@@ -71,7 +71,8 @@ int r3dg_raster_forward(const r3dg_raster_fwd_args* a, r3dg_stream_t stream_) {
     if (a->P > 0) {
         if ((rc = launch_projection(*a, gl, stream)) != 0) return rc;
         prof_mark(true, 1, stream);
-        if ((rc = launch_binning(a->P, a->W, a->H, geom, gl, img, il, bin, bl, num_sms(), stream, mark)) != 0) return rc;
+        if ((rc = launch_binning(a->P, a->W, a->H, geom, gl, img, il, bin, bl, num_sms(), stream, mark, a->num_rendered_host,
+                                 a->count_ready_event)) != 0) return rc;
         g_launches += 1 + (1 + R3DG_SORT_MAX_PASSES) + 5;   // project; histogram + radix passes; count, colsum, starts, apply, scatter
     } else {
         R3DG_CUDA_TRY(cudaMemsetAsync(img + il.ranges, 0, (size_t)tiles * 8, stream));
@@ -84,8 +85,10 @@ int r3dg_raster_forward(const r3dg_raster_fwd_args* a, r3dg_stream_t stream_) {
     prof_mark(true, 7, stream);
     g_launches += 2 + (a->P > 0 ? 1 : 0) + (a->computer_pseudo_normal ? 1 : 0);   // tile order, block masks, composite, normals
     if (g_prof.on) g_prof.fwd_calls++;
-    if (a->num_rendered_host)
-        R3DG_CUDA_TRY(cudaMemcpyAsync(a->num_rendered_host, geom + gl.header, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    if (a->P == 0) {      // (P > 0: the count was copied, and the event recorded, as soon as the binning offsets existed)
+        if (a->num_rendered_host) R3DG_CUDA_TRY(cudaMemcpyAsync(a->num_rendered_host, geom + gl.header, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        if (a->count_ready_event) R3DG_CUDA_TRY(cudaEventRecord((cudaEvent_t)a->count_ready_event, stream));
+    }
     if (a->debug) {   // reference CHECK_CUDA semantics (auxiliary.h:166-173): sync and report
         cudaError_t e = cudaStreamSynchronize(stream);
         if (e != cudaSuccess) return -(int)e;

@@ -352,7 +352,8 @@ int launch_rebuild_keys(int T, const void* ranges, const uint32_t* point_list, c
 }
 
 int launch_binning(int P, int W, int H, char* geom, const GeomLayout& gl, char* img, const ImgLayout& il,
-                   char* bin, const BinLayout& bl, int num_sms, cudaStream_t stream, stage_mark_fn mark) {
+                   char* bin, const BinLayout& bl, int num_sms, cudaStream_t stream, stage_mark_fn mark,
+                   int* num_rendered_host, void* count_ready_event) {
     const int gx = (W + R3DG_TILE - 1) / R3DG_TILE, gy = (H + R3DG_TILE - 1) / R3DG_TILE;
     const int T = gx * gy;
     const int CH = bin_chunk_len(P, (size_t)T);
@@ -395,6 +396,9 @@ int launch_binning(int P, int W, int H, char* geom, const GeomLayout& gl, char* 
     mark(3, stream);
     bin_colsum_kernel<<<sgrid, sblock, 0, stream>>>(T, chunks, M, slab_sum);
     bin_starts_kernel<<<1, 1024, 0, stream>>>(T, slabs, slab_sum, ranges, header, bl.capacity);
+    // the instance count exists now: hand it to the host early (the scatter and the compositor are still to run)
+    if (num_rendered_host) R3DG_CUDA_TRY(cudaMemcpyAsync(num_rendered_host, header, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    if (count_ready_event) R3DG_CUDA_TRY(cudaEventRecord((cudaEvent_t)count_ready_event, stream));
     bin_apply_kernel<<<sgrid, sblock, 0, stream>>>(T, chunks, M, slab_sum);
     mark(4, stream);
     bin_scatter_kernel<<<chunks, BIN_SCATTER_THREADS, smem_scatter, stream>>>(P, T, gx, CH, cap, header, va, vb, rects, M,

@@ -430,9 +430,13 @@ __global__ void __launch_bounds__(TRACE_THREADS) bvh_trace_kernel(int P, long lo
             }
         }
         if (!__any_sync(0xffffffffu, has_ray)) break;
-        // ---- a bounded burst of traversal steps, then look for idle lanes again -----------------
+        // ---- a bounded burst of traversal steps, then look for idle lanes again.  The burst ends early as soon as a
+        // quarter of the warp has finished its ray (checked every 4 steps: rays that hit T < 0.9 quickly would otherwise
+        // idle their lanes for the rest of the burst — ncu: 12.5 of 32 lanes active with 93 % blocked rays) ----------
 #pragma unroll 1
-        for (int step = 0; step < 24 && has_ray; ++step) {
+        for (int step = 0; step < 32; ++step) {
+            if (step > 0 && (step & 3) == 0 && __popc(__ballot_sync(0xffffffffu, !has_ray && !exhausted)) >= 8) break;   // 8+ lanes can be refilled
+            if (!has_ray) continue;
             const int node = pop(sp);
             if (node >= 0) {
                 const float4* p = packets + (size_t)node * 4;

@@ -18,7 +18,8 @@ int launch_sort(void* geom_header, char* buf, const SortLayout& sl, long long n,
                 cudaStream_t stream);
 // binning.cu: depth sort + order-preserving tile binning -> point_list, ranges, num_rendered
 int launch_binning(int P, int W, int H, char* geom, const GeomLayout& gl, char* img, const ImgLayout& il,
-                   char* bin, const BinLayout& bl, int num_sms, cudaStream_t stream, stage_mark_fn mark);
+                   char* bin, const BinLayout& bl, int num_sms, cudaStream_t stream, stage_mark_fn mark,
+                   int* num_rendered_host, void* count_ready_event);
 int launch_rebuild_keys(int T, const void* ranges, const uint32_t* point_list, const float* rec, int recf,
                         long long limit, uint64_t* keys, cudaStream_t stream);
 int launch_block_masks(int W, int H, const GeomLayout& gl, const ImgLayout& il, char* geom, char* img, char* bin,

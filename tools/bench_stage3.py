@@ -121,6 +121,31 @@ def shade_kernels(P, N):
                               checksum_rel=[abs(x - y) / (abs(y) + 1e-30) for x, y in zip(sig, ref)])), flush=True)
 
 
+def adam_stage2(P):
+    """FusedAdam over the stage-2 parameter groups (114 floats per Gaussian, bench_stage2.make_model)."""
+    from relightable3dgaussian_b200.optim import FusedAdam
+    shapes = [(3,), (3,), (4,), (3,), (1,), (1, 3), (15, 3), (3,), (1,), (1, 3), (15, 3)]
+    ps = [torch.randn((P,) + s, device="cuda").requires_grad_(True) for s in shapes]
+    for q in ps:
+        q.grad = torch.randn_like(q) * 1e-3
+    opt = FusedAdam([{"params": [q], "lr": 1e-3} for q in ps], lr=0.0, eps=1e-15)
+    t = timeit(opt.step, n=10, warm=3)
+    elems = P * 114
+    print(json.dumps(dict(what="adam step (stage-2 groups)", P=P, elems=elems, ours_ms=t, ours_GBps=elems * 28 / t / 1e6)), flush=True)
+
+
+def shade_once(P, N):
+    """One fused rendering_equation forward + backward (ncu target)."""
+    c = {k: v.cuda() for k, v in shading_case(P, N, 16, seed=2).items()}
+    leaves = {k: c[k].clone().requires_grad_(True) for k in ("base_color", "roughness", "viewdirs", "incidents")}
+    env_raw = c["env_raw"].clone().requires_grad_(True)
+    for _ in range(2):
+        pbr, ex = shading.rendering_equation(leaves["base_color"], leaves["roughness"], c["normals"], leaves["viewdirs"],
+                                             leaves["incidents"], Light(env_raw), c["visibility"], c["incident_dirs"], c["incident_areas"])
+        ((pbr * c["cot_pbr"]).sum() + (ex["diffuse_light"] * c["cot_diffuse"]).sum()).backward()
+    torch.cuda.synchronize()
+
+
 def adam(P):
     """Fused optimiser step over the reference's stage-1 parameter groups (62 floats per Gaussian)
     vs torch.optim.Adam (foreach) and torch's own fused implementation."""
@@ -157,3 +182,7 @@ if __name__ == "__main__":
         shade_kernels(100_000, 384)
     if "adam" in which:
         adam(1_000_000)
+    if "adam2" in which:
+        adam_stage2(1_500_000)
+    if "shade_once" in which:
+        shade_once(300_000, 64)
