@@ -81,9 +81,15 @@ def make_cameras(cfg, dev):
     return cams, camd
 
 
-def neilf_features(m, cd, brdf, extra, vis_mean):
-    """neilf.py:110-118 (training branch): depth, depth^2, brdf, normal, base_color, roughness, diffuse, visibility."""
+def neilf_features(m, cd, brdf, extra, vis_mean, pack=None):
+    """neilf.py:110-118 (training branch): depth, depth^2, brdf, normal, base_color, roughness, diffuse, visibility.
+    `pack`: the optional fused operator (rasterizer.pack_features) instead of the PyTorch expression."""
     xyz = m["xyz"]
+    if pack is not None:
+        base_color = torch.sigmoid(m["base_color"]) * 0.77 + 0.03
+        roughness = torch.sigmoid(m["roughness"]) * 0.9 + 0.09
+        nrm = F.normalize(m["normal"], dim=-1)
+        return pack([brdf, nrm, base_color, roughness, extra["diffuse_light"], vis_mean], means3D=xyz, viewmatrix=cd["view"])
     depths = (torch.cat([xyz, torch.ones_like(xyz[:, :1])], dim=-1) @ cd["view"])[:, 2:3]
     base_color = torch.sigmoid(m["base_color"]) * 0.77 + 0.03          # gaussian_model.py base_color_activation
     roughness = torch.sigmoid(m["roughness"]) * 0.9 + 0.09
@@ -113,8 +119,8 @@ def _median_ms(events):
 def run_ours(args, cfg, rank, local, world):
     from relightable3dgaussian_b200 import _lib, dist as rdist, raytracer, shading
     from relightable3dgaussian_b200.optim import FusedAdam
-    from relightable3dgaussian_b200.rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, set_deferred_count, unpremultiply,
-                                                        set_grad_exchange)
+    from relightable3dgaussian_b200.rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, pack_features, set_deferred_count,
+                                                        unpremultiply, set_grad_exchange)
     from bench import ClockSampler, alg_bytes, measured_peak
     import torch.distributed as tdist
     dev = torch.device("cuda", local)
@@ -183,7 +189,7 @@ def run_ours(args, cfg, rank, local, world):
         brdf, extra = shading.rendering_equation(base_color, roughness, nrm.detach(), viewdirs, incidents, light,
                                                  visibility_precompute=vis, incident_dirs_precompute=dirs, incident_areas_precompute=areas)
         mark(1)
-        feats = neilf_features(m, cd, brdf, extra, vis_mean)
+        feats = neilf_features(m, cd, brdf, extra, vis_mean, pack=pack_features)
         rs = GaussianRasterizationSettings(H, W, c.tanfovx, c.tanfovy, c.cx, c.cy, bg, 1.0, cd["view"], cd["proj"], 3, cd["pos"],
                                            False, True, True, False)
         a = activated(m)
@@ -262,7 +268,7 @@ def run_ours(args, cfg, rank, local, world):
         "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"stage-2 neilf training step (BASELINE config #{'5' if world > 1 else '4'} shape): shading N={N} -> 16-channel pack -> raster fwd -> "
-                               f"un-premultiply + L1 -> backward -> FusedAdam; {cfg['recipe']} seed {cfg['seed']}, P={P}, {W}x{H}, {cfg['views']}-camera ring",
+                               f"un-premultiply + L1 -> backward -> FusedAdam (optional fused operators used: pack_features, unpremultiply, FusedAdam); {cfg['recipe']} seed {cfg['seed']}, P={P}, {W}x{H}, {cfg['views']}-camera ring",
                    "P": P, "W": W, "H": H, "S": S2, "N": N, "num_rendered": R, "P_visible": Pv,
                    "parallelism": "single GPU" if world == 1 else (
                        f"view-parallel x{world} ({exchange_kind}): SH gradient rebuilt inside backward from the ranks' factors "

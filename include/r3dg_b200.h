@@ -251,6 +251,22 @@ int r3dg_unpremultiply_backward(int S, long long HW, const float* feature, const
                                 const int32_t* n_contrib, const float* dL_dout, float* dL_dfeature,
                                 float* dL_dopacity, r3dg_stream_t stream);
 
+/* Optional fused feature pack in front of the rasterizer (gaussian_renderer/neilf.py:110-126,
+ * render.py:88-93): features[P,S] = cat([depths, depths^2, src_0, src_1, ...], -1) with
+ * depths = (cat([means3D, 1]) @ viewmatrix)[:, 2] — means3D / viewmatrix NULL: no depth channels.  S must equal
+ * (2 if depth) + sum(width).  Backward: writes every source's gradient slice contiguous (ptr NULL: skipped) and, when
+ * dL_dmeans3D is given, the gradient through the two depth channels. */
+#define R3DG_PACK_MAX 16
+typedef struct r3dg_pack_src {
+    const float* ptr;              /* [P,width] contiguous (backward: destination of the gradient slice) */
+    int width;
+} r3dg_pack_src;
+int r3dg_pack_features_forward(int P, int S, const float* means3D, const float* viewmatrix, int num,
+                               const r3dg_pack_src* srcs, float* out, r3dg_stream_t stream);
+int r3dg_pack_features_backward(int P, int S, const float* means3D, const float* viewmatrix,
+                                const float* dL_dout, int num, const r3dg_pack_src* dsts,
+                                float* dL_dmeans3D, r3dg_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Densification surgery: stable compaction of the rows of MANY per-Gaussian tensors
  * by one keep-mask.  Replaces the ~40 `tensor[mask]` boolean-index launches of

@@ -63,6 +63,10 @@ class ExchangeArgs(ctypes.Structure):
                  ("n_dense", c_ll), ("dense", c_void_p * 64), ("dense_multicast", c_void_p)])
 
 
+class PackSrc(ctypes.Structure):
+    _fields_ = [("ptr", c_void_p), ("width", c_int)]
+
+
 class CompactTensor(ctypes.Structure):
     _fields_ = [("src", c_void_p), ("dst", c_void_p), ("row_bytes", c_ll)]
 
@@ -99,6 +103,8 @@ SYMBOLS = [
     ("r3dg_unpremultiply_backward", c_int, [c_int, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("r3dg_render_equation_forward", c_int, [ctypes.POINTER(ShadeArgs), c_void_p]),
     ("r3dg_render_equation_backward", c_int, [ctypes.POINTER(ShadeArgs), c_void_p]),
+    ("r3dg_pack_features_forward", c_int, [c_int, c_int, c_void_p, c_void_p, c_int, ctypes.POINTER(PackSrc), c_void_p, c_void_p]),
+    ("r3dg_pack_features_backward", c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, ctypes.POINTER(PackSrc), c_void_p, c_void_p]),
     ("r3dg_compact_tmp_bytes", c_size_t, [c_int]),
     ("r3dg_compact_scan", c_int, [c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     ("r3dg_compact_rows", c_int, [c_int, c_int, ctypes.POINTER(CompactTensor), c_void_p, c_void_p, c_void_p]),

@@ -17,7 +17,12 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
 # shading.cu mirrors a chain of separate PyTorch elementwise kernels (each op rounded on its own);
 # without FMA contraction the fused kernel reproduces that rounding instead of a differently
 # (if slightly better) rounded result of an ill-conditioned GGX denominator.
-PER_FILE_FLAGS = {"shading.cu": ["-fmad=false"]}
+# adam.cu: flush-to-zero arithmetic.  Real gradients span the whole fp32 range (g^2 of a barely visible Gaussian is a
+# denormal); IEEE sqrt / division take a slow subroutine for denormal operands, and one such lane stalls its warp:
+# measured 1.33 ms inside the stage-2 step vs 0.70 ms on well-scaled data (profiles/r02_launches_stage2.csv vs
+# r02_stage3_bvh2.jsonl).  With -ftz the results are unchanged for every normal number (torch's own CUDA kernels are
+# compiled the same way).
+PER_FILE_FLAGS = {"shading.cu": ["-fmad=false"], "adam.cu": ["-ftz=true"]}
 
 
 def sources():

@@ -231,6 +231,19 @@ int r3dg_unpremultiply_backward(int S, long long HW, const float* feature, const
     return launch_unpremultiply_backward(S, HW, feature, opacity, n_contrib, dL_dout, dL_dfeature, dL_dopacity, num_sms(), (cudaStream_t)stream);
 }
 
+int r3dg_pack_features_forward(int P, int S, const float* means3D, const float* viewmatrix, int num, const r3dg_pack_src* srcs,
+                               float* out, r3dg_stream_t stream) {
+    if (num > 0 && !srcs) return R3DG_ERR_BAD_ARG;
+    g_launches += P > 0 ? 1 : 0;
+    return launch_pack_features_forward(P, S, means3D, viewmatrix, num, srcs, out, num_sms(), (cudaStream_t)stream);
+}
+int r3dg_pack_features_backward(int P, int S, const float* means3D, const float* viewmatrix, const float* dL_dout, int num,
+                                const r3dg_pack_src* dsts, float* dL_dmeans3D, r3dg_stream_t stream) {
+    if (num > 0 && !dsts) return R3DG_ERR_BAD_ARG;
+    g_launches += P > 0 ? 1 : 0;
+    return launch_pack_features_backward(P, S, means3D, viewmatrix, dL_dout, num, dsts, dL_dmeans3D, num_sms(), (cudaStream_t)stream);
+}
+
 size_t r3dg_compact_tmp_bytes(int P) { return compact_tmp_bytes(P < 0 ? 0 : P); }
 int r3dg_compact_scan(int P, const uint8_t* keep, void* tmp, size_t tmp_bytes, int* count_host, r3dg_stream_t stream) {
     if (P < 0 || !tmp) return R3DG_ERR_BAD_ARG;

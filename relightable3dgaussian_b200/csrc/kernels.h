@@ -55,6 +55,11 @@ int launch_unpremultiply_forward(int S, long long HW, const float* feature, cons
 int launch_unpremultiply_backward(int S, long long HW, const float* feature, const float* opacity, const int32_t* n_contrib,
                                   const float* g, float* d_feature, float* d_opacity, int num_sms, cudaStream_t stream);
 
+int launch_pack_features_forward(int P, int S, const float* means3D, const float* view, int num, const r3dg_pack_src* srcs,
+                                 float* out, int num_sms, cudaStream_t stream);
+int launch_pack_features_backward(int P, int S, const float* means3D, const float* view, const float* g, int num,
+                                  const r3dg_pack_src* dsts, float* d_means3D, int num_sms, cudaStream_t stream);
+
 int shade_tune(const char* key, int value, int* previous);
 int composite_tune(const char* key, int value, int* previous);
 

@@ -254,3 +254,60 @@ def unpremultiply(rendered_feature, rendered_opacity, num_contrib):
     one HBM pass forward and one backward instead of 3 + ~6 PyTorch kernels.  The reference's own files keep
     the PyTorch expression; callers opt in by calling this instead."""
     return _Unpremultiply.apply(rendered_feature, rendered_opacity, num_contrib)
+
+
+class _PackFeatures(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, viewmatrix, *tensors):
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        P = tensors[0].shape[0] if tensors else means3D.shape[0]
+        dev = (tensors[0] if tensors else means3D).device
+        srcs = [t.detach().float().contiguous().view(P, -1) for t in tensors]
+        depth = means3D is not None
+        S = (2 if depth else 0) + sum(t.shape[1] for t in srcs)
+        out = torch.empty((P, S), dtype=torch.float32, device=dev)
+        m = means3D.detach().float().contiguous() if depth else None
+        v = viewmatrix.detach().float().contiguous() if depth else None
+        arr = (_lib.PackSrc * max(len(srcs), 1))()
+        for k, t in enumerate(srcs):
+            arr[k].ptr, arr[k].width = t.data_ptr(), t.shape[1]
+        if P > 0:
+            with torch.cuda.device(dev):
+                _lib.check(lib.r3dg_pack_features_forward(P, S, m.data_ptr() if depth else None, v.data_ptr() if depth else None, len(srcs), arr,
+                                                          out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "pack_features")
+        ctx.meta = (P, S, [tuple(t.shape) for t in tensors], [t.shape[1] for t in srcs], depth)
+        ctx.save_for_backward(*([m, v] if depth else []))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        P, S, shapes, widths, depth = ctx.meta
+        m, v = ctx.saved_tensors if depth else (None, None)
+        dev = g.device
+        g = g.float().contiguous()
+        need = ctx.needs_input_grad
+        outs = [torch.empty((P, w), dtype=torch.float32, device=dev) if need[2 + k] else None for k, w in enumerate(widths)]
+        d_m = torch.empty((P, 3), dtype=torch.float32, device=dev) if depth and need[0] else None
+        arr = (_lib.PackSrc * max(len(widths), 1))()
+        for k, w in enumerate(widths):
+            arr[k].ptr, arr[k].width = (outs[k].data_ptr() if outs[k] is not None else None), w
+        if P > 0:
+            with torch.cuda.device(dev):
+                _lib.check(lib.r3dg_pack_features_backward(P, S, m.data_ptr() if depth else None, v.data_ptr() if depth else None, g.data_ptr(),
+                                                           len(widths), arr, d_m.data_ptr() if d_m is not None else None,
+                                                           torch.cuda.current_stream(dev).cuda_stream), "pack_features backward")
+        return (d_m, None) + tuple(o.view(s) if o is not None else None for o, s in zip(outs, shapes))
+
+
+def pack_features(tensors, means3D=None, viewmatrix=None):
+    """Optional fused form of the feature pack the reference's render functions build in front of
+    the rasterizer (gaussian_renderer/neilf.py:110-126, render.py:88-93):
+        depths = (cat([means3D, 1]) @ viewmatrix)[:, 2:3];  features = cat([depths, depths.square(), *tensors], -1)
+    (without means3D / viewmatrix: a plain fused cat).  One pass forward, one backward that writes every source
+    gradient contiguous.  No gradient flows to `viewmatrix` (a camera constant in the reference)."""
+    return _PackFeatures.apply(means3D, viewmatrix, *tensors)

@@ -78,3 +78,35 @@ def test_deferred_count_overflow_is_repaired_in_backward():
         _C_raster._HEADROOM = old
         set_deferred_count(False)
         _C_raster._state.clear()
+
+
+def test_pack_features_matches_reference_expression():
+    """rasterizer.pack_features == neilf.py:110-118: depths via the homogeneous matmul, squares, 8-tensor cat; gradients
+    of every source and of means3D through the depth channels."""
+    from relightable3dgaussian_b200.rasterizer import pack_features
+    from relightable3dgaussian_b200 import synth
+    g = torch.Generator().manual_seed(1)
+    P = 10_007
+    cam = synth.make_camera(3, 320, 200)
+    view = cam.viewmatrix.cuda()
+    leaf = lambda *s: torch.randn(*s, generator=g).cuda().requires_grad_(True)
+    xyz, brdf, nrm, base, rough, diff, vis = leaf(P, 3), leaf(P, 3), leaf(P, 3), leaf(P, 3), leaf(P, 1), leaf(P, 3), leaf(P, 1)
+    srcs = [brdf, nrm, base, rough, diff, vis]
+    depths = (torch.cat([xyz, torch.ones_like(xyz[:, :1])], dim=-1) @ view)[:, 2:3]
+    ref = torch.cat([depths, depths.square()] + srcs, dim=-1)
+    cot = torch.randn(P, 16, generator=g).cuda()
+    (ref * cot).sum().backward()
+    want = [t.grad.clone() for t in [xyz] + srcs]
+    for t in [xyz] + srcs:
+        t.grad = None
+    out = pack_features(srcs, means3D=xyz, viewmatrix=view)
+    assert out.shape == (P, 16) and (out - ref.detach()).abs().max().item() <= 1e-5 and torch.equal(out[:, 2:], ref.detach()[:, 2:])
+    (out * cot).sum().backward()
+    for t, w in zip([xyz] + srcs, want):
+        assert t.grad is not None and t.grad.is_contiguous() and rel_l2(npy(t.grad), npy(w)) < 1e-6
+    # plain fused cat (no depth channels), one source without grad
+    a, b = leaf(P, 2), torch.randn(P, 5, generator=g).cuda()
+    out = pack_features([a, b])
+    assert torch.equal(out, torch.cat([a, b], -1).detach())
+    out.sum().backward()
+    assert torch.equal(a.grad, torch.ones_like(a))
