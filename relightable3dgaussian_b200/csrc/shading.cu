@@ -125,6 +125,17 @@ __device__ __forceinline__ void stage_incidents(const ShadeArgs& a, int g, float
     __syncwarp();
 }
 
+// 1/x with one MUFU (<= 1 ulp), for the BACKWARD kernel only: its recomputed forward quantities and its gradient
+// arithmetic tolerate a last-bit difference (tests: 1e-4 relative), while the ~19 IEEE divisions per sample cost ~230 of
+// its ~1500 instructions (FCHK + slow-path branch each; profiles/r02_ncu_shade_bwd.md).  The forward kernel keeps the
+// IEEE divisions of the PyTorch expression.
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+#define INV_PI_F 0.318309873342514038f    // float32(1 / float32(np.pi))
+
 struct SampleEval {       // forward quantities of one (Gaussian, direction) pair
     float local_raw[3], glob[3], ndi, fs;
     float w[16];
@@ -133,7 +144,7 @@ struct SampleEval {       // forward quantities of one (Gaussian, direction) pai
     float H[3], hn, NoL, NoV, NoH, VoH, NoL_r, NoV_r, NoH_r, VoH_r, p2, frac0, nom0, nom1, nom2, nom_r, nom;
 };
 
-template <bool SMEM_ENV, bool INC_SMEM>
+template <bool SMEM_ENV, bool INC_SMEM, bool FAST = false>
 __device__ __forceinline__ void eval_sample(const ShadeArgs& a, const GaussianOperands& o, const float* __restrict__ env,
                                             const float* __restrict__ sinc, float dx, float dy, float dz, float vis, SampleEval& e) {
     // ---- environment + local SH light --------------------------------------------------------
@@ -174,10 +185,13 @@ __device__ __forceinline__ void eval_sample(const ShadeArgs& a, const GaussianOp
     e.ndi = fmaxf(o.n[0] * dx + o.n[1] * dy + o.n[2] * dz, 0.f);
     // ---- GGX_specular (neilf.py:374-406) ----------------------------------------------------------
     const float ln = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
-    const float L0 = dx / ln, L1 = dy / ln, L2 = dz / ln;
+    float L0, L1, L2;
+    if (FAST) { const float il = fast_rcp(ln); L0 = dx * il; L1 = dy * il; L2 = dz * il; }
+    else { L0 = dx / ln; L1 = dy / ln; L2 = dz / ln; }
     const float h0 = (L0 + o.V[0]) / 2.0f, h1 = (L1 + o.V[1]) / 2.0f, h2 = (L2 + o.V[2]) / 2.0f;
     e.hn = fmaxf(sqrtf(h0 * h0 + h1 * h1 + h2 * h2), 1e-12f);
-    e.H[0] = h0 / e.hn; e.H[1] = h1 / e.hn; e.H[2] = h2 / e.hn;
+    if (FAST) { const float ih = fast_rcp(e.hn); e.H[0] = h0 * ih; e.H[1] = h1 * ih; e.H[2] = h2 * ih; }
+    else { e.H[0] = h0 / e.hn; e.H[1] = h1 / e.hn; e.H[2] = h2 / e.hn; }
     e.NoL_r = o.Ns[0] * L0 + o.Ns[1] * L1 + o.Ns[2] * L2;
     e.NoV_r = o.Ns[0] * o.V[0] + o.Ns[1] * o.V[1] + o.Ns[2] * o.V[2];
     e.NoH_r = o.Ns[0] * e.H[0] + o.Ns[1] * e.H[1] + o.Ns[2] * e.H[2];
@@ -192,7 +206,7 @@ __device__ __forceinline__ void eval_sample(const ShadeArgs& a, const GaussianOp
     e.nom2 = e.NoL * (1.0f - o.k) + o.k;
     e.nom_r = 4.0f * PI_F * e.nom0 * e.nom0 * e.nom1 * e.nom2;
     e.nom = fminf(fmaxf(e.nom_r, 1e-6f), 4.0f * PI_F);
-    e.fs = e.frac0 * o.a2 / e.nom;
+    e.fs = FAST ? e.frac0 * o.a2 * fast_rcp(e.nom) : e.frac0 * o.a2 / e.nom;
 }
 
 // ---- sub-warp groups ---------------------------------------------------------------------------
@@ -327,7 +341,6 @@ __global__ void __launch_bounds__(SHADE_THREADS, VAR == 0 ? 1 : VAR == 1 ? 3 : (
     constexpr int DINC_FLOATS = VAR == 2 ? 48 * SHADE_THREADS : 0;
     float* s_mem = s_bwd + INC_FLOATS + DINC_FLOATS;
     float* sinc = s_bwd + ((threadIdx.x >> 5) * GPW + (threadIdx.x & 31) / G) * SHADE_INC_STRIDE;
-    float* sdinc = s_bwd + INC_FLOATS + threadIdx.x;  // this lane's accumulator q lives at sdinc[q * SHADE_THREADS]
     constexpr int VP = (48 + G - 1) / G * G;         // SH-gradient row padded to a multiple of G
     constexpr int RQ = VP / G;                       // finished components per lane
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -369,8 +382,9 @@ __global__ void __launch_bounds__(SHADE_THREADS, VAR == 0 ? 1 : VAR == 1 ? 3 : (
 #pragma unroll
         for (int q = 0; q < VP; ++q) dinc[q] = 0.f;
         if (VAR == 2) {
+            float4* acc4 = reinterpret_cast<float4*>(s_bwd + INC_FLOATS) + threadIdx.x;
 #pragma unroll
-            for (int q = 0; q < 48; ++q) sdinc[q * SHADE_THREADS] = 0.f;
+            for (int q = 0; q < 12; ++q) acc4[q * SHADE_THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         const size_t row = (size_t)g * a.N;
         for (int i0 = 0; i0 < a.N; i0 += G) {          // warp-uniform trip count (collectives inside in ENV_TAG mode)
@@ -379,27 +393,37 @@ __global__ void __launch_bounds__(SHADE_THREADS, VAR == 0 ? 1 : VAR == 1 ? 3 : (
             const float dx = a.dirs[3 * (row + i)], dy = a.dirs[3 * (row + i) + 1], dz = a.dirs[3 * (row + i) + 2];
             const float vis = a.visibility[row + i], area = a.areas[row + i];
             SampleEval e;
-            eval_sample<SMEM_ENV, (VAR >= 1)>(a, o, env, sinc, dx, dy, dz, vis, e);
+            eval_sample<SMEM_ENV, (VAR >= 1), true>(a, o, env, sinc, dx, dy, dz, vis, e);
             float dfs = 0.f;
-            float dG[3];
+            float dG[3], dLg[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const float loc = fmaxf(e.local_raw[c], 0.f);
                 const float T = (loc + e.glob[c]) * area * e.ndi;
-                const float fd = o.base[c] / PI_F;
+                const float fd = o.base[c] * INV_PI_F;
                 const float dT = act ? gp[c] * (fd + e.fs) + gs[c] * e.fs + gd[c] : 0.f;
-                if (act) { dbase[c] += gp[c] * T / PI_F; dfs += (gp[c] + gs[c]) * T; }
+                if (act) { dbase[c] += gp[c] * T * INV_PI_F; dfs += (gp[c] + gs[c]) * T; }
                 const float dL = dT * area * e.ndi;
-                if (act && e.local_raw[c] >= 0.f) {                // clamp_min(0) passes the gradient at equality
-                    if (VAR == 2) {
+                dLg[c] = (act && e.local_raw[c] >= 0.f) ? dL : 0.f;  // clamp_min(0) passes the gradient at equality
+                if (VAR != 2 && dLg[c] != 0.f) {
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) sdinc[(3 * k + c) * SHADE_THREADS] = fmaf(dL, e.w[k], sdinc[(3 * k + c) * SHADE_THREADS]);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) dinc[3 * k + c] = fmaf(dL, e.w[k], dinc[3 * k + c]);
-                    }
+                    for (int k = 0; k < 16; ++k) dinc[3 * k + c] = fmaf(dL, e.w[k], dinc[3 * k + c]);
                 }
                 dG[c] = act ? dL * vis : 0.f;                        // -> env texels (grid_sample backward)
+            }
+            if (VAR == 2) {
+                // dinc[3k + c] += dL[c] * w[k]: the lane's 48 accumulators as 12 float4 in shared memory ([12][threads]
+                // 16-byte slots: conflict-free 128-bit accesses) — 12 LDS.128 + 48 FFMA + 12 STS.128 per sample
+                float4* acc4 = reinterpret_cast<float4*>(s_bwd + INC_FLOATS) + threadIdx.x;
+#pragma unroll
+                for (int q = 0; q < 12; ++q) {
+                    float4 v = acc4[q * SHADE_THREADS];
+                    v.x = fmaf(dLg[(4 * q) % 3], e.w[(4 * q) / 3], v.x);
+                    v.y = fmaf(dLg[(4 * q + 1) % 3], e.w[(4 * q + 1) / 3], v.y);
+                    v.z = fmaf(dLg[(4 * q + 2) % 3], e.w[(4 * q + 2) / 3], v.z);
+                    v.w = fmaf(dLg[(4 * q + 3) % 3], e.w[(4 * q + 3) / 3], v.w);
+                    acc4[q * SHADE_THREADS] = v;
+                }
             }
             if (ENV_MODE == ENV_TAG) {
                 const bool any = dG[0] != 0.f || dG[1] != 0.f || dG[2] != 0.f;
@@ -418,8 +442,9 @@ __global__ void __launch_bounds__(SHADE_THREADS, VAR == 0 ? 1 : VAR == 1 ? 3 : (
             }
             if (act) {
                 // ---- GGX backward --------------------------------------------------------------
-                const float dfrac = dfs / e.nom;
-                const float dnom = -dfs * (e.frac0 * o.a2) / (e.nom * e.nom);
+                const float inom = fast_rcp(e.nom);
+                const float dfrac = dfs * inom;
+                const float dnom = -dfs * (e.frac0 * o.a2) * inom * inom;
                 const float dnom_r = (e.nom_r >= 1e-6f && e.nom_r <= 4.0f * PI_F) ? dnom : 0.f;
                 const float dnom0 = dnom_r * 8.0f * PI_F * e.nom0 * e.nom1 * e.nom2;
                 const float dnom1 = dnom_r * 4.0f * PI_F * e.nom0 * e.nom0 * e.nom2;
@@ -436,9 +461,10 @@ __global__ void __launch_bounds__(SHADE_THREADS, VAR == 0 ? 1 : VAR == 1 ? 3 : (
                 float dH[3], hdot = 0.f;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) { dH[c] = dNoH * o.Ns[c] + dVoH * o.V[c]; hdot += e.H[c] * dH[c]; }
+                const float ihn = fast_rcp(e.hn);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const float dHraw = (dH[c] - e.H[c] * hdot) / e.hn;
+                    const float dHraw = (dH[c] - e.H[c] * hdot) * ihn;
                     dV[c] += dNoV * o.Ns[c] + dVoH * e.H[c] + 0.5f * dHraw;
                 }
             }
@@ -449,8 +475,9 @@ __global__ void __launch_bounds__(SHADE_THREADS, VAR == 0 ? 1 : VAR == 1 ? 3 : (
         for (int c = 0; c < 3; ++c) { dbase[c] = group_sum<G>(dbase[c]); dV[c] = group_sum<G>(dV[c]); }
         drough = group_sum<G>(drough);
         if (VAR == 2) {
+            const float4* acc4 = reinterpret_cast<const float4*>(s_bwd + INC_FLOATS) + threadIdx.x;
 #pragma unroll
-            for (int q = 0; q < 48; ++q) dinc[q] = sdinc[q * SHADE_THREADS];
+            for (int q = 0; q < 12; ++q) { const float4 v = acc4[q * SHADE_THREADS]; dinc[4 * q] = v.x; dinc[4 * q + 1] = v.y; dinc[4 * q + 2] = v.z; dinc[4 * q + 3] = v.w; }
         }
         group_reduce_scatter<G, VP>(dinc, sub);        // lane `sub` now owns components [sub*RQ, sub*RQ + RQ)
         if (valid) {
