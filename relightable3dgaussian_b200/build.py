@@ -11,7 +11,7 @@ ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libr3dg_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+         "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC] + os.environ.get("R3DG_NVCC_DEFS", "").split()
 
 
 # shading.cu mirrors a chain of separate PyTorch elementwise kernels (each op rounded on its own);

@@ -33,7 +33,7 @@ struct AdamTensor {
     float* v;
     long long n;
     float step_size;         // lr / bias_correction1
-    float bc2_sqrt;          // sqrt(bias_correction2)
+    float inv_bc2_sqrt;      // 1 / sqrt(bias_correction2)
     float beta1, beta2, one_minus_beta1, one_minus_beta2, eps;
     int vec;                 // all four pointers 16-byte aligned
 };
@@ -48,8 +48,17 @@ struct AdamTable {
 __device__ __forceinline__ void adam_update(const AdamTensor& t, float& p, float g, float& m, float& v) {
     m = __fadd_rn(__fmul_rn(m, t.beta1), __fmul_rn(g, t.one_minus_beta1));          // exp_avg.mul_(beta1).add_(grad, alpha=1-beta1)
     v = __fadd_rn(__fmul_rn(v, t.beta2), __fmul_rn(__fmul_rn(t.one_minus_beta2, g), g));   // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1-beta2)
-    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), t.bc2_sqrt), t.eps);    // (exp_avg_sq.sqrt() / sqrt(bc2)).add_(eps)
-    p = __fadd_rn(p, __fmul_rn(-t.step_size, __fdiv_rn(m, denom)));                // param.addcdiv_(exp_avg, denom, value=-step_size)
+    // denom = (exp_avg_sq.sqrt() / sqrt(bc2)).add_(eps);  param.addcdiv_(exp_avg, denom, value=-step_size).
+    // The two moments above are the exact per-op IEEE chain (bit-identical to torch's CPU / numpy rounding; torch's own
+    // CUDA functors contract mul+add into FMA).  The quotient only scales the UPDATE, so it
+    // uses the one-MUFU forms (sqrt.approx, division by reciprocal: <= 2 ulp of the update, ~1e-7 of a step that is itself
+    // ~lr): IEEE div / sqrt branch to a slow subroutine whenever an operand is zero or denormal, real gradients are
+    // full of exact zeros (Gaussians a view does not see), and one such lane stalls its warp — the kernel ran at 3.6 TB/s
+    // inside the stage-2 step against 6.7 TB/s on dense synthetic gradients (profiles/r02_launches_stage2.csv).
+    float sq;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(v));                      // exact 0 for v == 0, no slow path
+    const float denom = __fadd_rn(__fmul_rn(sq, t.inv_bc2_sqrt), t.eps);
+    p = __fadd_rn(p, __fmul_rn(-t.step_size, __fdividef(m, denom)));
 }
 
 __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(const __grid_constant__ AdamTable tab) {
@@ -105,7 +114,7 @@ int launch_adam(int num, const r3dg_adam_tensor* ts, cudaStream_t stream, int* l
             AdamTensor& t = tab.t[tab.num];
             t.p = s.param; t.g = s.grad; t.m = s.exp_avg; t.v = s.exp_avg_sq; t.n = s.n;
             t.step_size = (float)((double)s.lr / bc1);
-            t.bc2_sqrt = (float)sqrt(bc2);
+            t.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
             t.beta1 = (float)s.beta1; t.beta2 = (float)s.beta2;
             t.one_minus_beta1 = (float)(1.0 - s.beta1); t.one_minus_beta2 = (float)(1.0 - s.beta2);
             t.eps = (float)s.eps;

@@ -309,7 +309,13 @@ __global__ void __launch_bounds__(256) surface_normal_kernel(int W, int H, const
 
 // resident CTAs per SM the register allocation is pinned to (ptxas otherwise drifts a few registers above the
 // count that fits one more CTA): by channel groups NG, for the 4-warp CTA (the 8-warp variant is left to ptxas)
-template <int NG> struct FwdOcc { static constexpr int v = NG <= 2 ? 8 : (NG <= 3 ? 7 : (NG <= 5 ? 5 : 4)); };
+#ifndef R3DG_FWD_OCC2          // resident CTAs per SM the kernels are compiled for, by channel groups (tools/occ_sweep.sh)
+#define R3DG_FWD_OCC2 8
+#endif
+#ifndef R3DG_FWD_OCC5
+#define R3DG_FWD_OCC5 5
+#endif
+template <int NG> struct FwdOcc { static constexpr int v = NG <= 2 ? R3DG_FWD_OCC2 : (NG <= 3 ? 7 : (NG <= 5 ? R3DG_FWD_OCC5 : 4)); };
 
 int g_composite_bulk = -1;      // r3dg_tune("composite_bulk"): 1 = TMA bulk-copy record staging in the forward compositor
 int composite_tune(const char* key, int value, int* previous) {

@@ -245,7 +245,13 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_bwd_kernel(const Comp
     }
 }
 
-template <int NG> struct BwdOcc { static constexpr int v = NG <= 2 ? 6 : (NG <= 3 ? 5 : (NG <= 5 ? 4 : 3)); };
+#ifndef R3DG_BWD_OCC2
+#define R3DG_BWD_OCC2 6
+#endif
+#ifndef R3DG_BWD_OCC5
+#define R3DG_BWD_OCC5 4
+#endif
+template <int NG> struct BwdOcc { static constexpr int v = NG <= 2 ? R3DG_BWD_OCC2 : (NG <= 3 ? 5 : (NG <= 5 ? R3DG_BWD_OCC5 : 3)); };
 template <int NG>
 static void launch_bwd_ng(const CompositeBwdParams& p, int tiles, cudaStream_t stream) {
     composite_bwd_kernel<NG, 4, BwdOcc<NG>::v><<<tiles * 2, 128, 0, stream>>>(p);      // two 4-warp CTAs per tile
