@@ -23,6 +23,8 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
 # r02_stage3_bvh2.jsonl).  With -ftz the results are unchanged for every normal number (torch's own CUDA kernels are
 # compiled the same way).
 PER_FILE_FLAGS = {"shading.cu": ["-fmad=false"], "adam.cu": ["-ftz=true"]}
+if os.environ.get("R3DG_SHADING_FMAD") == "1":      # experiment knob (tools/): let nvcc contract mul+add in shading.cu
+    PER_FILE_FLAGS["shading.cu"] = []
 
 
 def sources():

@@ -144,7 +144,10 @@ struct SampleEval {       // forward quantities of one (Gaussian, direction) pai
     float H[3], hn, NoL, NoV, NoH, VoH, NoL_r, NoV_r, NoH_r, VoH_r, p2, frac0, nom0, nom1, nom2, nom_r, nom;
 };
 
-template <bool SMEM_ENV, bool INC_SMEM, bool FAST = false>
+#ifndef R3DG_SHADE_FWD_FAST        // experiment knob: one-MUFU reciprocals in the FORWARD kernel too (default: IEEE divisions)
+#define R3DG_SHADE_FWD_FAST false
+#endif
+template <bool SMEM_ENV, bool INC_SMEM, bool FAST = R3DG_SHADE_FWD_FAST>
 __device__ __forceinline__ void eval_sample(const ShadeArgs& a, const GaussianOperands& o, const float* __restrict__ env,
                                             const float* __restrict__ sinc, float dx, float dy, float dz, float vis, SampleEval& e) {
     // ---- environment + local SH light --------------------------------------------------------
