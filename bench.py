@@ -38,8 +38,8 @@ sys.path.insert(0, ROOT)
 
 HEADLINE = dict(P=1_000_000, W=800, H=800, S=5, views=8, recipe="shell-v1", seed=0)
 # DRAM bytes per launch of the compositors at the headline config, from ncu --set full (profiles/)
-NCU_TRAFFIC = {"composite_bwd": 98067712 + 7328000, "composite_fwd": 56485632 + 6283776}
-STAGES = ["project", "depth_sort", "bin_count", "bin_offsets", "bin_scatter", "composite_fwd",
+NCU_TRAFFIC = {"composite_bwd": 63916544 + 1808640, "composite_fwd": 48908800 + 5070592}
+STAGES = ["project", "depth_sort", "bin_count", "bin_offsets", "bin_scatter", "composite_fwd",   # bin_scatter includes tile_order + block_mask
           "surface_normal", "composite_bwd", "project_bwd"]
 
 
@@ -351,7 +351,7 @@ def bench_ours(args, cfg, rank, local, world):
             "stage_ms": stage,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(dom) if cfg == HEADLINE else None,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture per launch (profiles/r01_ncu_composite_*_final.md)",
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture per launch (profiles/r02_ncu_composite_*_final.md)",
                          "peak_source": peak_src,
                          "alg_bytes_per_launch": ab[dom],
                          "step_alg_bytes": step_alg, "step_frac_of_peak": step_alg / (ms / args.steps * 1e-3) / 1e9 / peak},
