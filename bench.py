@@ -505,6 +505,10 @@ def main():
         if args.impl == "reference":
             if rank == 0:
                 emit(bench_stage2.run_reference(args, cfg2, rank, local, world))
+            if world > 1:
+                import torch.distributed as tdist
+                tdist.barrier()
+                tdist.destroy_process_group()
             return
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a CUDA GPU: the hot path has no CPU fallback")
@@ -519,6 +523,10 @@ def main():
     if args.impl == "reference":
         if rank == 0:
             emit(bench_reference(args, cfg, rank, local, world))
+        if world > 1:                      # the other ranks do no work; leave the group together
+            import torch.distributed as tdist
+            tdist.barrier()
+            tdist.destroy_process_group()
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA GPU: the rasterizer hot path has no CPU fallback")
