@@ -167,7 +167,7 @@ __device__ __forceinline__ void load_rows_transposed(float* s, const float* __re
 }
 
 __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjParams p) {
-    extern __shared__ float sSH[];                 // [3M][PROJ_THREADS + 1] when SHs are given
+    extern __shared__ __align__(16) float sSH[];   // SH slab ([3M][PROJ_THREADS + 1] transposed, or row-major), later the record slab
     __shared__ float sV[16], sPr[16], sCam[3];
     if (threadIdx.x < 16) { sV[threadIdx.x] = p.viewmatrix[threadIdx.x]; sPr[threadIdx.x] = p.projmatrix[threadIdx.x]; }
     if (threadIdx.x < 3) sCam[threadIdx.x] = p.campos[threadIdx.x];
@@ -306,24 +306,43 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_kernel(const ProjParams 
         p.rects[idx] = alive ? make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)(x1 - x0) | ((uint32_t)(y1 - y0) << 16))
                              : make_uint2(0u, 0u);
     }
-    if (!alive) return;
-    p.brects[idx] = block_rect(pix_x, pix_y, con_a, con_b, con_c, p.opacities[idx]);
-    float4* rec = reinterpret_cast<float4*>(p.rec + (size_t)idx * p.recf);
-    rec[0] = make_float4(pix_x, pix_y, con_a, con_b);
-    rec[1] = make_float4(con_c, p.opacities[idx], tz, __int_as_float(my_radius));
-    // channels {r,g,b,f0..}, zero padded
-    const float* f = p.features + (size_t)idx * p.S;
-    for (int g = 0; g < p.ng; ++g) {
-        float v[4];
+    // ---- packed record row: staged in shared memory (the SH slab is dead by now), written back by ONE TMA bulk store ---
+    // A thread writing its own 64-112 B row straight to global memory issues 4-7 STG.128 whose 32 lanes are 64-112 B
+    // apart: every instruction touches 32 half-used sectors and the kernel was bound by the L1/TEX pipeline (78-87 % of
+    // its peak, profiles/r02_ncu_project_kernel_bulk.md), not by HBM.  The CTA's rows are one contiguous slab; rows of
+    // culled Gaussians are written as zeros (nothing ever reads them: they are in no tile list).
+    const int rec4n = p.recf >> 2;
+    float4* srow = reinterpret_cast<float4*>(sSH) + (size_t)threadIdx.x * rec4n;
+    __syncthreads();                                   // every thread is done with the SH slab
+    if (alive) {
+        const float op = p.opacities[idx];
+        p.brects[idx] = block_rect(pix_x, pix_y, con_a, con_b, con_c, op);
+        srow[0] = make_float4(pix_x, pix_y, con_a, con_b);
+        srow[1] = make_float4(con_c, op, tz, __int_as_float(my_radius));
+        // channels {r,g,b,f0..}, zero padded
+        const float* f = p.features + (size_t)idx * p.S;
+        for (int g = 0; g < p.ng; ++g) {
+            float v[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int c = 4 * g + k;
-            v[k] = c < 3 ? rgb[c] : (c - 3 < p.S ? f[c - 3] : 0.0f);
+            for (int k = 0; k < 4; ++k) {
+                const int c = 4 * g + k;
+                v[k] = c < 3 ? rgb[c] : (c - 3 < p.S ? f[c - 3] : 0.0f);
+            }
+            srow[2 + g] = make_float4(v[0], v[1], v[2], v[3]);
         }
-        rec[2 + g] = make_float4(v[0], v[1], v[2], v[3]);
+        p.radii[idx] = my_radius;
+        p.tiles_touched[idx] = (uint32_t)((y1 - y0) * (x1 - x0));
+    } else if (idx < p.P) {
+        for (int g = 0; g < rec4n; ++g) srow[g] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    p.radii[idx] = my_radius;
-    p.tiles_touched[idx] = (uint32_t)((y1 - y0) * (x1 - x0));
+    fence_proxy_async_smem();                          // this thread's shared-memory stores -> visible to the bulk-copy engine
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int block_base = blockIdx.x * PROJ_THREADS;
+        const int nvalid = min(PROJ_THREADS, p.P - block_base);
+        bulk_copy_s2g(p.rec + (size_t)block_base * p.recf, sSH, (unsigned)nvalid * (unsigned)p.recf * 4u);
+        bulk_wait_read_all();                          // the slab must stay alive until the engine has read it
+    }
 }
 
 // ---- chained (decoupled look-back) inclusive scan of tiles_touched -> point_offsets ----------
@@ -462,7 +481,10 @@ int launch_projection(const r3dg_raster_fwd_args& a, const GeomLayout& gl, cudaS
     p.sort_keys = (uint32_t*)(geom + gl.sort + sl.keys_a);
     p.sort_vals = (uint32_t*)(geom + gl.sort + sl.vals_a);
     p.rects = (uint2*)(geom + gl.rects); p.brects = (uint2*)(geom + gl.brects);
-    const size_t sh_smem = a.shs ? (size_t)3 * a.M * (PROJ_THREADS + 1) * sizeof(float) : 0;
+    // dynamic shared memory: the SH slab (transposed fallback layout is the larger one), reused for the record slab
+    size_t sh_smem = a.shs ? (size_t)3 * a.M * (PROJ_THREADS + 1) * sizeof(float) : 0;
+    const size_t rec_smem = (size_t)PROJ_THREADS * gl.recf * sizeof(float);
+    if (rec_smem > sh_smem) sh_smem = rec_smem;
     project_kernel<<<(a.P + PROJ_THREADS - 1) / PROJ_THREADS, PROJ_THREADS, sh_smem, stream>>>(p);
     R3DG_CUDA_TRY(cudaGetLastError());
     return 0;

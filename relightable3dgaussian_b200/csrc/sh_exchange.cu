@@ -92,13 +92,20 @@ __device__ __forceinline__ void dense_mean_slice(const ShxParams& p, int block, 
 __global__ void __launch_bounds__(SHX_THREADS) sh_from_factors_kernel(const ShxParams p) {
     extern __shared__ float sOut[];                       // [3M][SHX_LD]
     __shared__ float sCam[3 * SHX_MAX_VIEWS];
-    if ((int)blockIdx.x >= p.sh_blocks) {                 // the dense-mean job rides in the same launch
-        dense_mean_slice(p, (int)blockIdx.x - p.sh_blocks, (int)gridDim.x - p.sh_blocks);
-        return;
+    // The dense-mean job rides in the same launch, its CTAs INTERLEAVED with the rebuild CTAs (every `period`-th block)
+    // so that the NVLink-bound reduction and the HBM-write-bound rebuild run side by side instead of one after the other.
+    const int dense_blocks = (int)gridDim.x - p.sh_blocks;
+    int sh_block = (int)blockIdx.x;
+    if (dense_blocks > 0) {
+        const int period = max(1, (int)gridDim.x / dense_blocks);
+        const int b = (int)blockIdx.x;
+        const int q = b / period;                              // dense blocks at b = 0, period, 2 period, ... while q < dense_blocks
+        if (b % period == 0 && q < dense_blocks) { dense_mean_slice(p, q, dense_blocks); return; }
+        sh_block = b - min(dense_blocks, q + 1);               // dense blocks seen so far: indices 0..q (or all of them)
     }
     for (int i = threadIdx.x; i < 3 * p.num_views; i += SHX_THREADS) sCam[i] = p.campos[i];
     __syncthreads();
-    const int block_base = blockIdx.x * SHX_THREADS;
+    const int block_base = sh_block * SHX_THREADS;
     const int idx = block_base + threadIdx.x;
     const int rowf = 3 * p.M;
     const int nvalid = min(SHX_THREADS, p.P - block_base);
