@@ -73,8 +73,7 @@ __global__ void __launch_bounds__(256) block_mask_kernel(int gx, const uint2* __
 // Per warp (one 8x4 pixel block): the tile's block pre-filter mask bytes are streamed 128 instances at a time and the
 // positions whose bit for THIS block is set are compacted into a circular queue (warp scan); batches of 32 queued
 // entries are then fetched (id -> packed record, registers, one batch ahead), staged in the warp's shared-memory slab
-// and composited.  (Measured, profiles/r02_ncu_composite_fwd.md: the block-rectangle pre-filter passes only 4% more
-// entries than the exact ellipse / rectangle test of round 1, so no second test is applied.)
+// and composited after a second, exact per-lane filter (see below).
 //
 // BULK = false: the next batch's records are prefetched into registers (r[RG]) and stored to a SoA slab.
 // BULK = true : the TMA-unit experiment north_star asks for — every lane issues ONE 1-D bulk copy (cp.async.bulk, SASS
@@ -178,6 +177,13 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_fwd_kernel(const Comp
 #pragma unroll
             for (int g = 0; g < RG; ++g) sRec[warp][g][lane] = r[g];
         }
+        // second, exact filter — each lane applies round 1's exact-conservative ellipse / rectangle test to ITS OWN staged
+        // entry (one evaluation per entry): the block rectangle lets through 3.26 M (warp, entry) pairs at the headline
+        // config, the exact test 2.28 M (profiles/r02_ncu_composite_fwd_final.md vs _v2_), and every pair dropped here
+        // saves the ~41-instruction alpha evaluation of the loop below
+        uint32_t word;
+        if (BULK) word = n == 32 ? 0xffffffffu : ((1u << n) - 1u);       // (records are not in registers in this variant)
+        else word = __ballot_sync(0xffffffffu, lane < n && touch_block(r[0], r[1], (float)bx0, (float)by0));
         const int h0 = qhead;
         qhead = (qhead + n) & (R3DG_QCAP - 1);
         qcount -= n;
@@ -196,8 +202,9 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_fwd_kernel(const Comp
         uint32_t cw = 0u;                                               // bit j: entry j was composited by some pixel
         int last_j = -1;                                                // this pixel's last accepted entry of the batch
         int my_wsum = 0;                                                // lane j keeps the warp's weight sum of entry j
-#pragma unroll 1
-        for (int j = 0; j < n; ++j) {
+        while (word) {
+            const int j = __ffs(word) - 1;
+            word &= word - 1;
             const float4 a = BULK ? sRecB[warp][stage][j][0] : sRec[warp][0][j];
             const float4 b = BULK ? sRecB[warp][stage][j][1] : sRec[warp][1][j];
             const float dx = sub_(a.x, pxf), dy = sub_(a.y, pyf);
