@@ -17,50 +17,40 @@ import torch.nn.functional as F
 
 
 def rotation_between_z(vec):
-    """utils/sh_utils.py:36-68: rotation taking +z to `vec` ([...,3] -> [...,3,3]); -I when vec.z + 1 <= 0."""
-    v1, v2 = -vec[..., 1], vec[..., 0]
-    v3 = torch.zeros_like(v1)
-    v11, v22, v33 = v1 * v1, v2 * v2, v3 * v3
-    v12, v13, v23 = v1 * v2, v1 * v3, v2 * v3
-    cos_p_1 = (vec[..., 2] + 1).clamp_min(1e-7)
-    R = torch.zeros(vec.shape[:-1] + (3, 3), dtype=torch.float32, device=vec.device)
-    R[..., 0, 0] = 1 + (-v33 - v22) / cos_p_1
-    R[..., 0, 1] = -v3 + v12 / cos_p_1
-    R[..., 0, 2] = v2 + v13 / cos_p_1
-    R[..., 1, 0] = v3 + v12 / cos_p_1
-    R[..., 1, 1] = 1 + (-v33 - v11) / cos_p_1
-    R[..., 1, 2] = -v1 + v23 / cos_p_1
-    R[..., 2, 0] = -v2 + v13 / cos_p_1
-    R[..., 2, 1] = v1 + v23 / cos_p_1
-    R[..., 2, 2] = 1 + (-v22 - v11) / cos_p_1
-    return torch.where((vec[..., 2] + 1 > 0)[..., None, None], R,
-                       -torch.eye(3, dtype=torch.float32, device=vec.device).expand_as(R))
+    """Rotation taking +z to `vec` ([...,3] -> [...,3,3]); -I when vec.z + 1 <= 0 (utils/sh_utils.py:36-68).
+
+    Rodrigues' formula about the axis (-n.y, n.x, 0).  Because the axis has no z component, the reference's nine
+    expressions collapse exactly in IEEE arithmetic (x + 0 == x, -0 - x == -x, 0 / c == 0), which is the form written
+    here — and in the CUDA kernel (csrc/bvh.cu rotate_from_z); tests/golden/sampling.npz pins the equality bit for bit."""
+    nx, ny, nz = vec.unbind(-1)
+    ax, ay = -ny, nx
+    c = (nz + 1).clamp_min(1e-7)
+    xy = (ax * ay) / c
+    rows = torch.stack([torch.stack([1 + (-(ay * ay)) / c, xy, ay], -1),
+                        torch.stack([xy, 1 + (-(ax * ax)) / c, -ax], -1),
+                        torch.stack([-ay, ax, 1 + (-(ay * ay) - ax * ax) / c], -1)], -2)
+    flip = -torch.eye(3, dtype=torch.float32, device=vec.device).expand_as(rows)
+    return torch.where((nz + 1 > 0)[..., None, None], rows, flip)
 
 
 def fibonacci_sphere_sampling(normals, sample_num, random_rotate=True, phase=None):
-    """utils/graphics_utils.py:9-37.  `phase` replaces the internal torch.rand draw (so that a test can feed
-    the same random numbers to the kernel)."""
-    pre_shape = normals.shape[:-1]
-    if len(pre_shape) > 1:
-        normals = normals.reshape(-1, 3)
-    delta = np.pi * (3.0 - np.sqrt(5.0))
-    idx = torch.arange(sample_num, dtype=torch.float, device=normals.device)[None]
-    z = (1 - 2 * idx / (2 * sample_num - 1)).clamp_min(np.sin(10 / 180 * np.pi))
-    rad = torch.sqrt(1 - z ** 2)
-    theta = delta * idx
+    """Hemisphere directions around `normals` on a Fibonacci spiral (utils/graphics_utils.py:9-37): sample i sits at height
+    z_i = max(1 - 2 i / (2N - 1), sin 10 deg) and azimuth i * pi (3 - sqrt 5) (+ a per-normal random phase when
+    `random_rotate`; `phase` replaces the internal torch.rand draw so a test can feed the kernel the same numbers).
+    Returns (dirs [...,N,3], areas [...,N,1] = 2 pi)."""
+    lead = normals.shape[:-1]
+    n = normals.reshape(-1, 3)
+    i = torch.arange(sample_num, dtype=torch.float, device=n.device)[None]
+    z = (1 - 2 * i / (2 * sample_num - 1)).clamp_min(np.sin(10 / 180 * np.pi))
+    ring = torch.sqrt(1 - z ** 2)
+    azimuth = (np.pi * (3.0 - np.sqrt(5.0))) * i
     if random_rotate:
-        u = torch.rand(*pre_shape, 1, device=normals.device) if phase is None else phase.reshape(-1, 1)
-        theta = u * 2 * np.pi + theta
-    y = torch.cos(theta) * rad
-    x = torch.sin(theta) * rad
-    z_samples = torch.stack([x, y, z.expand_as(y)], dim=-2)
-    incident_dirs = rotation_between_z(normals) @ z_samples
-    incident_dirs = F.normalize(incident_dirs, dim=-2).transpose(-1, -2)
-    incident_areas = torch.ones_like(incident_dirs)[..., 0:1] * 2 * np.pi
-    if len(pre_shape) > 1:
-        incident_dirs = incident_dirs.reshape(*pre_shape, sample_num, 3)
-        incident_areas = incident_areas.reshape(*pre_shape, sample_num, 1)
-    return incident_dirs, incident_areas
+        u = torch.rand(n.shape[0], 1, device=n.device) if phase is None else phase.reshape(-1, 1)
+        azimuth = u * 2 * np.pi + azimuth
+    canonical = torch.stack([torch.sin(azimuth) * ring, torch.cos(azimuth) * ring, z.expand_as(azimuth)], dim=-2)     # [*,3,N]
+    dirs = F.normalize(rotation_between_z(n) @ canonical, dim=-2).transpose(-1, -2)
+    areas = torch.ones_like(dirs)[..., 0:1] * 2 * np.pi
+    return dirs.reshape(*lead, sample_num, 3), areas.reshape(*lead, sample_num, 1)
 
 
 def sample_incident_rays(normals, is_training=False, sample_num=24):
