@@ -79,11 +79,11 @@ int r3dg_raster_forward(const r3dg_raster_fwd_args* a, r3dg_stream_t stream_) {
         for (int i = 1; i <= 4; ++i) prof_mark(true, i, stream);
     }
     if ((rc = launch_tile_order(img + il.ranges, (uint32_t*)(img + il.tile_order), tiles, stream)) != 0) return rc;
-    if (a->P > 0 && !bin_fuses_masks(a->P) && (rc = launch_block_masks(a->W, a->H, gl, il, geom, img, bin, bl, stream)) != 0) return rc;   // else: done by bin_scatter
+    if (a->P > 0 && (rc = launch_block_masks(a->W, a->H, gl, il, geom, img, bin, bl, stream)) != 0) return rc;
     prof_mark(true, 5, stream);
     if ((rc = launch_composite_forward(*a, gl, il, bin, bl, stream, mark)) != 0) return rc;
     prof_mark(true, 7, stream);
-    g_launches += 2 + ((a->P > 0 && !bin_fuses_masks(a->P)) ? 1 : 0) + (a->computer_pseudo_normal ? 1 : 0);   // tile order, (block masks), composite, normals
+    g_launches += 2 + (a->P > 0 ? 1 : 0) + (a->computer_pseudo_normal ? 1 : 0);   // tile order, block masks, composite, normals
     if (g_prof.on) g_prof.fwd_calls++;
     if (a->P == 0) {      // (P > 0: the count was copied, and the event recorded, as soon as the binning offsets existed)
         if (a->num_rendered_host) R3DG_CUDA_TRY(cudaMemcpyAsync(a->num_rendered_host, geom + gl.header, sizeof(int), cudaMemcpyDeviceToHost, stream));

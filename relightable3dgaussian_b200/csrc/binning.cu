@@ -77,11 +77,7 @@ __global__ void __launch_bounds__(256) bin_count_kernel(int P, int T, int gx, in
 __global__ void __launch_bounds__(BIN_SCATTER_THREADS) bin_scatter_kernel(
     int P, int T, int gx, int CH, int cap, const GeomHeader* __restrict__ header, const uint32_t* __restrict__ vals_a,
     const uint32_t* __restrict__ vals_b, const uint2* __restrict__ rects, const uint32_t* __restrict__ M,
-    uint32_t* __restrict__ point_list, long long capacity, const uint2* __restrict__ brects, uint8_t* __restrict__ bmask,
-    uint8_t* __restrict__ cmask) {
-    // brects != nullptr (P < 2^24): the instance's 8-bit block pre-filter mask (common.cuh block_mask_of) is computed here,
-    // where the Gaussian's block rectangle is loaded ONCE per Gaussian, travels in the spare top byte of the staged id and
-    // is written next to the list entry together with the zeroed contributor byte — no separate pass over the instances.
+    uint32_t* __restrict__ point_list, long long capacity) {
     extern __shared__ __align__(16) uint32_t bin_smem[];
     uint32_t* a = bin_smem;                               // [T] counts -> exclusive offsets -> cursors
     const int words = (CH + 31) >> 5;                     // bitmap over the chunk positions, per warp
@@ -165,17 +161,14 @@ __global__ void __launch_bounds__(BIN_SCATTER_THREADS) bin_scatter_kernel(
             uint32_t tile = (r.x >> 16) * (uint32_t)gx + (r.x & 0xffffu), x = 0;
             const uint32_t n = w * h, skip = (uint32_t)gx - w;
             const uint32_t seq = (uint32_t)(j - j0);
-            const uint2 br = brects ? brects[g] : make_uint2(0u, 0u);
-            uint32_t txx = r.x & 0xffffu, tyy = r.x >> 16;
 #pragma unroll 1
             for (uint32_t k = 0; k < n; ++k) {
                 if ((int)tile >= lo && (int)tile < hi) {
                     const uint32_t slot = atomicAdd(&a[tile], 1u) - first;
-                    const uint32_t m = brects ? block_mask_of(br, txx, tyy) : 0u;
-                    stage[slot] = make_uint2(g | (m << 24), (tile << 16) | seq);
+                    stage[slot] = make_uint2(g, (tile << 16) | seq);
                 }
-                ++tile; ++txx;
-                if (++x == w) { x = 0; tile += skip; txx = r.x & 0xffffu; ++tyy; }
+                ++tile;
+                if (++x == w) { x = 0; tile += skip; }
             }
         }
         __syncthreads();
@@ -199,10 +192,7 @@ __global__ void __launch_bounds__(BIN_SCATTER_THREADS) bin_scatter_kernel(
 #pragma unroll 2
             for (uint32_t k = rb; k < re; ++k) rank += ((stage[k].y & 0xffffu) < seq) ? 1u : 0u;
             const long long pos = (long long)row[t] + rank;
-            if (pos < capacity) {
-                if (brects) { point_list[pos] = e.x & 0xffffffu; bmask[pos] = (uint8_t)(e.x >> 24); cmask[pos] = 0; }
-                else point_list[pos] = e.x;
-            }
+            if (pos < capacity) point_list[pos] = e.x;
         }
         // 3b. long runs (depth slices that pile up on few tiles): one warp per run; a bitmap over the
         //     chunk positions turns the rank into a prefix population count
@@ -235,10 +225,7 @@ __global__ void __launch_bounds__(BIN_SCATTER_THREADS) bin_scatter_kernel(
                     const uint32_t sq = e.y & 0xffffu;
                     const uint32_t rank = bp[sq >> 5] + (uint32_t)__popc(bm[sq >> 5] & ((1u << (sq & 31u)) - 1u));
                     const long long pos = (long long)base + rank;
-                    if (pos < capacity) {
-                        if (brects) { point_list[pos] = e.x & 0xffffffu; bmask[pos] = (uint8_t)(e.x >> 24); cmask[pos] = 0; }
-                        else point_list[pos] = e.x;
-                    }
+                    if (pos < capacity) point_list[pos] = e.x;
                 }
                 __syncwarp();
             }
@@ -414,10 +401,8 @@ int launch_binning(int P, int W, int H, char* geom, const GeomLayout& gl, char* 
     if (count_ready_event) R3DG_CUDA_TRY(cudaEventRecord((cudaEvent_t)count_ready_event, stream));
     bin_apply_kernel<<<sgrid, sblock, 0, stream>>>(T, chunks, M, slab_sum);
     mark(4, stream);
-    const bool fused_masks = bin_fuses_masks(P);       // the mask rides in the top byte of the staged Gaussian id
-    bin_scatter_kernel<<<chunks, BIN_SCATTER_THREADS, smem_scatter, stream>>>(
-        P, T, gx, CH, cap, header, va, vb, rects, M, point_list, bl.capacity, fused_masks ? (const uint2*)(geom + gl.brects) : nullptr,
-        (uint8_t*)(bin + bl.bmask), (uint8_t*)(bin + bl.cmask));
+    bin_scatter_kernel<<<chunks, BIN_SCATTER_THREADS, smem_scatter, stream>>>(P, T, gx, CH, cap, header, va, vb, rects, M,
+                                                                               point_list, bl.capacity);
     R3DG_CUDA_TRY(cudaGetLastError());
     return 0;
 }

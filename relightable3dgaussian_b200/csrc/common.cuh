@@ -146,15 +146,6 @@ struct ImgLayout {
     }
 };
 
-// bin_scatter writes the per-instance pre-filter mask itself when the Gaussian id leaves the top byte of the staged word
-// free (P < 2^24); otherwise (or with R3DG_SEPARATE_MASKS=1: tests) a separate pass does it (composite.cu block_mask_kernel).
-inline __host__ bool bin_fuses_masks(int P) {
-#ifndef __CUDA_ARCH__
-    if (const char* e = getenv("R3DG_SEPARATE_MASKS")) { if (atoi(e) == 1) return false; }
-#endif
-    return P < (1 << 24);
-}
-
 // Binning buffer (capacity-sized, speculative): the per-tile depth-sorted Gaussian lists (reference
 // binningState.point_list) plus one byte per instance for each of
 //   bmask: bit b = 8x4 pixel block b of the instance's tile may be touched by the Gaussian (block_mask_kernel,
@@ -341,22 +332,6 @@ __device__ __forceinline__ uint2 block_rect(float gx, float gy, float ca, float 
     // a box entirely left of / above the image maps to an empty range (pixels have coordinates >= 0)
     if (gx + hx < 0.0f || gy + hy < 0.0f) return make_uint2(1u, 0u);
     return make_uint2(blk(gx - hx, 0.125f) | (blk(gx + hx, 0.125f) << 16), blk(gy - hy, 0.25f) | (blk(gy + hy, 0.25f) << 16));
-}
-
-// 8-bit pre-filter mask of one (tile, Gaussian) instance: bit b = block b of tile (tx, ty) (block column 2 tx + (b & 1),
-// block row 4 ty + (b >> 1)) lies inside the Gaussian's block rectangle.
-__device__ __forceinline__ uint32_t block_mask_of(uint2 br, uint32_t tx, uint32_t ty) {
-    const uint32_t bx0 = br.x & 0xffffu, bx1 = br.x >> 16, by0 = br.y & 0xffffu, by1 = br.y >> 16;
-    const uint32_t c0 = 2u * tx, r0 = 4u * ty;
-    uint32_t cols = 0u, rows = 0u;
-    if (bx0 <= c0 && c0 <= bx1) cols |= 1u;
-    if (bx0 <= c0 + 1u && c0 + 1u <= bx1) cols |= 2u;
-#pragma unroll
-    for (uint32_t k = 0; k < 4; ++k)
-        if (by0 <= r0 + k && r0 + k <= by1) rows |= 1u << k;
-    // block b = (row b >> 1, column b & 1): spread the row bits to even positions, combine with the column bits
-    const uint32_t spread = (rows & 1u) | ((rows & 2u) << 1) | ((rows & 4u) << 2) | ((rows & 8u) << 3);
-    return ((cols & 1u) ? spread : 0u) | ((cols & 2u) ? (spread << 1) : 0u);
 }
 
 // The same test for all 8 blocks of a tile at once (block b: x offset 8 * (b & 1), y offset 4 * (b >> 1)), with

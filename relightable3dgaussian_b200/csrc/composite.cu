@@ -41,8 +41,7 @@ struct CompositeFwdParams {
 
 // One thread per (tile, Gaussian) instance: the 8-bit block pre-filter mask of the instance (bit b = block b of the
 // tile intersects the Gaussian's conservative block rectangle, projection.cu / block_rect()) and a zeroed contributor
-// byte.  CTA per tile (heaviest first); reads 4 B + a gathered 8 B, writes 2 B per instance.  Only used when the masks
-// could not be produced by bin_scatter itself (P >= 2^24: no spare bits in the staged id, binning.cu).
+// byte.  CTA per tile (heaviest first); reads 4 B + a gathered 8 B, writes 2 B per instance.
 __global__ void __launch_bounds__(256) block_mask_kernel(int gx, const uint2* __restrict__ ranges,
                                                          const uint32_t* __restrict__ tile_order,
                                                          const uint32_t* __restrict__ point_list,
@@ -50,9 +49,19 @@ __global__ void __launch_bounds__(256) block_mask_kernel(int gx, const uint2* __
                                                          uint8_t* __restrict__ cmask) {
     const int tile = (int)tile_order[blockIdx.x];
     const uint2 range = ranges[tile];
-    const uint32_t tx = (uint32_t)(tile % gx), ty = (uint32_t)(tile / gx);
+    const uint32_t c0 = 2u * (uint32_t)(tile % gx), r0 = 4u * (uint32_t)(tile / gx);   // first block column / row of the tile
     for (uint32_t i = range.x + threadIdx.x; i < range.y; i += 256) {
-        const uint32_t m = block_mask_of(brects[point_list[i]], tx, ty);
+        const uint2 br = brects[point_list[i]];
+        const uint32_t bx0 = br.x & 0xffffu, bx1 = br.x >> 16, by0 = br.y & 0xffffu, by1 = br.y >> 16;
+        uint32_t cols = 0u, rows = 0u;
+        if (bx0 <= c0 && c0 <= bx1) cols |= 1u;
+        if (bx0 <= c0 + 1u && c0 + 1u <= bx1) cols |= 2u;
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k)
+            if (by0 <= r0 + k && r0 + k <= by1) rows |= 1u << k;
+        // block b = (row b >> 1, column b & 1): spread the row bits to even positions, combine with the column bits
+        const uint32_t spread = (rows & 1u) | ((rows & 2u) << 1) | ((rows & 4u) << 2) | ((rows & 8u) << 3);
+        const uint32_t m = ((cols & 1u) ? spread : 0u) | ((cols & 2u) ? (spread << 1) : 0u);
         bmask[i] = (uint8_t)m;
         cmask[i] = 0;
     }

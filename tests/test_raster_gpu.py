@@ -97,21 +97,6 @@ def test_matches_reference_cuda_golden(C, path):
         assert max_rel_above_floor(npy(o["grads"][n]), g["grad_" + n], floor=1e-3) < 1e-2, n
 
 
-def test_separate_block_mask_pass_matches_fused(C, monkeypatch):
-    """P >= 2^24 cannot carry the pre-filter mask in the staged id: the separate block_mask_kernel pass must give the same
-    images (forced here with R3DG_SEPARATE_MASKS=1)."""
-    g = np.load(RASTER_CASES[0])
-    kw, (P, W, H, S, R) = golden_kwargs(g)
-    cots = [g["cot_color"], g["cot_opacity"], g["cot_depth"], g["cot_feature"]]
-    a = run_ours(C, cots=cots, **kw)
-    monkeypatch.setenv("R3DG_SEPARATE_MASKS", "1")
-    b = run_ours(C, cots=cots, **kw)
-    for n in ("color", "opacity", "depth", "feature", "n_contrib"):
-        assert torch.equal(a[n], b[n]), n
-    for n in a["grads"]:
-        assert rel_l2(npy(b["grads"][n]), npy(a["grads"][n])) < 1e-5 or not npy(a["grads"][n]).any(), n
-
-
 def test_binning_multi_window_path(C, monkeypatch):
     """bin_scatter stages a chunk's instances in shared memory; a chunk that does not fit is handled in
     several windows of tiles.  Force a tiny staging area and require the same bit-exact lists."""
