@@ -378,7 +378,8 @@ __global__ void __launch_bounds__(TRACE_THREADS) bvh_trace_kernel(int P, long lo
     auto push = [&](int& sp, int v) {
         if (sp < TRACE_STACK_SH) sStack[sp][tid] = v;
         else if (sp < TRACE_STACK) lStack[sp - TRACE_STACK_SH] = v;
-        else return;                                       // deeper than the reference's own stack (it prints and drops too)
+        else { printf("WARNING TOO BIG\n"); return; }           // the reference's own message (bvh/include/trace.cuh:24-29; it then writes
+                                                           // past its array) — here the push is dropped, nothing out of bounds
         ++sp;
     };
     auto pop = [&](int& sp) {
