@@ -38,7 +38,7 @@ sys.path.insert(0, ROOT)
 
 HEADLINE = dict(P=1_000_000, W=800, H=800, S=5, views=8, recipe="shell-v1", seed=0)
 # DRAM bytes per launch of the compositors at the headline config, from ncu --set full (profiles/)
-NCU_TRAFFIC = {"composite_bwd": 63916544 + 1808640, "composite_fwd": 48908800 + 5070592}
+NCU_TRAFFIC = {"composite_bwd": 63920896 + 1852928, "composite_fwd": 48885504 + 4542976}
 STAGES = ["project", "depth_sort", "bin_count", "bin_offsets", "bin_scatter", "composite_fwd",   # bin_scatter includes tile_order + block_mask
           "surface_normal", "composite_bwd", "project_bwd"]
 
@@ -301,7 +301,7 @@ def bench_ours(args, cfg, rank, local, world):
         loss_host[i % 64:i % 64 + 1].copy_(loss.detach().reshape(1), non_blocking=True)
 
     leaf_bucket = rdist.LeafGradBucket([params[k] for k in (0, 1, 3, 4, 5)], dev, symmetric=exchange_kind == "p2p") if factored else None
-    e_steps = max(3, args.steps // 2)
+    e_steps = max(10, args.steps)
     # (1) the path an UNCHANGED caller of the reference surface gets: synchronous instance count (one host wait per forward,
     #     like the reference's own cudaMemcpy at rasterizer_impl.cu:291).  Its warm-up also teaches the deferred path the counts.
     set_deferred_count(False)
