@@ -301,7 +301,7 @@ def bench_ours(args, cfg, rank, local, world):
         loss_host[i % 64:i % 64 + 1].copy_(loss.detach().reshape(1), non_blocking=True)
 
     leaf_bucket = rdist.LeafGradBucket([params[k] for k in (0, 1, 3, 4, 5)], dev, symmetric=exchange_kind == "p2p") if factored else None
-    e_steps = max(10, args.steps)
+    e_steps = max(50, args.steps)
     # (1) the path an UNCHANGED caller of the reference surface gets: synchronous instance count (one host wait per forward,
     #     like the reference's own cudaMemcpy at rasterizer_impl.cu:291).  Its warm-up also teaches the deferred path the counts.
     set_deferred_count(False)

@@ -131,6 +131,7 @@ int r3dg_tune(const char* key, int value, int* previous) {
     int prev = 0;
     int rc = shade_tune(key, value, &prev);
     if (rc != 0) rc = composite_tune(key, value, &prev);
+    if (rc != 0) rc = composite_bwd_tune(key, value, &prev);
     if (previous) *previous = prev;
     return rc;
 }

@@ -189,6 +189,15 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+#ifdef R3DG_WARP_TIMING
+// Diagnostic build only (tools/warp_timing.py): every compositor warp records its start / end time, the entries it
+// composited and its SM, to study the load balance of the tile-ordered launch.
+struct WarpTiming { unsigned long long t0, t1; unsigned iters, smid; };
+constexpr int R3DG_WT_MAX = 1 << 17;
+__device__ __forceinline__ unsigned long long wt_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned wt_smid() { unsigned v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
+#endif
+
 // ---- TMA-unit bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier (SYNCS) -------------------
 // One instruction moves a contiguous, 16-byte aligned slab global -> shared with no register staging and no
 // per-thread address arithmetic; completion is signalled by transaction bytes on a shared-memory mbarrier.
@@ -255,6 +264,18 @@ __device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf
 __device__ __forceinline__ float mul_(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float add_(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float sub_(float a, float b) { return __fsub_rn(a, b); }
+// c += w * x on the lanes where `on` holds, as predicated FFMAs: no branch and no select, and a lane that is off keeps
+// its accumulators bit for bit even when x is not finite (what the reference's per-thread `continue` guarantees).
+__device__ __forceinline__ void fma4_if(bool on, float w, const float4& x, float& c0, float& c1, float& c2, float& c3) {
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %4, 0;\n\t@q fma.rn.f32 %0, %5, %6, %0;\n\t@q fma.rn.f32 %1, %5, %7, %1;\n\t"
+        "@q fma.rn.f32 %2, %5, %8, %2;\n\t@q fma.rn.f32 %3, %5, %9, %3;\n\t}"
+        : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
+        : "r"((unsigned)on), "f"(w), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w));
+}
+__device__ __forceinline__ void fma_add_if(bool on, float w, float x, float& c, float& sum) {   // c += w * x ; sum += w
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q fma.rn.f32 %0, %3, %4, %0;\n\t@q add.rn.f32 %1, %1, %3;\n\t}"
+        : "+f"(c), "+f"(sum) : "r"((unsigned)on), "f"(w), "f"(x));
+}
 __device__ __forceinline__ float div_(float a, float b) { return __fdiv_rn(a, b); }
 __device__ __forceinline__ float rcp_(float a) { return __frcp_rn(a); }
 __device__ __forceinline__ float sqrt_(float a) { return __fsqrt_rn(a); }

@@ -22,6 +22,15 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#ifndef R3DG_FWD_CTAS          // default resident CTAs per SM of the forward compositor (0 = whatever fits)
+#define R3DG_FWD_CTAS 0
+#endif
+#ifndef R3DG_FWD_ILP           // staged entries whose alpha evaluation is in flight together (composite_fwd_kernel), S <= 5
+#define R3DG_FWD_ILP 4
+#endif
+#ifndef R3DG_FWD_ILP_WIDE      // the same for S > 5 (more accumulators per pixel: registers)
+#define R3DG_FWD_ILP_WIDE 2
+#endif
 namespace r3dg {
 
 struct CompositeFwdParams {
@@ -39,9 +48,30 @@ struct CompositeFwdParams {
     float *out_color, *out_opacity, *out_depth, *out_feature, *out_weights;
 };
 
-// One thread per (tile, Gaussian) instance: the 8-bit block pre-filter mask of the instance (bit b = block b of the
-// tile intersects the Gaussian's conservative block rectangle, projection.cu / block_rect()) and a zeroed contributor
-// byte.  CTA per tile (heaviest first); reads 4 B + a gathered 8 B, writes 2 B per instance.
+#ifdef R3DG_WARP_TIMING
+__device__ WarpTiming g_wt_fwd[R3DG_WT_MAX];
+extern "C" int r3dg_debug_wt_fwd(void* dst, size_t bytes) { return (int)cudaMemcpyFromSymbol(dst, g_wt_fwd, bytes); }
+#endif
+
+// The 8-bit block pre-filter mask of one (tile, Gaussian) instance: bit b = block b of the tile intersects the
+// Gaussian's conservative block rectangle (projection.cu / block_rect()).
+__device__ __forceinline__ uint32_t block_mask_of_rect(uint2 br, uint32_t c0, uint32_t r0) {
+    const uint32_t bx0 = br.x & 0xffffu, bx1 = br.x >> 16, by0 = br.y & 0xffffu, by1 = br.y >> 16;
+    uint32_t cols = 0u, rows = 0u;
+    if (bx0 <= c0 && c0 <= bx1) cols |= 1u;
+    if (bx0 <= c0 + 1u && c0 + 1u <= bx1) cols |= 2u;
+#pragma unroll
+    for (uint32_t k = 0; k < 4; ++k)
+        if (by0 <= r0 + k && r0 + k <= by1) rows |= 1u << k;
+    // block b = (row b >> 1, column b & 1): spread the row bits to even positions, combine with the column bits
+    const uint32_t spread = (rows & 1u) | ((rows & 2u) << 1) | ((rows & 4u) << 2) | ((rows & 8u) << 3);
+    return ((cols & 1u) ? spread : 0u) | ((cols & 2u) ? (spread << 1) : 0u);
+}
+
+// Pre-filter mask byte + zeroed contributor byte for every instance.  CTA per tile (heaviest first).  A thread takes
+// FOUR consecutive instances of the tile's list: one 16-byte load of the ids, four independent 8-byte gathers of the
+// block rectangles (the latency this kernel is bound by), one 4-byte store per mask array.  The ragged ends of the
+// tile's range (it starts and ends anywhere inside a word shared with the neighbouring tiles) are written bytewise.
 __global__ void __launch_bounds__(256) block_mask_kernel(int gx, const uint2* __restrict__ ranges,
                                                          const uint32_t* __restrict__ tile_order,
                                                          const uint32_t* __restrict__ point_list,
@@ -50,20 +80,24 @@ __global__ void __launch_bounds__(256) block_mask_kernel(int gx, const uint2* __
     const int tile = (int)tile_order[blockIdx.x];
     const uint2 range = ranges[tile];
     const uint32_t c0 = 2u * (uint32_t)(tile % gx), r0 = 4u * (uint32_t)(tile / gx);   // first block column / row of the tile
-    for (uint32_t i = range.x + threadIdx.x; i < range.y; i += 256) {
-        const uint2 br = brects[point_list[i]];
-        const uint32_t bx0 = br.x & 0xffffu, bx1 = br.x >> 16, by0 = br.y & 0xffffu, by1 = br.y >> 16;
-        uint32_t cols = 0u, rows = 0u;
-        if (bx0 <= c0 && c0 <= bx1) cols |= 1u;
-        if (bx0 <= c0 + 1u && c0 + 1u <= bx1) cols |= 2u;
-#pragma unroll
-        for (uint32_t k = 0; k < 4; ++k)
-            if (by0 <= r0 + k && r0 + k <= by1) rows |= 1u << k;
-        // block b = (row b >> 1, column b & 1): spread the row bits to even positions, combine with the column bits
-        const uint32_t spread = (rows & 1u) | ((rows & 2u) << 1) | ((rows & 4u) << 2) | ((rows & 8u) << 3);
-        const uint32_t m = ((cols & 1u) ? spread : 0u) | ((cols & 2u) ? (spread << 1) : 0u);
-        bmask[i] = (uint8_t)m;
-        cmask[i] = 0;
+    const uint32_t a0 = min((range.x + 3u) & ~3u, range.y), a1 = max(range.y & ~3u, a0);  // [a0, a1): whole words
+    if (threadIdx.x < 8) {                                                                // <= 3 head + <= 3 tail bytes
+        const uint32_t i = threadIdx.x < 4 ? range.x + threadIdx.x : a1 + (threadIdx.x - 4);
+        const bool mine = threadIdx.x < 4 ? i < a0 : i < range.y;
+        if (mine) {
+            bmask[i] = (uint8_t)block_mask_of_rect(brects[point_list[i]], c0, r0);
+            cmask[i] = 0;
+        }
+    }
+    const uint4* __restrict__ ids4 = reinterpret_cast<const uint4*>(point_list);
+    uint32_t* __restrict__ bmask32 = reinterpret_cast<uint32_t*>(bmask);
+    uint32_t* __restrict__ cmask32 = reinterpret_cast<uint32_t*>(cmask);
+    for (uint32_t w = (a0 >> 2) + threadIdx.x; w < (a1 >> 2); w += 256) {
+        const uint4 id = ids4[w];
+        const uint2 b0 = brects[id.x], b1 = brects[id.y], b2 = brects[id.z], b3 = brects[id.w];
+        bmask32[w] = block_mask_of_rect(b0, c0, r0) | (block_mask_of_rect(b1, c0, r0) << 8) |
+                     (block_mask_of_rect(b2, c0, r0) << 16) | (block_mask_of_rect(b3, c0, r0) << 24);
+        cmask32[w] = 0u;
     }
 }
 
@@ -104,6 +138,10 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_fwd_kernel(const Comp
     const uint32_t* __restrict__ plist = p.point_list + lo;
     uint32_t* q = sQ[warp];
 
+#ifdef R3DG_WARP_TIMING
+    const unsigned long long wt_t0 = wt_now();
+    unsigned wt_iters = 0;
+#endif
     float T = 1.0f, Dp = 0.0f, Op = 0.0f;
     float C[4 * NG];
 #pragma unroll
@@ -202,45 +240,70 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_fwd_kernel(const Comp
         uint32_t cw = 0u;                                               // bit j: entry j was composited by some pixel
         int last_j = -1;                                                // this pixel's last accepted entry of the batch
         int my_wsum = 0;                                                // lane j keeps the warp's weight sum of entry j
+        // U staged entries per round.  The alpha evaluations (record fetch, quadratic form, exp — two thirds of the
+        // work) depend neither on one another nor on the pixel's state, so all U are issued back to back: U dependency
+        // chains in flight per warp instead of one.  Only the short transmittance recurrence that follows is sequential,
+        // in list order, with exactly the reference's arithmetic.  This is what bounds the kernel: the heaviest pixel
+        // blocks composite ~1000 entries one after the other, and while the light tiles drain the machine those few
+        // warps decide the makespan (tools/warp_timing.py, profiles/r02_warp_timing.md).  A round with fewer than U
+        // entries left re-evaluates the last one, masked out.
+        constexpr int U = NG <= 2 ? R3DG_FWD_ILP : R3DG_FWD_ILP_WIDE;
         while (word) {
-            const int j = __ffs(word) - 1;
-            word &= word - 1;
-            const float4 a = BULK ? sRecB[warp][stage][j][0] : sRec[warp][0][j];
-            const float4 b = BULK ? sRecB[warp][stage][j][1] : sRec[warp][1][j];
-            const float dx = sub_(a.x, pxf), dy = sub_(a.y, pyf);
-            // power = -0.5f*(ca*dx*dx + cc*dy*dy) - cb*dx*dy  (forward.cu:344) as compiled
-            const float qd = fma_(dx, mul_(dx, a.z), mul_(dy, mul_(dy, b.x)));
-            const float power = fma_(qd, -0.5f, -mul_(dy, mul_(dx, a.w)));
-            const float alpha = fminf(0.99f, mul_(b.y, expf(power)));
-            const float test_T = mul_(T, sub_(1.0f, alpha));
-            bool valid = !done && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-            if (valid && test_T < 0.0001f) { done = true; valid = false; }
-            float w = 0.0f;
-            if (valid) {
-                w = mul_(T, alpha);
+            int jj[U];
+            bool pv[U];
+            float al[U], om[U], dep[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {                                // (1) independent: alpha of U entries
+                const bool have = word != 0u;
+                jj[u] = have ? __ffs(word) - 1 : jj[u ? u - 1 : 0];
+                word &= word - 1u;
+#ifdef R3DG_WARP_TIMING
+                wt_iters += have ? 1u : 0u;
+#endif
+                const float4 a = BULK ? sRecB[warp][stage][jj[u]][0] : sRec[warp][0][jj[u]];
+                const float4 b = BULK ? sRecB[warp][stage][jj[u]][1] : sRec[warp][1][jj[u]];
+                const float dx = sub_(a.x, pxf), dy = sub_(a.y, pyf);
+                // power = -0.5f*(ca*dx*dx + cc*dy*dy) - cb*dx*dy  (forward.cu:344) as compiled
+                const float qd = fma_(dx, mul_(dx, a.z), mul_(dy, mul_(dy, b.x)));
+                const float power = fma_(qd, -0.5f, -mul_(dy, mul_(dx, a.w)));
+                al[u] = fminf(0.99f, mul_(b.y, expf(power)));
+                om[u] = sub_(1.0f, al[u]);
+                dep[u] = b.z;
+                pv[u] = have && !(power > 0.0f) && !(al[u] < 1.0f / 255.0f);
+            }
+            int wq[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {                                // (2) sequential, branch-free: T, accumulators
+                const float test_T = mul_(T, om[u]);
+                bool valid = !done && pv[u];
+                const bool stop = valid && test_T < 0.0001f;             // forward.cu:352-356: this pixel is finished
+                done = done || stop;
+                valid = valid && !stop;
+                const float w = mul_(T, al[u]);
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
-                    const float4 c = BULK ? sRecB[warp][stage][j][2 + g] : sRec[warp][2 + g][j];
-                    C[4 * g + 0] = fma_(w, c.x, C[4 * g + 0]);
-                    C[4 * g + 1] = fma_(w, c.y, C[4 * g + 1]);
-                    C[4 * g + 2] = fma_(w, c.z, C[4 * g + 2]);
-                    C[4 * g + 3] = fma_(w, c.w, C[4 * g + 3]);
+                    const float4 c = BULK ? sRecB[warp][stage][jj[u]][2 + g] : sRec[warp][2 + g][jj[u]];
+                    fma4_if(valid, w, c, C[4 * g + 0], C[4 * g + 1], C[4 * g + 2], C[4 * g + 3]);
                 }
-                Dp = fma_(w, b.z, Dp);
-                Op = add_(Op, w);
-                T = test_T;
-                last_j = j;
+                fma_add_if(valid, w, dep[u], Dp, Op);
+                T = valid ? test_T : T;
+                last_j = valid ? jj[u] : last_j;
+                // w in [0,1) in 2^-24 fixed point for the out_weights statistic (below); >= 6 whenever the entry was accepted
+                wq[u] = valid ? __float2int_rn(w * 16777216.0f) : 0;
             }
-            if (__any_sync(0xffffffffu, valid)) {
-                cw |= 1u << j;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {                                // (3) independent again: per-entry warp sums
                 // sum over the warp's pixels of w for out_weights: one integer REDUX instead of a 5-step float shuffle tree
-                // (w in [0,1) in 2^-24 fixed point: error <= 1e-6 per warp, far below the reference's own atomic-order
-                // noise on this statistic); lane j keeps entry j's sum, ONE atomic instruction per batch adds them
-                const int wsum = __reduce_add_sync(0xffffffffu, valid ? __float2int_rn(w * 16777216.0f) : 0);
-                if (lane == j) my_wsum = wsum;
+                // (error <= 1e-6 per warp, far below the reference's own atomic-order noise on this statistic); non-zero
+                // exactly when some pixel accepted the entry.  Lane j keeps entry j's sum: ONE atomic instruction per batch.
+                const int wsum = __reduce_add_sync(0xffffffffu, wq[u]);
+                if (wsum != 0) {
+                    cw |= 1u << jj[u];
+                    if (lane == jj[u]) my_wsum = wsum;
+                }
             }
-            if (__all_sync(0xffffffffu, done)) { all_done = true; break; }
-        }
+            if (__all_sync(0xffffffffu, done)) { all_done = true; break; }      // once per round: entries after the last
+        }                                                                        // pixel finished change nothing (valid needs !done)
         if (last_j >= 0) last_contributor = q[(h0 + last_j) & (R3DG_QCAP - 1)] + 1u;     // 1-based position in the tile list
         if (my_wsum != 0) atomicAdd(&p.out_weights[sId[warp][lane]], (float)my_wsum * (1.0f / 16777216.0f));
         stage ^= 1;
@@ -262,6 +325,9 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_fwd_kernel(const Comp
         p.out_depth[pix] = Dp;
         p.out_opacity[pix] = Op;
     }
+#ifdef R3DG_WARP_TIMING
+    if (lane == 0 && blockIdx.x * NW + warp < R3DG_WT_MAX) g_wt_fwd[blockIdx.x * NW + warp] = WarpTiming{wt_t0, wt_now(), wt_iters, wt_smid()};
+#endif
 }
 
 // renderSurfaceXYZCUDA + renderPseudoNormalCUDA fused: neighbours' surface points are recomputed
@@ -317,28 +383,49 @@ __global__ void __launch_bounds__(256) surface_normal_kernel(int W, int H, const
 // resident CTAs per SM the register allocation is pinned to (ptxas otherwise drifts a few registers above the
 // count that fits one more CTA): by channel groups NG, for the 4-warp CTA (the 8-warp variant is left to ptxas)
 #ifndef R3DG_FWD_OCC2          // resident CTAs per SM the kernels are compiled for, by channel groups (tools/occ_sweep.sh)
-#define R3DG_FWD_OCC2 8
+#define R3DG_FWD_OCC2 7
 #endif
 #ifndef R3DG_FWD_OCC5
 #define R3DG_FWD_OCC5 5
 #endif
-template <int NG> struct FwdOcc { static constexpr int v = NG <= 2 ? R3DG_FWD_OCC2 : (NG <= 3 ? 7 : (NG <= 5 ? R3DG_FWD_OCC5 : 4)); };
+template <int NG> struct FwdOcc { static constexpr int v = NG <= 2 ? R3DG_FWD_OCC2 : (NG <= 3 ? 6 : (NG <= 5 ? R3DG_FWD_OCC5 : (NG <= 6 ? 4 : 3))); };
 
 int g_composite_bulk = -1;      // r3dg_tune("composite_bulk"): 1 = TMA bulk-copy record staging in the forward compositor
-int composite_tune(const char* key, int value, int* previous) {
-    if (strcmp(key, "composite_bulk") != 0) return R3DG_ERR_BAD_ARG;
+int g_fwd_ctas = -1;            // r3dg_tune("composite_fwd_ctas"): resident CTAs per SM (0 = whatever fits)
+static void composite_env() {
     if (g_composite_bulk < 0) { const char* e = getenv("R3DG_COMPOSITE_BULK"); g_composite_bulk = (e && atoi(e) == 1) ? 1 : 0; }
-    if (previous) *previous = g_composite_bulk;
-    if (value != 0 && value != 1) return R3DG_ERR_BAD_ARG;
-    g_composite_bulk = value;
-    return 0;
+    if (g_fwd_ctas < 0) { const char* e = getenv("R3DG_FWD_CTAS"); g_fwd_ctas = e ? atoi(e) : R3DG_FWD_CTAS; if (g_fwd_ctas < 0) g_fwd_ctas = 0; }
+}
+int composite_tune(const char* key, int value, int* previous) {
+    composite_env();
+    if (strcmp(key, "composite_bulk") == 0) {
+        if (previous) *previous = g_composite_bulk;
+        if (value != 0 && value != 1) return R3DG_ERR_BAD_ARG;
+        g_composite_bulk = value;
+        return 0;
+    }
+    if (strcmp(key, "composite_fwd_ctas") == 0) {
+        if (previous) *previous = g_fwd_ctas;
+        if (value < 0 || value > 32) return R3DG_ERR_BAD_ARG;
+        g_fwd_ctas = value;
+        return 0;
+    }
+    return R3DG_ERR_BAD_ARG;
+}
+template <typename K>
+static void launch_fwd_kernel(K kernel, const CompositeFwdParams& p, int tiles, cudaStream_t stream) {
+    static int pad_for = -1, pad_dev = -1;
+    static size_t pad = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (pad_for != g_fwd_ctas || pad_dev != dev) { pad = residency_pad(kernel, g_fwd_ctas); pad_for = g_fwd_ctas; pad_dev = dev; }
+    kernel<<<tiles * 2, 128, pad, stream>>>(p);                          // two 4-warp CTAs per tile
 }
 template <int NG>
 static void launch_fwd_ng(const CompositeFwdParams& p, int tiles, cudaStream_t stream) {
-    if (g_composite_bulk < 0) { const char* e = getenv("R3DG_COMPOSITE_BULK"); g_composite_bulk = (e && atoi(e) == 1) ? 1 : 0; }
-    // two 4-warp CTAs per tile
-    if (g_composite_bulk == 1 && NG <= 6) composite_fwd_kernel<NG <= 6 ? NG : 1, 4, FwdOcc<NG>::v, true><<<tiles * 2, 128, 0, stream>>>(p);
-    else composite_fwd_kernel<NG, 4, FwdOcc<NG>::v, false><<<tiles * 2, 128, 0, stream>>>(p);
+    composite_env();
+    if (g_composite_bulk == 1 && NG <= 6) launch_fwd_kernel(composite_fwd_kernel<NG <= 6 ? NG : 1, 4, FwdOcc<NG>::v, true>, p, tiles, stream);
+    else launch_fwd_kernel(composite_fwd_kernel<NG, 4, FwdOcc<NG>::v, false>, p, tiles, stream);
 }
 
 int launch_block_masks(int W, int H, const GeomLayout& gl, const ImgLayout& il, char* geom, char* img, char* bin,

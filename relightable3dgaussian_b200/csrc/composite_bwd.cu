@@ -2,10 +2,13 @@
 //
 // B200 design notes
 //  * the reference issues 10+S global atomicAdds per contributing (pixel, Gaussian) pair.  Here a
-//    warp (8x4 pixels) first reduces its 32 per-pixel gradient rows with a transposed butterfly
-//    ("reduce-scatter": ~V shuffles for V values instead of 5V), after which 16/32 lanes each
-//    hold one finished component and add the whole per-Gaussian gradient row with ONE vectorised
-//    atomic instruction into a packed [P][RECF] row (2-4 sectors);
+//    warp (8x4 pixels) first reduces its 32 per-pixel gradient rows with transposed butterflies
+//    ("reduce-scatter": ~V shuffles for V values instead of 5V), after which every lane holds one
+//    finished component and the warp adds the whole per-Gaussian gradient row with ONE reduction
+//    instruction into a packed [P][RECF] row (2-4 sectors).  The colour / feature components are
+//    all  (alpha T) * dL_dpix[c] : each lane keeps its dL_dpix in a lane-specific PERMUTED order,
+//    so that what a lane sends and what it keeps at every butterfly level sit in fixed registers —
+//    no select instructions (reduce_scatter_permuted); only the 7 geometry components pay them;
 //  * warps are autonomous (no CTA barrier; see composite.cu): each starts at ITS pixel block's
 //    largest n_contrib instead of the end of the tile list — entries behind every pixel's last
 //    contributor are never loaded — and skips entries its block cannot see via touch_block();
@@ -14,10 +17,23 @@
 //  * gradients differ from the reference only by fp32 summation order (the reference's own
 //    atomics make it run-to-run nondeterministic), tolerance 1e-3 relative.
 #include <cstdlib>
+#include <cstring>
 #include "common.cuh"
 #include "kernels.h"
 
+#ifndef R3DG_BWD_CTAS          // default resident CTAs per SM of the backward compositor (0 = whatever fits)
+#define R3DG_BWD_CTAS 0
+#endif
+#ifndef R3DG_BWD_ILP           // entries per round of the backward walk (composite_bwd_kernel), S <= 5
+#define R3DG_BWD_ILP 2
+#endif
+#ifndef R3DG_BWD_ILP_WIDE      // the same for S > 5 (twice the accumulators: registers)
+#define R3DG_BWD_ILP_WIDE 1
+#endif
+
 namespace r3dg {
+
+template <int NG> struct BwdIlp { static constexpr int v = NG <= 2 ? R3DG_BWD_ILP : R3DG_BWD_ILP_WIDE; };
 
 struct CompositeBwdParams {
     int W, H, gx, S, recf, backward_geometry;
@@ -56,19 +72,95 @@ __device__ __forceinline__ float reduce_scatter(float (&v)[N], int lane) {
     return r;
 }
 
+// U independent reduce-scatters advanced level by level together: U shuffle chains in flight instead of one (the last
+// levels of a single butterfly are one dependent SHFL -> FADD after the other).
+template <int U, int N>
+__device__ __forceinline__ void reduce_scatter_multi(float (&v)[U][N], int lane, float (&r)[U]) {
+    int m = 16;
+#pragma unroll
+    for (int n = N; n > 1; n >>= 1) {
+        const bool upper = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const float send = upper ? v[u][i] : v[u][i + n / 2];
+                const float keep = upper ? v[u][i + n / 2] : v[u][i];
+                v[u][i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+            }
+        }
+        m >>= 1;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) r[u] = v[u][0];
+#pragma unroll
+    for (int mm = 16 / N; mm > 0; mm >>= 1) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) r[u] += __shfl_xor_sync(0xffffffffu, r[u], mm);
+    }
+}
+
+// The same reduce-scatter without selects, for W values whose slot order the caller chose per lane: slot p of lane l
+// must hold component  p ^ (~(l >> (5 - log2 W)) & (W - 1)).  At level n every lane sends slots [0, n/2) and keeps
+// [n/2, n): with that order the kept slot i + n/2 and the partner's sent slot i are the same component.  On return
+// lane l holds the total of component  l >> (5 - log2 W)  (as reduce_scatter).
+template <int W>
+__device__ __forceinline__ float reduce_scatter_permuted(float (&x)[W]) {
+    int m = 16;
+#pragma unroll
+    for (int n = W; n > 1; n >>= 1) {
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) x[i] = x[i + n / 2] + __shfl_xor_sync(0xffffffffu, x[i], m);
+        m >>= 1;
+    }
+    float r = x[0];
+#pragma unroll
+    for (int mm = 16 / W; mm > 0; mm >>= 1) r += __shfl_xor_sync(0xffffffffu, r, mm);
+    return r;
+}
+
+#ifdef R3DG_WARP_TIMING
+__device__ WarpTiming g_wt_bwd[R3DG_WT_MAX];
+extern "C" int r3dg_debug_wt_bwd(void* dst, size_t bytes) { return (int)cudaMemcpyFromSymbol(dst, g_wt_bwd, bytes); }
+#endif
+
+template <int U, int W>
+__device__ __forceinline__ void reduce_scatter_permuted_multi(float (&x)[U][W], float (&r)[U]) {
+    int m = 16;
+#pragma unroll
+    for (int n = W; n > 1; n >>= 1) {
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) x[u][i] = x[u][i + n / 2] + __shfl_xor_sync(0xffffffffu, x[u][i], m);
+        }
+        m >>= 1;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) r[u] = x[u][0];
+#pragma unroll
+    for (int mm = 16 / W; mm > 0; mm >>= 1) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) r[u] += __shfl_xor_sync(0xffffffffu, r[u], mm);
+    }
+}
+
 // Per warp (one 8x4 pixel block): the forward pass left one contributor bit per (instance, block).  The warp streams
 // its tile's contributor bytes BACK TO FRONT, 128 instances per step, compacts the positions whose bit is set into a
 // circular queue (warp scan) and processes batches of 32 of them: every staged entry is one that some pixel of the
 // block composited in the forward pass — no culling test, no record fetch and no exp() for anything else.
 template <int NG, int NW, int MINB>
 __global__ void __launch_bounds__(32 * NW, MINB) composite_bwd_kernel(const CompositeBwdParams p) {
-    constexpr int NC = 4 * NG;              // padded channel count {r,g,b,f...}
-    constexpr int V = 8 + NC;               // gradient row width
-    constexpr int V0 = V <= 16 ? 16 : 32;   // first butterfly chunk
-    constexpr int V1 = V > 32 ? 4 : 0;      // tail chunk (only V == 36)
+    constexpr int NC = 4 * NG;              // padded channel count {r,g,b,f...}; gradient row = 8 geometry slots + NC
+    // the NC channel components are reduced in power-of-two chunks of 16 / 8 / 4 (select-free butterflies)
+    constexpr int C16 = NC >= 16 ? 16 : 0, C8 = (NC - C16) >= 8 ? 8 : 0, C4 = NC - C16 - C8;
+    constexpr int B8 = C16, B4 = C16 + C8;
+    static_assert(C4 == 0 || C4 == 4, "channel groups come in fours");
     constexpr int RG = 2 + NG;
+    constexpr int U = BwdIlp<NG>::v;                 // entries per round of the walk below
     __shared__ float4 sRec[NW][RG][32];
     __shared__ uint32_t sId[NW][32];
+    __shared__ uint32_t sK[NW][32];
     __shared__ uint32_t sQ[NW][R3DG_QCAP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int PARTS = 8 / NW;
@@ -87,6 +179,13 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_bwd_kernel(const Comp
     const uint32_t* __restrict__ plist = p.point_list + lo;
     uint32_t* q = sQ[warp];
 
+#ifdef R3DG_WARP_TIMING
+    const unsigned long long wt_t0 = wt_now();
+    unsigned wt_iters = 0;
+    auto wt_done = [&]() {
+        if (lane == 0 && blockIdx.x * NW + warp < R3DG_WT_MAX) g_wt_bwd[blockIdx.x * NW + warp] = WarpTiming{wt_t0, wt_now(), wt_iters, wt_smid()};
+    };
+#endif
     const float T_final = inside ? p.final_T[pix] : 0.0f;
     float T = T_final;
     const int last_contributor = inside ? p.n_contrib[pix] : 0;
@@ -95,18 +194,46 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_bwd_kernel(const Comp
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) total = max(total, __shfl_xor_sync(0xffffffffu, total, o));
     total = min(total, (int)(range.y - range.x));
+#ifdef R3DG_WARP_TIMING
+    if (total == 0) wt_done();
+#endif
     if (total == 0) return;
 
+    auto load_dpix = [&](int c) -> float {                   // cotangent of channel c of {r,g,b,f0..} at this lane's pixel
+        if (!inside) return 0.0f;
+        if (c < 3) return p.dL_dpix[c * HW + pix];
+        return c - 3 < p.S ? p.dL_dpix_f[(size_t)(c - 3) * HW + pix] : 0.0f;
+    };
     float dpix[NC];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        float g = 0.0f;
-        if (inside) {
-            if (c < 3) g = p.dL_dpix[c * HW + pix];
-            else if (c - 3 < p.S) g = p.dL_dpix_f[(size_t)(c - 3) * HW + pix];
-        }
-        dpix[c] = g;
+    for (int c = 0; c < NC; ++c) dpix[c] = load_dpix(c);
+    // the same cotangents in this lane's butterfly slot order (reduce_scatter_permuted), one array per chunk
+    float cst16[C16 ? C16 : 1], cst8[C8 ? C8 : 1], cst4[C4 ? C4 : 1];
+    if constexpr (C16 > 0) {
+        const int K = ~(lane >> 1) & 15;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cst16[i] = load_dpix(i ^ K);
     }
+    if constexpr (C8 > 0) {
+        const int K = ~(lane >> 2) & 7;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cst8[i] = load_dpix(B8 + (i ^ K));
+    }
+    if constexpr (C4 > 0) {
+        const int K = ~(lane >> 3) & 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cst4[i] = load_dpix(B4 + (i ^ K));
+    }
+    // which finished component this lane adds to the Gaussian's gradient row: geometry slot lane >> 2 on lanes 0 mod 4,
+    // the 16-chunk on odd lanes, the 8-chunk on lanes 2 mod 4, the 4-chunk on a free lane class (second instruction
+    // only when all three chunks exist, NG == 7)
+    constexpr bool C4_SECOND = C16 > 0 && C8 > 0 && C4 > 0;
+    int my_sel = -1, my_off = 0;
+    if ((lane & 3) == 0) { if ((lane >> 2) != 7) { my_sel = 0; my_off = lane >> 2; } }
+    else if (C16 > 0 && (lane & 1)) { my_sel = 1; my_off = 8 + (lane >> 1); }
+    else if (C8 > 0 && (lane & 3) == 2) { my_sel = 2; my_off = 8 + B8 + (lane >> 2); }
+    if (C4 > 0 && !C4_SECOND && (lane & 7) == (C16 > 0 ? 2 : 1)) { my_sel = 3; my_off = 8 + B4 + (lane >> 3); }
+    if (my_sel > 0 && my_off - 8 >= 3 + p.S) my_sel = -1;    // zero padding channel
     const float dpix_d = inside ? p.dL_dpix_d[pix] : 0.0f;
     const float dpix_o = inside ? p.dL_dpix_o[pix] : 0.0f;
     const float bg_dot = p.bg[0] * dpix[0] + p.bg[1] * dpix[1] + p.bg[2] * dpix[2];
@@ -151,12 +278,13 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_bwd_kernel(const Comp
     while (qcount < 64 && w_next >= w_low) scan_step();
     __syncwarp();
 
-    uint32_t id_cur = 0u;
+    uint32_t id_cur = 0u, k_cur = 0u;
     float4 r[RG];
 #pragma unroll
     for (int g = 0; g < RG; ++g) r[g] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (lane < qcount) {
-        id_cur = plist[q[(qhead + lane) & (R3DG_QCAP - 1)]];
+        k_cur = q[(qhead + lane) & (R3DG_QCAP - 1)];
+        id_cur = plist[k_cur];
 #pragma unroll
         for (int g = 0; g < RG; ++g) r[g] = rec4[(size_t)id_cur * rec4n + g];
     }
@@ -165,96 +293,165 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_bwd_kernel(const Comp
         const int n = min(32, qcount);
         __syncwarp();
         sId[warp][lane] = id_cur * (uint32_t)p.recf;                   // element offset of the Gaussian's gradient row
+        sK[warp][lane] = k_cur;                                        // 0-based list position == contributor index
 #pragma unroll
         for (int g = 0; g < RG; ++g) sRec[warp][g][lane] = r[g];
-        const int h0 = qhead;
         qhead = (qhead + n) & (R3DG_QCAP - 1);
         qcount -= n;
         while (qcount < 64 && w_next >= w_low) scan_step();
         __syncwarp();
         if (lane < qcount) {
-            id_cur = plist[q[(qhead + lane) & (R3DG_QCAP - 1)]];
+            k_cur = q[(qhead + lane) & (R3DG_QCAP - 1)];
+            id_cur = plist[k_cur];
 #pragma unroll
             for (int g = 0; g < RG; ++g) r[g] = rec4[(size_t)id_cur * rec4n + g];
         }
+        // Rounds of U entries.  The kernel is latency-bound, not issue-bound (fewer resident CTAs make it slower at every
+        // setting, profiles/r02_warp_timing.md), and the heaviest pixel blocks walk ~500 contributors one after the other,
+        // so the round is laid out for instruction-level parallelism inside the warp: (1) everything that depends only on
+        // the entry — record fetch, exp(), alpha, 1/(1-alpha), the entry's own cotangent dot D — for all U entries; (2) the
+        // two short recurrences T and A in list order; (3) gradient rows and butterflies of the U entries, advanced level
+        // by level together.  A round with fewer than U entries left re-evaluates the last one with its gate closed.
 #pragma unroll 1
-        for (int j = 0; j < n; ++j) {
-            const int k = (int)q[(h0 + j) & (R3DG_QCAP - 1)];                    // 0-based list position == contributor
-            const float4 a = sRec[warp][0][j];
-            const float4 b = sRec[warp][1][j];
-            const float dx = sub_(a.x, pxf), dy = sub_(a.y, pyf);
-            const float qd = fma_(dx, mul_(dx, a.z), mul_(dy, mul_(dy, b.x)));
-            const float power = fma_(qd, -0.5f, -mul_(dy, mul_(dx, a.w)));
-            const float G = expf(power);
-            const float alpha = fminf(0.99f, mul_(b.y, G));
-            // the same three tests as the forward pass (identical arithmetic) + "not behind this pixel's last contributor"
-            const bool valid = k < last_contributor && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-            // branch-free: every lane runs the arithmetic, lanes that did not composite this entry contribute zeros and
-            // keep their state (some lane always did — that is what the contributor bit says)
-            const float gate = valid ? 1.0f : 0.0f;
-            float inv;                                                   // 1 / (1 - alpha), 1 - alpha in [0.01, 1]: one MUFU
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.0f - alpha));
-            const float Tn = T * inv;                                   // T before this entry (backward.cu:533)
-            const float dchannel_dcolor = gate * alpha * Tn;
-            float v0[V0];
-            float v1[V1 > 0 ? V1 : 4];
+        for (int j0 = 0; j0 < n; j0 += U) {
+            int ju[U];
+            bool valid[U];
+            float dx[U], dy[U], G[U], alpha[U], inv[U], D[U];
 #pragma unroll
-            for (int i = 0; i < V0; ++i) v0[i] = 0.0f;
+            for (int u = 0; u < U; ++u) {                                   // (1)
+                ju[u] = min(j0 + u, n - 1);
+                const int k = (int)sK[warp][ju[u]];
+#ifdef R3DG_WARP_TIMING
+                wt_iters += j0 + u < n ? 1u : 0u;
+#endif
+                const float4 a = sRec[warp][0][ju[u]];
+                const float4 b = sRec[warp][1][ju[u]];
+                dx[u] = sub_(a.x, pxf); dy[u] = sub_(a.y, pyf);
+                const float qd = fma_(dx[u], mul_(dx[u], a.z), mul_(dy[u], mul_(dy[u], b.x)));
+                const float power = fma_(qd, -0.5f, -mul_(dy[u], mul_(dx[u], a.w)));
+                G[u] = expf(power);
+                alpha[u] = fminf(0.99f, mul_(b.y, G[u]));
+                // the same three tests as the forward pass (identical arithmetic) + "not behind this pixel's last contributor"
+                valid[u] = j0 + u < n && k < last_contributor && !(power > 0.0f) && !(alpha[u] < 1.0f / 255.0f);
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv[u]) : "f"(1.0f - alpha[u]));   // 1 - alpha in [0.01, 1]: one MUFU
+                float d = fmaf(b.z, dpix_d, dpix_o);                        // depth * dL_ddepth + 1 * dL_dopacity
 #pragma unroll
-            for (int i = 0; i < (V1 > 0 ? V1 : 4); ++i) v1[i] = 0.0f;
-            float D = fmaf(b.z, dpix_d, dpix_o);                        // depth * dL_ddepth + 1 * dL_dopacity
+                for (int g = 0; g < NG; ++g) {
+                    const float4 c4 = sRec[warp][2 + g][ju[u]];
+                    d = fmaf(c4.x, dsel[4 * g + 0], d);
+                    d = fmaf(c4.y, dsel[4 * g + 1], d);
+                    d = fmaf(c4.z, dsel[4 * g + 2], d);
+                    d = fmaf(c4.w, dsel[4 * g + 3], d);
+                }
+                D[u] = d;
+            }
+            float dcc[U], dL_dalpha[U];
 #pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                const float4 c4 = sRec[warp][2 + g][j];
-                const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+            for (int u = 0; u < U; ++u) {                                   // (2) branch-free: lanes that did not composite
+                const float gate = valid[u] ? 1.0f : 0.0f;                  // the entry contribute zeros and keep their state
+                const float Tn = T * inv[u];                                // T before this entry (backward.cu:533)
+                dcc[u] = gate * alpha[u] * Tn;
+                dL_dalpha[u] = gate * fmaf(D[u] - A, Tn, -(T_final * inv[u]) * bg_dot);
+                if (valid[u]) { A = fmaf(alpha[u], D[u] - A, A); T = Tn; } // A <- alpha D + (1 - alpha) A
+            }
+            float v0[U][8], mine[U];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int c = 4 * g + e;
-                    D = fmaf(cc[e], dsel[c], D);
-                    const float gv = dchannel_dcolor * dpix[c];
-                    if (8 + c < V0) v0[(8 + c) < V0 ? (8 + c) : 0] = gv;
-                    else v1[(8 + c - V0) >= 0 && (8 + c - V0) < 4 ? (8 + c - V0) : 0] = gv;
+            for (int u = 0; u < U; ++u) {                                   // (3)
+                const float4 a = sRec[warp][0][ju[u]];
+                const float4 b = sRec[warp][1][ju[u]];
+                const float dL_dG = b.y * dL_dalpha[u];
+                const float gdx = G[u] * dx[u], gdy = G[u] * dy[u];
+                const float dG_ddelx = -gdx * a.z - gdy * a.w;
+                const float dG_ddely = -gdy * b.x - gdx * a.w;
+                v0[u][0] = dL_dG * dG_ddelx * ddelx_dx;
+                v0[u][1] = dL_dG * dG_ddely * ddely_dy;
+                v0[u][2] = dpix_d * dcc[u];
+                v0[u][3] = G[u] * dL_dalpha[u];
+                v0[u][4] = -0.5f * gdx * dx[u] * dL_dG;
+                v0[u][5] = -0.5f * gdx * dy[u] * dL_dG;
+                v0[u][6] = -0.5f * gdy * dy[u] * dL_dG;
+                v0[u][7] = 0.0f;
+            }
+            reduce_scatter_multi<U, 8>(v0, lane, mine);                     // geometry slots: lanes 0 mod 4
+            if constexpr (C16 > 0) {
+                float x[U][16], t[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) x[u][i] = dcc[u] * cst16[i];
+                reduce_scatter_permuted_multi<U, 16>(x, t);
+#pragma unroll
+                for (int u = 0; u < U; ++u) if (my_sel == 1) mine[u] = t[u];
+            }
+            if constexpr (C8 > 0) {
+                float x[U][8], t[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) x[u][i] = dcc[u] * cst8[i];
+                reduce_scatter_permuted_multi<U, 8>(x, t);
+#pragma unroll
+                for (int u = 0; u < U; ++u) if (my_sel == 2) mine[u] = t[u];
+            }
+            float t4[U];
+            if constexpr (C4 > 0) {
+                float x[U][4];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) x[u][i] = dcc[u] * cst4[i];
+                reduce_scatter_permuted_multi<U, 4>(x, t4);
+                if constexpr (!C4_SECOND) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) if (my_sel == 3) mine[u] = t4[u];
                 }
             }
-            const float dL_dalpha = gate * fmaf(D - A, Tn, -(T_final * inv) * bg_dot);
-            if (valid) { A = fmaf(alpha, D - A, A); T = Tn; }           // A <- alpha D + (1 - alpha) A
-            const float dL_dG = b.y * dL_dalpha;
-            const float gdx = G * dx, gdy = G * dy;
-            const float dG_ddelx = -gdx * a.z - gdy * a.w;
-            const float dG_ddely = -gdy * b.x - gdx * a.w;
-            v0[0] = dL_dG * dG_ddelx * ddelx_dx;
-            v0[1] = dL_dG * dG_ddely * ddely_dy;
-            v0[2] = dpix_d * dchannel_dcolor;
-            v0[3] = G * dL_dalpha;
-            v0[4] = -0.5f * gdx * dx * dL_dG;
-            v0[5] = -0.5f * gdx * dy * dL_dG;
-            v0[6] = -0.5f * gdy * dy * dL_dG;
-            float* grow = p.grad + sId[warp][j];
-            const float r0 = reduce_scatter<V0>(v0, lane);
-            {
-                constexpr int SH = V0 == 32 ? 0 : 1;            // lanes per component - 1 (log2)
-                const int comp = lane >> SH;
-                if ((lane & ((1 << SH) - 1)) == 0 && comp < V && comp != 7) atomicAdd(grow + comp, r0);
-            }
-            if constexpr (V1 > 0) {
-                const float r1 = reduce_scatter<4>(v1, lane);
-                const int comp = lane >> 3;
-                if ((lane & 7) == 0 && V0 + comp < V) atomicAdd(grow + V0 + comp, r1);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (j0 + u < n) {                                           // (warp-uniform)
+                    float* grow = p.grad + sId[warp][ju[u]];
+                    if constexpr (C4_SECOND) {
+                        if ((lane & 7) == 0 && B4 + (lane >> 3) < 3 + p.S) atomicAdd(grow + 8 + B4 + (lane >> 3), t4[u]);
+                    }
+                    if (my_sel >= 0) atomicAdd(grow + my_off, mine[u]);
+                }
             }
         }
     }
+#ifdef R3DG_WARP_TIMING
+    wt_done();
+#endif
 }
 
 #ifndef R3DG_BWD_OCC2
-#define R3DG_BWD_OCC2 6
+#define R3DG_BWD_OCC2 5
 #endif
 #ifndef R3DG_BWD_OCC5
 #define R3DG_BWD_OCC5 4
 #endif
 template <int NG> struct BwdOcc { static constexpr int v = NG <= 2 ? R3DG_BWD_OCC2 : (NG <= 3 ? 5 : (NG <= 5 ? R3DG_BWD_OCC5 : 3)); };
+int g_bwd_ctas = -1;            // r3dg_tune("composite_bwd_ctas"): resident CTAs per SM (0 = whatever fits)
+static void composite_bwd_env() {
+    if (g_bwd_ctas < 0) { const char* e = getenv("R3DG_BWD_CTAS"); g_bwd_ctas = e ? atoi(e) : R3DG_BWD_CTAS; if (g_bwd_ctas < 0) g_bwd_ctas = 0; }
+}
+int composite_bwd_tune(const char* key, int value, int* previous) {
+    composite_bwd_env();
+    if (strcmp(key, "composite_bwd_ctas") != 0) return R3DG_ERR_BAD_ARG;
+    if (previous) *previous = g_bwd_ctas;
+    if (value < 0 || value > 32) return R3DG_ERR_BAD_ARG;
+    g_bwd_ctas = value;
+    return 0;
+}
 template <int NG>
 static void launch_bwd_ng(const CompositeBwdParams& p, int tiles, cudaStream_t stream) {
-    composite_bwd_kernel<NG, 4, BwdOcc<NG>::v><<<tiles * 2, 128, 0, stream>>>(p);      // two 4-warp CTAs per tile
+    composite_bwd_env();
+    auto kernel = composite_bwd_kernel<NG, 4, BwdOcc<NG>::v>;
+    static int pad_for = -1, pad_dev = -1;
+    static size_t pad = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (pad_for != g_bwd_ctas || pad_dev != dev) { pad = residency_pad(kernel, g_bwd_ctas); pad_for = g_bwd_ctas; pad_dev = dev; }
+    kernel<<<tiles * 2, 128, pad, stream>>>(p);                          // two 4-warp CTAs per tile
 }
 
 int launch_composite_backward(const r3dg_raster_bwd_args& a, const GeomLayout& gl, const ImgLayout& il,

@@ -62,6 +62,28 @@ int launch_pack_features_backward(int P, int S, const float* means3D, const floa
 
 int shade_tune(const char* key, int value, int* previous);
 int composite_tune(const char* key, int value, int* previous);
+int composite_bwd_tune(const char* key, int value, int* previous);
+
+// Dynamic shared memory to request so that at most `ctas` CTAs of `kernel` are resident per SM (0 when ctas <= 0 or
+// the kernel's own footprint already allows no more).  The compositors are bound by their heaviest warps (a pixel
+// block that composites ~1000 entries one after the other): fewer co-resident warps let those run faster while the
+// total throughput stays issue-bound — see the residency sweep in profiles/r02_warp_timing.md.
+template <typename K>
+inline size_t residency_pad(K kernel, int ctas) {
+    if (ctas <= 0) return 0;
+    cudaFuncAttributes fa;
+    int dev = 0, smem_sm = 0, smem_blk = 0;
+    if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess || cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const size_t fixed = fa.sharedSizeBytes + 1024;                       // static + the per-CTA system reservation
+    size_t per = ((size_t)smem_sm / (size_t)ctas) & ~(size_t)127;
+    if (per <= fixed) return 0;
+    size_t dyn = per - fixed;
+    if (fa.sharedSizeBytes + dyn > (size_t)smem_blk) dyn = (size_t)smem_blk - fa.sharedSizeBytes;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return dyn;
+}
 
 // adam.cu: one launch per <= 16 parameter tensors
 int launch_adam(int num, const r3dg_adam_tensor* tensors, cudaStream_t stream, int* launches);

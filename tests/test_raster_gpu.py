@@ -175,16 +175,17 @@ def test_matches_cpu_oracle_midsize(C, S, pseudo):
             assert rel_l2(npy(o["grads"][n]), gr[n]) < 1e-3, n
 
 
-def _live_reference_parity(C, P, W, H, S, view, center_shift, backward=True, recipe="shell-v1"):
+def _live_reference_parity(C, P, W, H, S, view, center_shift, backward=True, recipe="shell-v1", sh_degree=3, M=16, scale_boost=1.0):
     """Our kernels vs the UNMODIFIED reference kernels (oracle/_ref) on the same inputs, on this GPU:
     tile / sort indices bit-exact, images <= 1e-4 max-abs, all nine gradients <= 1e-3 relative (north_star)."""
     from oracle import ref_gpu
     if not ref_gpu.available():
         pytest.skip("oracle/_ref/libref_raster.so not present")
-    sc, cam = case_inputs(P, W, H, S, view=view, center_shift=center_shift, recipe=recipe)
+    sc, cam = case_inputs(P, W, H, S, view=view, center_shift=center_shift, recipe=recipe, scale_boost=scale_boost)
     bg = torch.tensor([0.0, 0.5, 1.0])
     kw = oracle_kwargs(sc, cam, bg)
-    extra = dict(shs=npy(sc.shs), scales=npy(sc.scales), rotations=npy(sc.rotations), features=npy(sc.features) if S else None)
+    extra = dict(shs=np.ascontiguousarray(npy(sc.shs)[:, :M]), scales=npy(sc.scales), rotations=npy(sc.rotations),
+                 features=npy(sc.features) if S else None, sh_degree=sh_degree)
     g = torch.Generator().manual_seed(2)
     cots = [torch.randn(c, H, W, generator=g) for c in (3, 1, 1, S)] if backward else None
     o = run_ours(C, cots=cots, **kw, **extra)
@@ -205,7 +206,7 @@ def _live_reference_parity(C, P, W, H, S, view, center_shift, backward=True, rec
     if backward:
         rg = ref.backward(ro, dL_dcolor=dev(cots[0]), dL_dopacity=dev(cots[1]), dL_ddepth=dev(cots[2]), dL_dfeature=dev(cots[3]),
                           **{k: v for k, v in tk.items() if k in ("means3D", "viewmatrix", "projmatrix", "campos", "bg",
-                                                                  "tan_fovx", "tan_fovy", "shs", "scales", "rotations", "features")})
+                                                                  "tan_fovx", "tan_fovy", "shs", "scales", "rotations", "features", "sh_degree")})
         for n in GRADS:
             if rg[n].numel() and float(rg[n].abs().max()) > 0:
                 assert rel_l2(npy(o["grads"][n]), npy(rg[n])) < 1e-3, n
@@ -226,6 +227,20 @@ def test_matches_live_reference_kernels_if_built(C):
 ], ids=["cfg2-300k-fwd", "cfg3-300k-fwdbwd", "headline-1M-S5", "cfg4-1.5M-1600x1200-S16", "cfg5-2M-1080p-S16"])
 def test_live_reference_parity_at_benchmark_sizes(C, P, W, H, S, view, shift, bwd):
     _live_reference_parity(C, P, W, H, S, view, shift, backward=bwd)
+
+
+@pytest.mark.parametrize("S", [1, 3, 7, 9, 12, 13, 17, 20, 21, 24, 28, 33])
+def test_every_channel_group_instantiation(C, S):
+    """The compositors are templates on the number of 4-channel groups (S = 0..33 forward, 0..24 backward, the
+    reference's limits forward.cu:312 / backward.cu:449): every instantiation against the reference kernels."""
+    _live_reference_parity(C, 6_000, 208, 144, S, view=S % 8, center_shift=bool(S & 1), backward=S <= 24, scale_boost=2.0)
+
+
+@pytest.mark.parametrize("deg,M", [(0, 1), (1, 4), (2, 9), (3, 16), (1, 16), (0, 16)])
+def test_sh_degrees_and_row_widths(C, deg, M):
+    """SH rows of 12 / 48 / 108 / 192 bytes: the bulk-copy slab path needs 16-byte rows, the others take the
+    transposed LDGSTS path (projection.cu); degrees below the stored width ignore the upper coefficients."""
+    _live_reference_parity(C, 9_000, 200, 136, 5, view=deg + 2, center_shift=False, sh_degree=deg, M=M, scale_boost=1.5)
 
 
 def test_full_size_properties(C):
