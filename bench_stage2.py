@@ -250,6 +250,9 @@ def run_ours(args, cfg, rank, local, world):
         ms = float(t.item())
     phases = {name: _median_ms([(mk[k], mk[k + 1]) for mk in marks]) for k, name in
               enumerate(["h2d_shading_fwd", "pack_raster_fwd", "unpremultiply_loss", "backward_exchange", "adam_d2h"])}
+    # start-to-start intervals of consecutive steps: a host hiccup (allocator, GC) shows up as an outlier here, not in the phases
+    gaps = sorted(marks[k][0].elapsed_time(marks[k + 1][0]) for k in range(len(marks) - 1))
+    step_stats = {"median": gaps[len(gaps) // 2], "min": gaps[0], "max": gaps[-1]} if gaps else None
     if rank != 0:
         return None
     R = int(out[0]); Pv = int((out[9] > 0).sum().item())
@@ -279,7 +282,7 @@ def run_ours(args, cfg, rank, local, world):
                 "what": "the step IS the public-API path (rendering_equation + GaussianRasterizer mirrors + autograd + FusedAdam); the per-step H2D of the "
                         "target image from pinned memory and the D2H of the loss are inside the timed region"},
         "gpu_launches": int(launches), "clocks": clocks,
-        "phase_ms_median": phases, "raster_stage_ms": stage,
+        "phase_ms_median": phases, "step_interval_ms": step_stats, "raster_stage_ms": stage,
         "bake": {"seconds": bake_s, "rays": P * N, "mrays_per_s": P * N / bake_s / 1e6, "blocked_fraction": blocked,
                  "what": "LBVH build + in-kernel Fibonacci direction sampling + opacity trace, once before the loop (not in ms_per_step)"},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -78,7 +78,7 @@ int r3dg_raster_forward(const r3dg_raster_fwd_args* a, r3dg_stream_t stream_) {
         R3DG_CUDA_TRY(cudaMemsetAsync(img + il.ranges, 0, (size_t)tiles * 8, stream));
         for (int i = 1; i <= 4; ++i) prof_mark(true, i, stream);
     }
-    if ((rc = launch_tile_order(img + il.ranges, (uint32_t*)(img + il.tile_order), tiles, stream)) != 0) return rc;
+    if ((rc = launch_tile_order(img + il.ranges, (uint32_t*)(img + il.tile_order), (uint32_t*)(img + il.bwd_work), tiles, stream)) != 0) return rc;
     if (a->P > 0 && (rc = launch_block_masks(a->W, a->H, gl, il, geom, img, bin, bl, stream)) != 0) return rc;
     prof_mark(true, 5, stream);
     if ((rc = launch_composite_forward(*a, gl, il, bin, bl, stream, mark)) != 0) return rc;
@@ -114,7 +114,7 @@ int r3dg_raster_backward(const r3dg_raster_bwd_args* a, r3dg_stream_t stream_) {
     prof_mark(false, 9, stream);
     if ((rc = launch_projection_backward(*a, gl, stream)) != 0) return rc;
     prof_mark(false, 10, stream);
-    g_launches += 2;
+    g_launches += 3;   // CTA order, composite, projection
     if (g_prof.on) g_prof.bwd_calls++;
     if (a->debug) {
         cudaError_t e = cudaStreamSynchronize(stream);

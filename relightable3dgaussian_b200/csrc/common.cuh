@@ -131,7 +131,7 @@ __host__ __device__ inline int bin_chunk_len(int P, size_t T) {     // Gaussians
 }
 
 struct ImgLayout {
-    size_t final_T, n_contrib, ranges, tile_order, slab_sum, bin_matrix, total;
+    size_t final_T, n_contrib, ranges, tile_order, bwd_work, bwd_order, slab_sum, bin_matrix, total;
     __host__ __device__ ImgLayout(int W, int H) {
         size_t HW = (size_t)W * H;
         size_t T = (size_t)((W + R3DG_TILE - 1) / R3DG_TILE) * ((H + R3DG_TILE - 1) / R3DG_TILE);
@@ -140,6 +140,8 @@ struct ImgLayout {
         n_contrib = off; off = align_up(off + HW * 4, 256);
         ranges = off;    off = align_up(off + T * 8, 256);
         tile_order = off; off = align_up(off + T * 4, 256);      // tiles by descending list length
+        bwd_work = off;  off = align_up(off + 2 * T * 4, 256);    // per half-tile CTA: entries its busiest warp composited (forward)
+        bwd_order = off; off = align_up(off + 2 * T * 4, 256);    // half-tile CTAs by descending bwd_work (backward launch order)
         slab_sum = off;  off = align_up(off + T * 4 * ((R3DG_BIN_MAX_CHUNKS + 511) / 512), 256);   // per 512-chunk slab
         bin_matrix = off; off = align_up(off + (size_t)bin_max_chunks(T) * T * 4, 256);
         total = off;

@@ -41,6 +41,7 @@ struct CompositeFwdParams {
     uint32_t* cmask32;           // per-instance contributor masks (zeroed by block_mask_kernel, set here)
     const GeomHeader* header;
     const uint32_t* tile_order;  // CTA -> tile, heaviest tiles first
+    uint32_t* bwd_work;          // [2 tiles] entries composited by the busiest warp of each half-tile CTA (backward launch order)
     const float* rec;
     const float* bg;
     float* final_T;
@@ -205,6 +206,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_fwd_kernel(const Comp
         }
     }
 
+    uint32_t composited = 0u;                                           // entries this warp composited = its backward twin's iterations
     bool all_done = __all_sync(0xffffffffu, done);
     while (qcount > 0 && !all_done) {
         const int n = min(32, qcount);
@@ -307,12 +309,14 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_fwd_kernel(const Comp
         if (last_j >= 0) last_contributor = q[(h0 + last_j) & (R3DG_QCAP - 1)] + 1u;     // 1-based position in the tile list
         if (my_wsum != 0) atomicAdd(&p.out_weights[sId[warp][lane]], (float)my_wsum * (1.0f / 16777216.0f));
         stage ^= 1;
+        composited += (uint32_t)__popc(cw);
         // contributor bits for the backward pass: one fire-and-forget atomic per composited entry
         if ((cw >> lane) & 1u) {
             const uint32_t e = lo + mypos;
             atomicOr(&p.cmask32[e >> 2], 1u << (8 * (e & 3u) + wb));
         }
     }
+    if (lane == 0 && composited) atomicMax(&p.bwd_work[blockIdx.x % PARTS + PARTS * tile], composited);
     if (inside) {
         const size_t HW = (size_t)p.H * p.W, pix = (size_t)p.W * py + px;
         p.final_T[pix] = T;
@@ -450,6 +454,7 @@ int launch_composite_forward(const r3dg_raster_fwd_args& a, const GeomLayout& gl
     p.bmask32 = (const uint32_t*)(bin + bl.bmask); p.cmask32 = (uint32_t*)(bin + bl.cmask);
     p.header = (const GeomHeader*)(geom + gl.header);
     p.tile_order = (const uint32_t*)(img + il.tile_order);
+    p.bwd_work = (uint32_t*)(img + il.bwd_work);
     p.rec = (const float*)(geom + gl.rec);
     p.bg = a.background;
     p.final_T = (float*)(img + il.final_T);

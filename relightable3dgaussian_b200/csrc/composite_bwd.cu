@@ -41,7 +41,7 @@ struct CompositeBwdParams {
     const uint32_t* point_list;  // per-tile depth-sorted Gaussian ids (binning.cu)
     const uint32_t* cmask32;     // per-instance contributor masks written by the forward compositor
     const GeomHeader* header;
-    const uint32_t* tile_order;  // CTA -> tile, heaviest tiles first
+    const uint32_t* cta_order;   // CTA -> half tile (2 * tile + part), most backward work first (cta_order_kernel)
     const float* rec;
     const float* bg;
     const float* final_T;
@@ -164,8 +164,10 @@ __global__ void __launch_bounds__(32 * NW, MINB) composite_bwd_kernel(const Comp
     __shared__ uint32_t sQ[NW][R3DG_QCAP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int PARTS = 8 / NW;
-    const int tile = (int)p.tile_order[blockIdx.x / PARTS];
-    const int wb = (blockIdx.x % PARTS) * NW + warp;
+    static_assert(PARTS == 2, "bwd_work / cta_order are per half tile");
+    const int cta = (int)p.cta_order[blockIdx.x];
+    const int tile = cta / PARTS;
+    const int wb = (cta % PARTS) * NW + warp;
     const int tx = tile % p.gx, ty = tile / p.gx;
     const int bx0 = tx * R3DG_TILE + (wb & 1) * 8, by0 = ty * R3DG_TILE + (wb >> 1) * 4;
     const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
@@ -465,7 +467,7 @@ int launch_composite_backward(const r3dg_raster_bwd_args& a, const GeomLayout& g
     p.ranges = (const uint2*)(img + il.ranges);
     p.point_list = (const uint32_t*)(bin + bl.point_list); p.cmask32 = (const uint32_t*)(bin + bl.cmask);
     p.header = (const GeomHeader*)(geom + gl.header);
-    p.tile_order = (const uint32_t*)(img + il.tile_order);
+    p.cta_order = (const uint32_t*)(img + il.bwd_order);
     p.rec = (const float*)(geom + gl.rec);
     p.bg = a.background;
     p.final_T = (const float*)(img + il.final_T);
@@ -475,6 +477,8 @@ int launch_composite_backward(const r3dg_raster_bwd_args& a, const GeomLayout& g
     p.n_contrib = (const int*)(img + il.n_contrib);
     R3DG_CUDA_TRY(cudaMemsetAsync(p.grad, 0, (size_t)a.P * gl.recf * 4, stream));
     const int tiles = p.gx * gy;
+    int rc = launch_cta_order((const uint32_t*)(img + il.bwd_work), (uint32_t*)(img + il.bwd_order), 2 * tiles, stream);
+    if (rc != 0) return rc;
     switch (num_groups(a.S)) {
         case 1: launch_bwd_ng<1>(p, tiles, stream); break;
         case 2: launch_bwd_ng<2>(p, tiles, stream); break;

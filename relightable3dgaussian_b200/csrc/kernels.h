@@ -10,7 +10,8 @@ typedef void (*stage_mark_fn)(int, cudaStream_t);
 int launch_projection(const r3dg_raster_fwd_args& a, const GeomLayout& gl, cudaStream_t stream);
 int launch_point_offsets(int P, const uint32_t* tiles_touched, uint32_t* out, uint32_t* state,
                          GeomHeader* ticket_header, cudaStream_t stream);
-int launch_tile_order(const void* ranges, uint32_t* tile_order, int num_tiles, cudaStream_t stream);
+int launch_tile_order(const void* ranges, uint32_t* tile_order, uint32_t* bwd_work, int num_tiles, cudaStream_t stream);
+int launch_cta_order(const uint32_t* work, uint32_t* order, int n, cudaStream_t stream);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,
                         cudaStream_t stream);
 // radix_sort.cu: stable sort of n (u32 key, u32 value) pairs laid out by SortLayout in `buf`

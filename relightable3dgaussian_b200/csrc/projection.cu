@@ -428,9 +428,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(int P, const uint32_
 // tiles (longest sorted lists) are launched first so that the grid's tail consists of light tiles
 // (with row-major order the last heavy CTAs left 20% of the SM-cycles idle).  Coarse counting sort
 // by list length (64 buckets), one CTA.
-__global__ void __launch_bounds__(1024) tile_order_kernel(int T, const uint2* __restrict__ ranges, uint32_t* __restrict__ order) {
+__global__ void __launch_bounds__(1024) tile_order_kernel(int T, const uint2* __restrict__ ranges, uint32_t* __restrict__ order,
+                                                          uint32_t* __restrict__ bwd_work) {
     __shared__ uint32_t s_max, s_cnt[64], s_cur[64];
     const int tid = threadIdx.x;
+    for (int i = tid; i < 2 * T; i += 1024) bwd_work[i] = 0u;          // the forward compositor atomicMax-es into it
     if (tid == 0) s_max = 0;
     if (tid < 64) s_cnt[tid] = 0;
     __syncthreads();
@@ -450,6 +452,31 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(int T, const uint2* __
         const uint2 r = ranges[t];
         order[atomicAdd(&s_cur[min(63u, (r.y - r.x) >> shift)], 1u)] = (uint32_t)t;
     }
+}
+
+// The same coarse LPT order for the backward compositor's CTAs, by what the forward pass measured: keys[c] = entries the
+// busiest warp of half-tile CTA c composited = exactly the iterations its backward twin will run.  List length is a poor
+// predictor there (a dense tile saturates after a fraction of its list): ordered by it, heavy backward CTAs started at
+// 40 % of the kernel and finished last (profiles/r02_warp_timing.md).
+__global__ void __launch_bounds__(1024) cta_order_kernel(int n, const uint32_t* __restrict__ keys, uint32_t* __restrict__ order) {
+    __shared__ uint32_t s_max, s_cnt[64], s_cur[64];
+    const int tid = threadIdx.x;
+    if (tid == 0) s_max = 0;
+    if (tid < 64) s_cnt[tid] = 0;
+    __syncthreads();
+    uint32_t m = 0;
+    for (int t = tid; t < n; t += 1024) m = max(m, keys[t]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0) atomicMax(&s_max, m);
+    __syncthreads();
+    const uint32_t mx = s_max;
+    const int shift = mx < 64 ? 0 : (32 - __clz(mx)) - 6;            // bucket = key >> shift in [0, 63]
+    for (int t = tid; t < n; t += 1024) atomicAdd(&s_cnt[min(63u, keys[t] >> shift)], 1u);
+    __syncthreads();
+    if (tid == 0) { uint32_t acc = 0; for (int b = 63; b >= 0; --b) { s_cur[b] = acc; acc += s_cnt[b]; } }   // descending
+    __syncthreads();
+    for (int t = tid; t < n; t += 1024) order[atomicAdd(&s_cur[min(63u, keys[t] >> shift)], 1u)] = (uint32_t)t;
 }
 
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D,
@@ -503,8 +530,14 @@ int launch_point_offsets(int P, const uint32_t* tiles_touched, uint32_t* out, ui
     return 0;
 }
 
-int launch_tile_order(const void* ranges, uint32_t* tile_order, int num_tiles, cudaStream_t stream) {
-    tile_order_kernel<<<1, 1024, 0, stream>>>(num_tiles, (const uint2*)ranges, tile_order);
+int launch_tile_order(const void* ranges, uint32_t* tile_order, uint32_t* bwd_work, int num_tiles, cudaStream_t stream) {
+    tile_order_kernel<<<1, 1024, 0, stream>>>(num_tiles, (const uint2*)ranges, tile_order, bwd_work);
+    R3DG_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int launch_cta_order(const uint32_t* work, uint32_t* order, int n, cudaStream_t stream) {
+    cta_order_kernel<<<1, 1024, 0, stream>>>(n, work, order);
     R3DG_CUDA_TRY(cudaGetLastError());
     return 0;
 }
