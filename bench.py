@@ -23,6 +23,7 @@ is absent it falls back to the CPU oracle port.
 """
 import argparse
 import ctypes
+import gc
 import json
 import os
 import statistics
@@ -196,12 +197,16 @@ def bench_ours(args, cfg, rank, local, world):
     def timed(fn, steps, warmup, profile=False):
         for i in range(warmup):
             fn(i)
+        # as timeit does: no collector inside the timed region — a pause in ONE of the N host processes stalls every rank
+        # at the exchange.  Collected BEFORE the barrier, so that the ranks still enter the region together.
+        gc.collect()
+        gc.disable()
+        if profile:
+            lib.r3dg_prof_begin(steps)
         torch.cuda.synchronize(dev)
         if world > 1:
             tdist.barrier()
         torch.cuda.synchronize(dev)
-        if profile:
-            lib.r3dg_prof_begin(steps)
         l0 = lib.r3dg_launch_count()
         # the contract's timed region is the whole K steps (e0..e1); events between 5 equal blocks (no
         # synchronisation) additionally give a median-of-blocks figure that is robust to a one-off hiccup
@@ -213,6 +218,7 @@ def bench_ours(args, cfg, rank, local, world):
             for i in range(cuts[b], cuts[b + 1]):
                 fn(warmup + i)
             evs[b + 1].record()
+        gc.enable()
         torch.cuda.synchronize(dev)
         if world > 1:
             tdist.barrier()
@@ -437,10 +443,13 @@ def bench_reference(args, cfg, rank, local, world):
         torch.cuda.synchronize()
         sampler = ClockSampler(local); sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gc.collect()
+        gc.disable()          # both arms are timed the same way
         e0.record()
         for i in range(args.steps):
             o = step(args.warmup + i)
         e1.record()
+        gc.enable()
         torch.cuda.synchronize()
         clocks = sampler.stop()
         ms = e0.elapsed_time(e1)

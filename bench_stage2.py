@@ -22,6 +22,7 @@ The loss is a plain L1 on the radiance and PBR images plus a light regulariser o
 reference's SSIM / smoothness terms are host PyTorch outside the hot path).
 """
 import ctypes
+import gc
 import json
 import os
 import statistics
@@ -218,20 +219,23 @@ def run_ours(args, cfg, rank, local, world):
     warm = max(args.warmup, 10)          # the first _LEARN forwards of a shape take the synchronous count path
     for i in range(warm):
         step(i)
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        tdist.barrier()
-    torch.cuda.synchronize(dev)
+    gc.collect()
+    gc.disable()              # as timeit does (both arms); before the barrier so that the ranks enter the region together
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     lib.r3dg_prof_begin(args.steps)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        tdist.barrier()
+    torch.cuda.synchronize(dev)
     l0 = lib.r3dg_launch_count()
     e0, e1 = ev(), ev()
     e0.record()
     for i in range(args.steps):
         out = step(warm + i, record=True)
     e1.record()
+    gc.enable()
     torch.cuda.synchronize(dev)
     if world > 1:
         tdist.barrier()
@@ -360,10 +364,13 @@ def run_reference(args, cfg, rank, local, world):
     torch.cuda.synchronize()
     sampler = ClockSampler(local); sampler.start()
     e0, e1 = ev(), ev()
+    gc.collect()
+    gc.disable()
     e0.record()
     for i in range(args.steps):
         out = step(args.warmup + i, record=True)
     e1.record()
+    gc.enable()
     torch.cuda.synchronize()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
