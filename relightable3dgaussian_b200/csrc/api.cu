@@ -129,9 +129,9 @@ unsigned long long r3dg_launch_count(void) { return g_launches + r3dg_adam_launc
 int r3dg_tune(const char* key, int value, int* previous) {
     if (!key) return R3DG_ERR_BAD_ARG;
     int prev = 0;
-    int rc = shade_tune(key, value, &prev);
-    if (rc != 0) rc = composite_tune(key, value, &prev);
-    if (rc != 0) rc = composite_bwd_tune(key, value, &prev);
+    int rc = shade_tune(key, value, &prev);                       // each returns R3DG_ERR_UNSUPPORTED for a key it does not own
+    if (rc == R3DG_ERR_UNSUPPORTED) rc = composite_tune(key, value, &prev);
+    if (rc == R3DG_ERR_UNSUPPORTED) rc = composite_bwd_tune(key, value, &prev);
     if (previous) *previous = prev;
     return rc;
 }

@@ -414,7 +414,7 @@ int composite_tune(const char* key, int value, int* previous) {
         g_fwd_ctas = value;
         return 0;
     }
-    return R3DG_ERR_BAD_ARG;
+    return R3DG_ERR_UNSUPPORTED;
 }
 template <typename K>
 static void launch_fwd_kernel(K kernel, const CompositeFwdParams& p, int tiles, cudaStream_t stream) {

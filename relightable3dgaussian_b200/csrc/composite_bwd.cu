@@ -438,7 +438,7 @@ static void composite_bwd_env() {
 }
 int composite_bwd_tune(const char* key, int value, int* previous) {
     composite_bwd_env();
-    if (strcmp(key, "composite_bwd_ctas") != 0) return R3DG_ERR_BAD_ARG;
+    if (strcmp(key, "composite_bwd_ctas") != 0) return R3DG_ERR_UNSUPPORTED;
     if (previous) *previous = g_bwd_ctas;
     if (value < 0 || value > 32) return R3DG_ERR_BAD_ARG;
     g_bwd_ctas = value;

@@ -70,6 +70,20 @@ def test_bad_arguments_are_rejected_without_touching_the_gpu():
     assert lib.r3dg_raster_backward(ctypes.byref(b), None) == -10002
 
 
+def test_tune_keys_and_error_codes():
+    """r3dg_tune: every documented key round-trips, unknown keys / out-of-range values are refused (host state only)."""
+    lib = _lib.load()
+    prev = ctypes.c_int(-5)
+    for key, ok, bad in (("composite_bulk", 1, 2), ("composite_fwd_ctas", 4, 99), ("composite_bwd_ctas", 3, -1), ("shade_group", 16, 7)):
+        assert lib.r3dg_tune(key.encode(), ok, ctypes.byref(prev)) == 0, key
+        old = prev.value
+        assert lib.r3dg_tune(key.encode(), bad, ctypes.byref(prev)) == -10001, key          # R3DG_ERR_BAD_ARG
+        assert prev.value == ok
+        assert lib.r3dg_tune(key.encode(), old, None) == 0
+    assert lib.r3dg_tune(b"no_such_knob", 1, None) == -10002                                  # R3DG_ERR_UNSUPPORTED
+    assert lib.r3dg_tune(None, 1, None) == -10001
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "_lib", None)
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
