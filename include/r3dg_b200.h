@@ -174,7 +174,9 @@ int r3dg_mark_visible(int P, const float* means3D, const float* viewmatrix,
  * `dst` (device pointer) as a dense array in the REFERENCE's element layout.
  * ids: 0 depths f32[P] | 1 clamped u8[3P] | 3 means2D f32[2P] | 5 conic_opacity f32[4P]
  *      6 rgb f32[3P] | 7 tiles_touched u32[P] | 8 point_offsets u32[P] | 9 point_list u32[R]
- *      10 point_list_keys u64[R] | 13 final_T f32[HW] | 15 ranges u32[2T]
+ *      10 point_list_keys u64[R] | 13 final_T f32[HW] | 14 n_contrib i32[HW] | 15 ranges u32[2T]
+ *      (ours only) 16 bwd_work u32[2T]: entries composited by the busiest warp of each half-tile
+ *      CTA | 17 bwd_order u32[2T]: the backward compositor's launch order (valid after a backward)
  * Returns bytes written or a negative error. */
 long long r3dg_raster_debug_copy(int id, int P, int S, int W, int H, const void* geom,
                                  const void* img, const void* binning, size_t binning_bytes,

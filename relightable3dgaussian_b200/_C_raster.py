@@ -306,7 +306,8 @@ def debug_intermediate(name, P, S, W, H, geomBuffer, imgBuffer, binningBuffer, n
             "point_offsets": (8, torch.int32, (P,)), "point_list": (9, torch.int32, (num_rendered,)),
             "point_list_keys": (10, torch.int64, (num_rendered,)),
             "final_T": (13, torch.float32, (H, W)), "n_contrib": (14, torch.int32, (H, W)),
-            "ranges": (15, torch.int32, (T, 2))}[name]
+            "ranges": (15, torch.int32, (T, 2)), "bwd_work": (16, torch.int32, (T, 2)),
+            "bwd_order": (17, torch.int32, (2 * T,))}[name]
     out = torch.empty(spec[2], dtype=spec[1], device=geomBuffer.device)
     if out.numel() == 0:
         return out

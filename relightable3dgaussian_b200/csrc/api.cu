@@ -330,6 +330,8 @@ long long r3dg_raster_debug_copy(int id, int P, int S, int W, int H, const void*
         case 13: return copy(img + il.final_T, 4 * HW);
         case 14: return copy(img + il.n_contrib, 4 * HW);
         case 15: return copy(img + il.ranges, 8 * (size_t)tiles);
+        case 16: return copy(img + il.bwd_work, 8 * (size_t)tiles);
+        case 17: return copy(img + il.bwd_order, 8 * (size_t)tiles);
         case 9: case 10: {
             const long long capacity = bin_capacity_for_bytes(binning_bytes);
             if (capacity < 1) return -1;

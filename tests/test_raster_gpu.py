@@ -243,6 +243,29 @@ def test_sh_degrees_and_row_widths(C, deg, M):
     _live_reference_parity(C, 9_000, 200, 136, 5, view=deg + 2, center_shift=False, sh_degree=deg, M=M, scale_boost=1.5)
 
 
+def test_backward_launch_order_follows_measured_forward_work(C):
+    """The forward compositor records, per half-tile CTA, how many entries its busiest warp composited; the backward's
+    CTAs are launched in that order (coarse 64-bucket LPT).  Invariants against n_contrib, and the order is a permutation."""
+    P, W, H, S = 40_000, 400, 304, 5
+    sc, cam = case_inputs(P, W, H, S, view=2, scale_boost=1.5)
+    kw = oracle_kwargs(sc, cam, torch.tensor([0.0, 0.0, 0.0]))
+    g = torch.Generator().manual_seed(3)
+    cots = [torch.randn(c, H, W, generator=g) for c in (3, 1, 1, S)]
+    o = run_ours(C, cots=cots, shs=npy(sc.shs), scales=npy(sc.scales), rotations=npy(sc.rotations), features=npy(sc.features), **kw)
+    gx, gy = (W + 15) // 16, (H + 15) // 16
+    work = o["mid"]("bwd_work").long()                      # [T, 2]: rows 0-7 / 8-15 of the tile
+    order = o["mid"]("bwd_order").long()
+    nc = torch.zeros(gy * 16, gx * 16, dtype=torch.int64, device="cuda")
+    nc[:H, :W] = o["n_contrib"].long()
+    half_max = nc.view(gy, 2, 8, gx, 16).amax(dim=(2, 4)).permute(0, 2, 1).reshape(gy * gx, 2)   # deepest contributor per half tile
+    assert bool(((work > 0) == (half_max > 0)).all())
+    assert bool((work <= half_max).all())                   # composited entries are a subset of the positions walked
+    assert torch.equal(torch.sort(order).values, torch.arange(2 * gx * gy, device="cuda"))
+    keys = work.reshape(-1)[order]
+    shift = max(int(keys.max()).bit_length() - 6, 0)
+    assert bool(((keys[:-1] >> shift) >= (keys[1:] >> shift)).all())
+
+
 def test_full_size_properties(C):
     """BASELINE.json headline size (1M Gaussians, 800x800): size-independent properties."""
     P, W, H, S = 1_000_000, 800, 800, 5
