@@ -3,18 +3,22 @@
 //
 // B200 design notes
 //  * each warp owns a compact 8x4 pixel block of a 16x16 tile and walks the tile's sorted list
-//    AUTONOMOUSLY: no CTA barrier, per-warp early termination, a register software pipeline that
-//    keeps the next 32-entry chunk (ids two chunks ahead, records one ahead) in flight while the
-//    current chunk is composited (the reference's CTA-wide fetch/compute lock-step spent ~half
-//    of its stall samples at the barrier);
-//  * per chunk each lane fetches ONE packed record (16B vector loads of 2 sectors, instead of the
-//    reference's five arrays), tests it against the warp's pixel block with an exact-conservative
-//    ellipse/rectangle test and a ballot yields the bitmap of entries worth compositing; the
-//    record is staged in a warp-private shared-memory slab and broadcast-read in the pixel loop;
+//    AUTONOMOUSLY: no CTA barrier, per-warp early termination (the reference's CTA-wide
+//    fetch/compute lock-step spent ~half of its stall samples at the barrier);
+//  * stream compaction instead of per-warp culling: block_mask_kernel leaves one pre-filter byte
+//    per (tile, Gaussian) instance; a warp streams the bytes 128 instances per step, compacts the
+//    positions whose bit for ITS block is set into a circular queue and composites batches of 32
+//    queued entries (id -> packed record prefetched one batch ahead, staged in a warp-private
+//    shared-memory slab, exact ellipse / block test once per entry by the lane that staged it);
+//  * the kernel is bound by per-warp latency and by its heaviest warps, not by issue slots
+//    (profiles/r02_warp_timing.md): entries are composited in rounds of U whose alpha evaluations
+//    are in flight together, the sequential part is branch-free (predicated FMAs);
 //  * accumulators live in registers (template on the number of float4 channel groups) — the
 //    reference's runtime-indexed F[33] spills to local memory;
-//  * out_weights: one atomic per (warp, Gaussian) after a single integer REDUX instead of one per
-//    (pixel, Gaussian);
+//  * out_weights: one atomic instruction per (warp, batch) after one integer REDUX per entry
+//    instead of one atomic per (pixel, Gaussian);
+//  * for the backward pass the warp leaves one contributor bit per (instance, block) and, per
+//    half-tile CTA, the number of entries its busiest warp composited (the backward launch order);
 //  * per-pixel arithmetic keeps the association of the reference binary, so n_contrib and the
 //    images are bit-identical to it for identical lists.
 #include <cstdlib>

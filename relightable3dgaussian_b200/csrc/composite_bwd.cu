@@ -9,9 +9,12 @@
 //    all  (alpha T) * dL_dpix[c] : each lane keeps its dL_dpix in a lane-specific PERMUTED order,
 //    so that what a lane sends and what it keeps at every butterfly level sit in fixed registers —
 //    no select instructions (reduce_scatter_permuted); only the 7 geometry components pay them;
-//  * warps are autonomous (no CTA barrier; see composite.cu): each starts at ITS pixel block's
-//    largest n_contrib instead of the end of the tile list — entries behind every pixel's last
-//    contributor are never loaded — and skips entries its block cannot see via touch_block();
+//  * warps are autonomous (no CTA barrier; see composite.cu): each walks ONLY the entries whose
+//    contributor bit the forward pass set for its pixel block, back to front from the block's
+//    deepest last contributor — no culling test, no record fetch, no exp() for anything else;
+//  * CTAs are launched in the order of the work the forward pass measured (cta_order_kernel), and
+//    the walk is laid out in rounds of U entries for instruction-level parallelism: the kernel is
+//    bound by per-warp latency and its heaviest warps (profiles/r02_warp_timing.md);
 //  * per-pixel state is register resident (template on channel groups); the reference keeps three
 //    float[24] arrays in local memory and 36 KB of shared memory per CTA;
 //  * gradients differ from the reference only by fp32 summation order (the reference's own
