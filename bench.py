@@ -39,7 +39,7 @@ sys.path.insert(0, ROOT)
 
 HEADLINE = dict(P=1_000_000, W=800, H=800, S=5, views=8, recipe="shell-v1", seed=0)
 # DRAM bytes per launch of the compositors at the headline config, from ncu --set full (profiles/)
-NCU_TRAFFIC = {"composite_bwd": 63920896 + 1852928, "composite_fwd": 48885504 + 4542976}
+NCU_TRAFFIC = {"composite_bwd": 63854848 + 1705728, "composite_fwd": 48878592 + 4990208}
 STAGES = ["project", "depth_sort", "bin_count", "bin_offsets", "bin_scatter", "composite_fwd",   # bin_scatter includes tile_order + block_mask
           "surface_normal", "composite_bwd", "project_bwd"]
 
